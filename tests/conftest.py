@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_oracle():
+    """The oracle's C shim must exist (built by `make -C oracle` / __graft_entry__.build())."""
+    so = os.path.join(ROOT, "oracle", "_build", "libsicmath.so")
+    if not os.path.isfile(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    yield
