@@ -1,0 +1,190 @@
+/* safeincave_cuda.h — C ABI of libsafeincave_cuda.so (hand-written FP64 CUDA for sm_100a).
+ *
+ * Drop-in boundary for SafeInCave's per-time-step mechanics hot path.  The reference has NO
+ * FFI of its own (it is pure Python over DOLFINx/PETSc/torch-CPU); each entry
+ * point below replaces the Python method(s) cited next to it.  All citations are relative to
+ * the reference checkout (safeincave/...).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; sic_last_error() gives the message
+ *     (thread-local).
+ *   - the CALLER owns every buffer (the Python host allocates them as torch CUDA tensors and
+ *     passes data_ptr()); the library borrows the pointers for the duration of a call and
+ *     enqueues work on the caller's cudaStream_t (passed as void*).  No hidden allocation.
+ *   - all floating point is IEEE double.  Tensors are symmetric 3x3 stored as 6 Voigt
+ *     components in the reference's order [xx, yy, zz, xy, xz, yz] with TENSORIAL shear
+ *     (Utils.py:171-227, 251-283).
+ *   - per-cell arrays are SoA: component c of cell i lives at a[c*cell_stride + i]
+ *     (cell_stride >= n_cells, multiple of 32).  6x6 tangents are 36 rows, row-major (r*6+c).
+ *   - nodal vectors (u, b, x, y ...) are interleaved: dof = 3*node + component, as in the
+ *     reference's vector P1 space (MomentumEquation.py:219).
+ */
+#ifndef SAFEINCAVE_CUDA_H_
+#define SAFEINCAVE_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIC_ABI_VERSION 1
+#define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
+#define SIC_MAX_THERMO 4
+
+/* non-elastic element kinds (MaterialProps.py classes) */
+enum {
+  SIC_ELEM_KELVIN = 1,       /* Viscoelastic          :795-885   params: eta, c11, c12, c44 (C1) */
+  SIC_ELEM_DISLOCATION = 2,  /* DislocationCreep      :890-961   params: A, Q, n */
+  SIC_ELEM_PRESSURE_SOL = 3, /* PressureSolutionCreep :964-1034  params: A, d, Q */
+  SIC_ELEM_DESAI = 4         /* ViscoplasticDesai     :1037-1562 params: mu_1,N_1,a_1,eta,n,beta_1,beta,m,gamma,sigma_t */
+};
+
+/* rows of the per-cell Desai state block [SIC_DESAI_ROWS][cell_stride] */
+enum {
+  SIC_DS_ALPHA = 0, SIC_DS_ALPHA0 = 1, SIC_DS_QSI = 2, SIC_DS_QSI_OLD = 3, SIC_DS_FVP = 4,
+  SIC_DS_R = 5, SIC_DS_H = 6, SIC_DS_HSMALL = 7, SIC_DS_P = 8 /* ..13 */,
+  SIC_DS_ALPHA_K = 14, SIC_DS_Q = 15 /* ..20 */, SIC_DESAI_ROWS = 21
+};
+
+/* flags of sic_post() */
+enum {
+  SIC_POST_STRAIN = 1,     /* eps = sym grad u            (compute_total_strain, MomentumEquation.py:326-341) */
+  SIC_POST_STRESS = 2,     /* sig = CT:(eps - eps_rhs)    (compute_stress :844-866 / compute_elastic_stress :822-842) */
+  SIC_POST_INCREMENT = 4,  /* increment_internal_variables (:428-443, MaterialProps.py:1129-1158) */
+  SIC_POST_RATES = 8,      /* compute_eps_ne_rate          (:379-395) */
+  SIC_POST_ERROR = 16      /* ||eps_k-eps||^2, ||eps||^2   (Simulators.py:433-435) */
+};
+
+typedef struct {
+  int32_t kind;        /* SIC_ELEM_* */
+  int32_t param_off;   /* offset of this element's parameters inside a material-table row */
+  double* eps_old;     /* [6][cell_stride]  eps_ne_old       */
+  double* rate_old;    /* [6][cell_stride]  eps_ne_rate_old  */
+  double* rate;        /* [6][cell_stride]  eps_ne_rate      */
+  double* eps_k;       /* [6][cell_stride]  eps_ne_k         */
+  double* desai;       /* [SIC_DESAI_ROWS][cell_stride] or NULL */
+} sic_elem_t;
+
+/* Everything a constitutive / assembly kernel needs.  Filled by the host, passed by pointer. */
+typedef struct {
+  int32_t abi_version;
+  int32_t n_cells, cell_stride, n_nodes;
+  /* mesh (P1 tets): connectivity and the constant shape-function gradients per cell */
+  const int32_t* conn;   /* [4][cell_stride] node ids */
+  const double* grad;    /* [12][cell_stride] d(phi_a)/dx_j at row 3*a+j */
+  const double* vol;     /* [cell_stride] */
+  /* material: deduplicated parameter rows + per-cell row index */
+  const int32_t* mat_id;     /* [cell_stride] */
+  const double* mat_table;   /* [n_rows][row_len] */
+  int32_t n_rows, row_len;
+  int32_t spring_off;        /* row offset of c11,c12,c44 (C) and ci11,ci12,ci44 (C_inv) */
+  int32_t n_thermo;          /* Thermoelastic elements (MaterialProps.py:333-382) */
+  int32_t thermo_off;        /* row offset of their alpha_th values */
+  int32_t n_elems;           /* non-elastic elements */
+  sic_elem_t elems[SIC_MAX_ELEMS];
+  const double* T;           /* [cell_stride] current temperature  (set_T)  */
+  const double* T0;          /* [cell_stride] reference temperature (set_T0) */
+  /* per-cell fields */
+  double* sig;      /* [6][cell_stride] stress of this iteration          */
+  double* sig_k;    /* [6][cell_stride] stress of the previous iteration  */
+  double* eps;      /* [6][cell_stride] total strain                      */
+  double* eps_prev; /* [6][cell_stride] total strain of previous iteration*/
+  double* CT;       /* [36][cell_stride] consistent tangent               */
+  double* eps_rhs;  /* [6][cell_stride]                                   */
+  int32_t* n_singular; /* device counter: cells whose tangent was singular (elastic fallback) */
+} sic_problem_t;
+
+const char* sic_last_error(void);
+int sic_abi_version(void);
+int sic_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- part (1): constitutive update ------------------------------------------------------- */
+
+/* LinearMomentum.compute_CT + compute_eps_rhs (MomentumEquation.py:799-820, 868-890):
+ * per cell, G = sum G_i, B = sum B_i (Material.compute_G_B, MaterialProps.py:172-200; FD tangent
+ * :640-675; Desai :1432-1562; Kelvin :861-885), CT = inv(C_inv + dt(1-theta)G) (:273-309, singular
+ * -> elastic fallback), eps_ne_k_i (:586-605), eps_th (:365-382), eps_rhs.  Reads sig_k. */
+int sic_tangent(const sic_problem_t* p, double dt, double theta, void* stream);
+
+/* CT <- C, eps_rhs <- 0: the operator of solve_elastic_response (MomentumEquation.py:892-923). */
+int sic_elastic_tangent(const sic_problem_t* p, void* stream);
+
+/* Post-solve phase of one Newton iteration (Simulators.py:416-436), selected by flags.
+ *   u            nodal displacement [3*n_nodes] (may be NULL without SIC_POST_STRAIN)
+ *   kelvin_phi2  dt(1-theta) of the LAST tangent phase, <0 if none has run yet (then the Kelvin G
+ *                is still zero)
+ *   err_out      device double[2]: sum (eps_prev-eps)^2 and sum eps^2 over all 9 tensor entries
+ *   err_scratch  device double[2*n_blocks] with n_blocks = sic_post_blocks(n_cells)            */
+int sic_post(const sic_problem_t* p, const double* u, double dt, double theta, double kelvin_phi2,
+             int flags, double* err_out, double* err_scratch, void* stream);
+int sic_post_blocks(int n_cells);
+
+/* Commit of a converged step (Simulators.py:509-517): update_internal_variables
+ * (MaterialProps.py:1119-1127), update_eps_ne_rate_old (:630-638), update_eps_ne_old (:607-628).
+ * The per-element G_i, B_i of the last tangent phase are RE-EVALUATED from sig_k (and the saved
+ * Desai alpha_k, Q, P, h, r) instead of being stored (36 doubles per element per cell). */
+int sic_commit(const sic_problem_t* p, double dt, double theta, void* stream);
+
+/* update_eps_ne_rate_old alone (Simulators.py:365). */
+int sic_commit_rates(const sic_problem_t* p, void* stream);
+
+/* ViscoplasticDesai.compute_initial_hardening (MaterialProps.py:1248-1288) for element `elem`,
+ * from the stress in p->sig.  n_clamped (device int) counts alpha_0 <= 1e-6 cells. */
+int sic_desai_initial_hardening(const sic_problem_t* p, int elem, double Fvp_0, int32_t* n_clamped,
+                                void* stream);
+
+/* ---- part (2): matrix-free tangent / RHS "assembly" -------------------------------------- */
+
+/* y = K x with K = sum_e V_e B^T W CT_e B  (a(u,v) of MomentumEquation.py:1008-1011), rows and
+ * columns of constrained dofs treated as in assemble_matrix(bcs): fixed[dof] != 0 -> y[dof] = x[dof].
+ * x must already be zero on fixed dofs for the symmetric elimination to hold (the solvers do that). */
+int sic_apply(const sic_problem_t* p, const double* x, double* y, const uint8_t* fixed, void* stream);
+
+/* r = b_ext - sum_e V_e B^T W CT_e (B x0 - eps_rhs_e), then r[fixed] = 0:
+ * linear form of MomentumEquation.py:1014-1020 (b_rhs + body + Neumann) with apply_lifting/set_bc. */
+int sic_residual0(const sic_problem_t* p, const double* b_ext, const double* x0, double* r,
+                  const uint8_t* fixed, void* stream);
+
+/* nodal 3x3 diagonal blocks of K, inverted, fixed dofs decoupled: dinv[9*node..] (block Jacobi) */
+int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint8_t* fixed, void* stream);
+
+/* Neumann load of MomentumBC.py:247-277: b[3*node+c] += int_F (p_bc + rho_bc g_bc (H_bc - x_dir)) n_c phi ds.
+ *   tri      [3][n_tri] node ids;  area_n [3][n_tri] outward normal * area;  bc_of_tri [n_tri] -> bc or -1
+ *   bc_par   [n_bc][4] = {p(t) (already negated as in :275), rho*g, H, direction}                     */
+int sic_neumann(int n_tri, const int32_t* tri, const double* area_n, const int32_t* bc_of_tri,
+                const double* coords, int n_bc, const double* bc_par, double* b, void* stream);
+
+/* ---- part (3): Krylov solve ---------------------------------------------------------------- */
+enum { SIC_KSP_CG = 1, SIC_KSP_BICGSTAB = 2 };
+
+typedef struct {
+  int32_t method;         /* SIC_KSP_* */
+  int32_t max_it;
+  double rtol;            /* on ||r||_2 / ||r0||_2, r0 = b - K x0 restricted to free dofs */
+  double atol;
+  int32_t check_every;    /* host looks at the residual every this many iterations */
+  int32_t use_graph;      /* capture check_every iterations into one CUDA graph */
+  /* results */
+  int32_t iterations;
+  int32_t reason;         /* >0 converged (2 rtol, 3 atol), <0 diverged (-3 max_it, -9 nan) as PETSc */
+  double rnorm, rnorm0;
+} sic_ksp_t;
+
+/* Workspace: sic_ksp_workspace_doubles(n_nodes, method) doubles, caller-allocated. */
+int64_t sic_ksp_workspace_doubles(int n_nodes, int method);
+
+/* Solve K u = b for the free dofs with u = x (in: initial guess incl. prescribed values on fixed
+ * dofs; out: solution).  Replaces solver.solve of MomentumEquation.py:1023-1025 / 920-922.
+ * dinv: block-Jacobi blocks from sic_block_jacobi. */
+int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
+                  const uint8_t* fixed, const double* dinv, double* work, void* stream);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* dependent-free DFMA chains; returns achieved FLOP/s in *flops (used to record the FP64 peak) */
+int sic_fp64_peak(double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFEINCAVE_CUDA_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libsafeincave_cuda.so (see include/safeincave_cuda.h).
+
+There is NO fallback: if the CUDA library is missing, or an entry point returns an error, an
+exception is raised.  The CPU oracle under ``oracle/`` is test infrastructure and is never
+imported from here.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsafeincave_cuda.so")
+
+SIC_ABI_VERSION = 1
+SIC_MAX_ELEMS = 8
+SIC_MAX_THERMO = 4
+
+ELEM_KELVIN, ELEM_DISLOCATION, ELEM_PRESSURE_SOL, ELEM_DESAI = 1, 2, 3, 4
+DS_ALPHA, DS_ALPHA0, DS_QSI, DS_QSI_OLD, DS_FVP, DS_R, DS_H, DS_HSMALL, DS_P, DS_ALPHA_K, DS_Q = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15)
+DESAI_ROWS = 21
+POST_STRAIN, POST_STRESS, POST_INCREMENT, POST_RATES, POST_ERROR = 1, 2, 4, 8, 16
+KSP_CG, KSP_BICGSTAB = 1, 2
+
+# every symbol include/safeincave_cuda.h declares
+EXPORTS = (
+    "sic_last_error", "sic_abi_version", "sic_device_info", "sic_tangent", "sic_elastic_tangent",
+    "sic_post", "sic_post_blocks", "sic_commit", "sic_commit_rates", "sic_desai_initial_hardening",
+    "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
+    "sic_ksp_solve", "sic_fp64_peak",
+)
+
+
+class SicElem(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("param_off", c_int32), ("eps_old", c_void_p), ("rate_old", c_void_p),
+                ("rate", c_void_p), ("eps_k", c_void_p), ("desai", c_void_p)]
+
+
+class SicProblem(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", c_int32), ("n_cells", c_int32), ("cell_stride", c_int32), ("n_nodes", c_int32),
+        ("conn", c_void_p), ("grad", c_void_p), ("vol", c_void_p),
+        ("mat_id", c_void_p), ("mat_table", c_void_p), ("n_rows", c_int32), ("row_len", c_int32),
+        ("spring_off", c_int32), ("n_thermo", c_int32), ("thermo_off", c_int32), ("n_elems", c_int32),
+        ("elems", SicElem * SIC_MAX_ELEMS),
+        ("T", c_void_p), ("T0", c_void_p),
+        ("sig", c_void_p), ("sig_k", c_void_p), ("eps", c_void_p), ("eps_prev", c_void_p),
+        ("CT", c_void_p), ("eps_rhs", c_void_p), ("n_singular", c_void_p),
+    ]
+
+
+class SicKsp(ctypes.Structure):
+    _fields_ = [("method", c_int32), ("max_it", c_int32), ("rtol", c_double), ("atol", c_double),
+                ("check_every", c_int32), ("use_graph", c_int32), ("iterations", c_int32), ("reason", c_int32),
+                ("rnorm", c_double), ("rnorm0", c_double)]
+
+
+class SicError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SicError(
+            f"{LIB_PATH} not found: build it with `python -m safeincave_b200.build` "
+            "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTS if not hasattr(lib, s)]
+    if missing:
+        raise SicError(f"libsafeincave_cuda.so lacks symbols {missing}")
+    lib.sic_last_error.restype = c_char_p
+    lib.sic_abi_version.restype = c_int
+    if lib.sic_abi_version() != SIC_ABI_VERSION:
+        raise SicError("libsafeincave_cuda.so ABI version mismatch; rebuild")
+    PP = POINTER(SicProblem)
+    lib.sic_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.sic_tangent.argtypes = [PP, c_double, c_double, c_void_p]
+    lib.sic_elastic_tangent.argtypes = [PP, c_void_p]
+    lib.sic_post.argtypes = [PP, c_void_p, c_double, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]
+    lib.sic_post_blocks.argtypes = [c_int]
+    lib.sic_commit.argtypes = [PP, c_double, c_double, c_void_p]
+    lib.sic_commit_rates.argtypes = [PP, c_void_p]
+    lib.sic_desai_initial_hardening.argtypes = [PP, c_int, c_double, c_void_p, c_void_p]
+    lib.sic_apply.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sic_residual0.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sic_block_jacobi.argtypes = [PP, c_void_p, c_void_p, c_void_p]
+    lib.sic_neumann.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
+    lib.sic_ksp_workspace_doubles.restype = c_int64
+    lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sic_last_error().decode(errors="replace")
+        raise SicError(f"{what} failed ({rc}): {msg}")

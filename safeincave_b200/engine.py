@@ -1,0 +1,243 @@
+"""Device-side state of the mechanics hot path and thin wrappers over the C ABI.
+
+``Engine`` owns every device buffer (as torch CUDA tensors: PyTorch is used for allocation,
+stream handling and host<->device copies only) and fills the ``sic_problem_t`` the CUDA library
+borrows raw pointers from.  No arithmetic of the hot path happens here.
+
+Layouts (see include/safeincave_cuda.h): per-cell fields are SoA ``(rows, cell_stride)`` with
+Voigt order [xx,yy,zz,xy,xz,yz]; nodal vectors are ``(n_nodes, 3)`` contiguous (dof = 3*node+c).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def tet_geometry(coords: torch.Tensor, cells: torch.Tensor):
+    """Constant P1 shape-function gradients (N,4,3) and volumes (N,) of tetrahedra.
+    vol = |det|/6 as in Grid.py:115-137; grad(lambda_1) = (e2 x e3)/det etc."""
+    x0, x1, x2, x3 = (coords[cells[:, a]] for a in range(4))
+    e1, e2, e3 = x1 - x0, x2 - x0, x3 - x0
+    c23 = torch.linalg.cross(e2, e3)
+    c31 = torch.linalg.cross(e3, e1)
+    c12 = torch.linalg.cross(e1, e2)
+    det = (e1 * c23).sum(dim=1)
+    g1, g2, g3 = c23 / det[:, None], c31 / det[:, None], c12 / det[:, None]
+    g0 = -(g1 + g2 + g3)
+    grad = torch.stack([g0, g1, g2, g3], dim=1)
+    return grad, det.abs() / 6.0
+
+
+@dataclass
+class ElemSpec:
+    kind: int          # L.ELEM_*
+    param_off: int     # offset inside a material-table row
+
+
+class ElemState:
+    """Device state of one non-elastic element (MaterialProps.py:567-574, 1089-1092)."""
+
+    def __init__(self, kind, ns, device):
+        z = lambda rows: torch.zeros((rows, ns), dtype=torch.float64, device=device)
+        self.kind = kind
+        self.eps_old, self.rate_old, self.rate, self.eps_k = z(6), z(6), z(6), z(6)
+        self.desai = z(L.DESAI_ROWS) if kind == L.ELEM_DESAI else None
+        if self.desai is not None:
+            self.desai[L.DS_H].fill_(1.0)
+
+    SNAP = ("rate", "rate_old", "eps_old", "eps_k")
+
+    def snapshot(self):
+        """save_internal_state, MomentumEquation.py:456-477 (alpha, qsi, qsi_old, Fvp for Desai)."""
+        snap = {k: getattr(self, k).clone() for k in self.SNAP}
+        if self.desai is not None:
+            snap["desai"] = self.desai[[L.DS_ALPHA, L.DS_QSI, L.DS_QSI_OLD, L.DS_FVP]].clone()
+        return snap
+
+    def restore(self, snap):
+        for k in self.SNAP:
+            getattr(self, k).copy_(snap[k])
+        if self.desai is not None:
+            self.desai[[L.DS_ALPHA, L.DS_QSI, L.DS_QSI_OLD, L.DS_FVP]] = snap["desai"]
+
+
+class Engine:
+    def __init__(self, coords, cells, device="cuda"):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.SicError("safeincave_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        coords = torch.as_tensor(coords, dtype=torch.float64).to(self.device).contiguous()
+        cells = torch.as_tensor(cells).to(self.device, dtype=torch.int64).contiguous()
+        self.N, self.M = int(cells.shape[0]), int(coords.shape[0])
+        self.ns = max(32, (self.N + 31) // 32 * 32)
+        self.coords = coords
+        grad, vol = tet_geometry(coords, cells)
+        # orientation does not matter for P1 gradients; degenerate cells are a mesh error
+        if self.N and not bool(torch.isfinite(grad).all()):
+            raise ValueError("degenerate tetrahedron (zero volume) in mesh")
+        ns, dev = self.ns, self.device
+        self.conn = torch.zeros((4, ns), dtype=torch.int32, device=dev)
+        self.conn[:, :self.N] = cells.t().to(torch.int32)
+        self.grad = torch.zeros((12, ns), dtype=torch.float64, device=dev)
+        self.grad[:, :self.N] = grad.reshape(self.N, 12).t()
+        self.vol = torch.zeros(ns, dtype=torch.float64, device=dev)
+        self.vol[:self.N] = vol
+        z = lambda rows: torch.zeros((rows, ns), dtype=torch.float64, device=dev)
+        self.sig, self.sig_k, self.eps, self.eps_prev = z(6), z(6), z(6), z(6)
+        self.CT, self.eps_rhs = z(36), z(6)
+        self.T = torch.zeros(ns, dtype=torch.float64, device=dev)     # MomentumEquation.py:116-117
+        self.T0 = torch.zeros(ns, dtype=torch.float64, device=dev)
+        self.n_singular = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_clamped = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err_out = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.err_scratch = torch.zeros(2 * max(1, self.lib.sic_post_blocks(self.N)), dtype=torch.float64, device=dev)
+        self.mat_id = torch.zeros(ns, dtype=torch.int32, device=dev)
+        self.mat_table = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+        self.spring_off, self.thermo_off, self.n_thermo = 0, 6, 0
+        self.elems: list[ElemState] = []
+        self.elem_specs: list[ElemSpec] = []
+        self._ksp_work = {}
+        self._prob = None
+        self.launches = 0   # kernels launched through this engine (bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------ material
+    def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False):
+        table = torch.as_tensor(np.ascontiguousarray(table), dtype=torch.float64)
+        self.mat_table = table.to(self.device).contiguous()
+        mid = torch.as_tensor(mat_id).to(self.device, dtype=torch.int32)
+        self.mat_id.zero_()
+        self.mat_id[:self.N] = mid
+        self.spring_off, self.thermo_off, self.n_thermo = int(spring_off), int(thermo_off), int(n_thermo)
+        if len(elem_specs) > L.SIC_MAX_ELEMS:
+            raise L.SicError(f"at most {L.SIC_MAX_ELEMS} non-elastic elements are supported")
+        if not keep_state or len(elem_specs) != len(self.elems):
+            self.elems = [ElemState(s.kind, self.ns, self.device) for s in elem_specs]
+        self.elem_specs = list(elem_specs)
+        self._prob = None
+
+    def problem(self) -> L.SicProblem:
+        if self._prob is not None:
+            return self._prob
+        P = L.SicProblem()
+        P.abi_version = L.SIC_ABI_VERSION
+        P.n_cells, P.cell_stride, P.n_nodes = self.N, self.ns, self.M
+        P.conn, P.grad, P.vol = _ptr(self.conn), _ptr(self.grad), _ptr(self.vol)
+        P.mat_id, P.mat_table = _ptr(self.mat_id), _ptr(self.mat_table)
+        P.n_rows, P.row_len = int(self.mat_table.shape[0]), int(self.mat_table.shape[1])
+        P.spring_off, P.n_thermo, P.thermo_off = self.spring_off, self.n_thermo, self.thermo_off
+        P.n_elems = len(self.elems)
+        for i, (st, sp) in enumerate(zip(self.elems, self.elem_specs)):
+            e = P.elems[i]
+            e.kind, e.param_off = sp.kind, sp.param_off
+            e.eps_old, e.rate_old, e.rate, e.eps_k = _ptr(st.eps_old), _ptr(st.rate_old), _ptr(st.rate), _ptr(st.eps_k)
+            e.desai = _ptr(st.desai)
+        P.T, P.T0 = _ptr(self.T), _ptr(self.T0)
+        P.sig, P.sig_k, P.eps, P.eps_prev = _ptr(self.sig), _ptr(self.sig_k), _ptr(self.eps), _ptr(self.eps_prev)
+        P.CT, P.eps_rhs = _ptr(self.CT), _ptr(self.eps_rhs)
+        P.n_singular = _ptr(self.n_singular)
+        self._prob = P
+        return P
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _pp(self):
+        return ctypes.byref(self.problem())
+
+    # ------------------------------------------------------------------ part (1)
+    def tangent(self, dt, theta):
+        L.check(self.lib.sic_tangent(self._pp(), float(dt), float(theta), self._stream()), "sic_tangent")
+        self.launches += 1
+
+    def elastic_tangent(self):
+        L.check(self.lib.sic_elastic_tangent(self._pp(), self._stream()), "sic_elastic_tangent")
+        self.launches += 1
+
+    def post(self, u, dt, theta, kelvin_phi2, flags):
+        up = _ptr(u) if u is not None else ctypes.c_void_p(0)
+        L.check(self.lib.sic_post(self._pp(), up, float(dt), float(theta), float(kelvin_phi2), int(flags),
+                                  _ptr(self.err_out), _ptr(self.err_scratch), self._stream()), "sic_post")
+        self.launches += 2 if (flags & L.POST_ERROR) else 1
+
+    def commit(self, dt, theta):
+        L.check(self.lib.sic_commit(self._pp(), float(dt), float(theta), self._stream()), "sic_commit")
+        self.launches += 1
+
+    def commit_rates(self):
+        L.check(self.lib.sic_commit_rates(self._pp(), self._stream()), "sic_commit_rates")
+        self.launches += 1
+
+    def desai_initial_hardening(self, elem, Fvp_0):
+        self.n_clamped.zero_()
+        L.check(self.lib.sic_desai_initial_hardening(self._pp(), int(elem), float(Fvp_0), _ptr(self.n_clamped),
+                                                     self._stream()), "sic_desai_initial_hardening")
+        self.launches += 1
+        return int(self.n_clamped.item())
+
+    # ------------------------------------------------------------------ part (2)
+    def apply(self, x, y, fixed):
+        L.check(self.lib.sic_apply(self._pp(), _ptr(x), _ptr(y), _ptr(fixed), self._stream()), "sic_apply")
+        self.launches += 2
+
+    def residual0(self, b_ext, x0, r, fixed):
+        L.check(self.lib.sic_residual0(self._pp(), _ptr(b_ext), _ptr(x0), _ptr(r), _ptr(fixed), self._stream()),
+                "sic_residual0")
+        self.launches += 2
+
+    def block_jacobi(self, dinv, fixed):
+        L.check(self.lib.sic_block_jacobi(self._pp(), _ptr(dinv), _ptr(fixed), self._stream()), "sic_block_jacobi")
+        self.launches += 2
+
+    def neumann(self, tri, area_n, bc_of_tri, bc_par, b):
+        n_tri = int(tri.shape[1])
+        n_bc = int(bc_par.shape[0])
+        L.check(self.lib.sic_neumann(n_tri, _ptr(tri), _ptr(area_n), _ptr(bc_of_tri), _ptr(self.coords), n_bc,
+                                     _ptr(bc_par), _ptr(b), self._stream()), "sic_neumann")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ part (3)
+    def ksp_solve(self, method, b_ext, x, fixed, dinv, rtol=1e-10, atol=0.0, max_it=10000, check_every=25):
+        key = method
+        need = int(self.lib.sic_ksp_workspace_doubles(self.M, method))
+        w = self._ksp_work.get(key)
+        if w is None or w.numel() < need:
+            w = torch.zeros(need, dtype=torch.float64, device=self.device)
+            self._ksp_work = {key: w}     # one workspace at a time
+        ksp = L.SicKsp()
+        ksp.method, ksp.max_it, ksp.rtol, ksp.atol = int(method), int(max_it), float(rtol), float(atol)
+        ksp.check_every, ksp.use_graph = int(check_every), 0
+        L.check(self.lib.sic_ksp_solve(self._pp(), ctypes.byref(ksp), _ptr(b_ext), _ptr(x), _ptr(fixed), _ptr(dinv),
+                                       _ptr(w), self._stream()), "sic_ksp_solve")
+        per_it = 3 if method == L.KSP_CG else 7
+        self.launches += 3 + per_it * int(ksp.iterations)
+        return ksp
+
+    def fp64_peak(self):
+        out = ctypes.c_double(0.0)
+        L.check(self.lib.sic_fp64_peak(ctypes.byref(out), self._stream()), "sic_fp64_peak")
+        return out.value
+
+    # ------------------------------------------------------------------ host <-> device helpers
+    def put6(self, dst, v6):
+        """(N,6) host/any array -> SoA (6, ns) device tensor."""
+        t = torch.as_tensor(np.ascontiguousarray(v6), dtype=torch.float64).to(self.device)
+        dst[:, :self.N] = t.t()
+
+    def get6(self, src):
+        return src[:, :self.N].t().contiguous().cpu().numpy()
+
+    def put1(self, dst, v):
+        dst[:self.N] = torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64).to(self.device)
+
+    def get1(self, src):
+        return src[:self.N].cpu().numpy()

@@ -127,7 +127,7 @@ def replay(g, mat, isolate=True):
     noise = oc.to_voigt(g["noise"])
     if bool(g["desai_init"]):
         for e in mat.elems:
-            if hasattr(e, "initial_hardening"):
+            if e.kind == "desai":
                 e.initial_hardening(sig, 0.0)
     mat.eval_rates(sig, 0.0 * theta, T)
     mat.commit_rates()
@@ -142,8 +142,9 @@ def replay(g, mat, isolate=True):
             else:
                 sig_k = sig.copy()
             CT, eps_rhs = mat.tangent_phase(sig_k, T, T0, dt, theta)
-            errs.setdefault("tan:G", []).append(err(mat.G, g[f"{tag}/G"]))
-            errs.setdefault("tan:B", []).append(err(mat.B, gold(g, f"{tag}/B"), ATOL["B"]))
+            if getattr(mat, "G", None) is not None:    # the CUDA path never materialises G, B
+                errs.setdefault("tan:G", []).append(err(mat.G, g[f"{tag}/G"]))
+                errs.setdefault("tan:B", []).append(err(mat.B, gold(g, f"{tag}/B"), ATOL["B"]))
             errs.setdefault("tan:CT", []).append(err(CT, g[f"{tag}/CT"]))
             errs.setdefault("tan:eps_rhs", []).append(err(eps_rhs, gold(g, f"{tag}/eps_rhs"), ATOL["eps_rhs"]))
             compare(mat, g, tag + "/tan", "tan", errs, ("eps_k", "qsi", "r", "h", "P"))
@@ -172,3 +173,54 @@ def replay(g, mat, isolate=True):
         compare(mat, g, f"s{step}/commit", "commit", errs, ("rate_old", "eps_old", "qsi_old"))
         prev = f"s{step}/commit"
     return {k: max(v) for k, v in errs.items()}
+
+
+def record(g, mat):
+    """Run ``mat`` free-running over the golden's load sequence (same procedure as
+    oracle/gen_golden.py) and return a record with the golden files' key layout, so that
+    ``replay(record(g, oracle), cuda, isolate=True)`` checks the CUDA path against the ORACLE phase
+    by phase on bit-identical inputs."""
+    rec = {k: v for k, v in g.items() if "/" not in k or k.startswith("param/")}
+    dt, theta = float(g["dt"]), float(g["theta"])
+    T, T0 = g["T"], g["T0"]
+    sig = oc.to_voigt(g["sig0"])
+    noise = oc.to_voigt(g["noise"])
+    C_inv = np.asarray(mat.C_inv)
+
+    def snap(tag):
+        for i, e in enumerate(mat.elems):
+            for f in STATE_FIELDS + ISV_FIELDS:
+                if hasattr(e, f):
+                    rec[f"{tag}/e{i}/{GOLD_NAME.get(f, f)}"] = np.array(getattr(e, f), dtype=np.float64)
+            if getattr(e, "G", None) is not None:
+                rec[f"{tag}/e{i}/G"] = np.array(e.G)
+                rec[f"{tag}/e{i}/B"] = np.array(e.B)
+
+    if bool(g["desai_init"]):
+        for e in mat.elems:
+            if e.kind == "desai":
+                e.initial_hardening(sig, 0.0)
+    mat.eval_rates(sig, 0.0 * theta, T)
+    mat.commit_rates()
+    snap("init")
+    for step in range(int(g["n_steps"])):
+        for it in range(int(g["n_iters"])):
+            tag = f"s{step}i{it}"
+            sig_k = sig.copy()
+            CT, eps_rhs = mat.tangent_phase(sig_k, T, T0, dt, theta)
+            rec[f"{tag}/sig_k"] = sig_k
+            rec[f"{tag}/CT"] = np.array(CT)
+            rec[f"{tag}/eps_rhs"] = np.array(eps_rhs)
+            if getattr(mat, "G", None) is not None:
+                rec[f"{tag}/G"] = np.array(mat.G)
+                rec[f"{tag}/B"] = np.array(mat.B)
+            snap(tag + "/tan")
+            scale = 1 + float(g["load_step"]) / (it + 1) * (1 + noise)
+            eps_tot = oc.ddot(C_inv, sig_k * scale) + rec[f"{tag}/eps_rhs"]
+            rec[f"{tag}/eps_tot"] = eps_tot
+            sig = np.array(mat.post_phase(eps_tot, sig_k, T, dt, theta))
+            rec[f"{tag}/sig"] = sig.copy()
+            snap(tag + "/post")
+        mat.commit(sig, sig_k, dt, theta)
+        snap(f"s{step}/commit")
+    return rec
