@@ -1,0 +1,324 @@
+"""``LinearMomentum`` with the method surface of the reference's safeincave/MomentumEquation.py
+(``LinearMomentumBase`` :36-701, ``LinearMomentum`` :707-1028), re-hosted on the device.
+
+Every method keeps its reference name, argument meaning and call order, but the work is
+done by the CUDA library through ``Engine``: there is no UFL form, no sparse matrix and no PETSc.
+Per-cell tensors that the reference passes around BY VALUE as CPU torch ``(N,3,3)`` tensors are
+``CellField`` handles to device buffers here; user hooks that need numbers call ``.to_tensor()``
+(or read ``mat.elems_ne[i].eps_ne_k`` etc., which pull lazily).
+
+User extension point 1 is kept: subclass, override ``initialize()`` / ``run_after_solve()``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as to
+
+from . import _lib as L
+from .engine import Engine
+from .MaterialProps import Material, tensor_to_voigt, voigt_to_tensor
+from .Solver import KSP
+
+
+class CellField:
+    """Handle to a per-cell symmetric-tensor field on the device, SoA ``(6, cell_stride)``."""
+
+    def __init__(self, engine: Engine, buf: to.Tensor):
+        self.engine, self.buf = engine, buf
+
+    def clone(self):
+        return CellField(self.engine, self.buf.clone())
+
+    def voigt(self):
+        """(N,6) float64 on the host."""
+        return self.buf[:, :self.engine.N].t().contiguous().cpu()
+
+    def to_tensor(self):
+        """(N,3,3) float64 on the host, the reference's currency."""
+        return voigt_to_tensor(self.voigt())
+
+    def numpy(self):
+        return self.to_tensor().numpy()
+
+    def __array__(self, dtype=None):
+        return self.numpy()
+
+
+class _DofArray:
+    """Minimal stand-in for ``dolfinx.fem.Function.x``: ``.array`` is a host copy."""
+
+    def __init__(self, getter):
+        self._getter = getter
+
+    @property
+    def array(self):
+        return self._getter()
+
+
+class _FunctionView:
+    def __init__(self, name, getter):
+        self.name = name
+        self.x = _DofArray(getter)
+
+
+class LinearMomentumBase:
+    pass
+
+
+class LinearMomentum(LinearMomentumBase):
+    def __init__(self, grid, theta: float, device="cuda"):
+        self.grid, self.theta = grid, float(theta)
+        self.engine = Engine(grid.tetmesh.coords, grid.tetmesh.cells, device=device)
+        eng = self.engine
+        self.n_elems, self.n_nodes = eng.N, eng.M
+        dev = eng.device
+        zn = lambda: to.zeros((eng.M, 3), dtype=to.float64, device=dev)
+        self.X = zn()                       # solution vector (displacement), dof = 3*node + c
+        self.b_body, self.b_neumann, self.b_ext = zn(), zn(), zn()
+        self.u_prescribed = zn().reshape(-1)
+        self.fixed = to.zeros(3 * eng.M, dtype=to.uint8, device=dev)
+        self.dinv = to.zeros((eng.M, 9), dtype=to.float64, device=dev)
+        self.solver: KSP | None = None
+        self.bc = None
+        self.mat: Material | None = None
+        self._kelvin_phi2 = -1.0            # dt(1-theta) of the last tangent phase
+        self._saved_state = None
+        self._elastic_tangent_live = False
+        self.ksp_log = []                   # (iterations, reason, rnorm) per linear solve
+        self.sig = CellField(eng, eng.sig)  # views that follow the engine's buffers
+        self.eps_tot = CellField(eng, eng.eps)
+        self._nodes_vol = None
+
+    # ------------------------------------------------------------------ configuration
+    def set_material(self, material: Material):
+        self.mat = material
+        material.bind(self.engine)
+        self.initialize()
+
+    def initialize(self):
+        """Hook (MomentumEquation.py:785-797).  The elastic tangent is read from the material
+        table on the device; nothing to copy."""
+        pass
+
+    def run_after_solve(self):
+        """Hook called after each linear solve (MomentumEquation.py:510-518)."""
+        pass
+
+    def set_T(self, T):
+        self.engine.T[:self.engine.N] = to.as_tensor(T).to(self.engine.device, dtype=to.float64)
+        self.Temp = T
+
+    def set_T0(self, T0):
+        self.engine.T0[:self.engine.N] = to.as_tensor(T0).to(self.engine.device, dtype=to.float64)
+        self.T0 = T0
+
+    def set_solver(self, solver):
+        if not hasattr(solver, "method"):
+            raise TypeError("set_solver expects safeincave_b200.Solver.KSP (the petsc4py facade)")
+        self.solver = solver
+
+    def set_boundary_conditions(self, bc):
+        self.bc = bc
+
+    def build_body_force(self, g):
+        """int rho g . v dx (MomentumEquation.py:255-275): rho_e g V_e / 4 per node of each cell."""
+        eng = self.engine
+        rho = to.as_tensor(self.mat.density).to(eng.device, dtype=to.float64)
+        w = rho * eng.vol[:eng.N] / 4.0
+        gv = to.tensor([float(c) for c in g], dtype=to.float64, device=eng.device)
+        self.b_body.zero_()
+        for a in range(4):
+            self.b_body.index_add_(0, eng.conn[a, :eng.N].long(), w[:, None] * gv[None, :])
+        to.add(self.b_body, self.b_neumann, out=self.b_ext)
+
+    # ------------------------------------------------------------------ fields
+    @property
+    def u(self):
+        return _FunctionView("u", lambda: self.X.reshape(-1).cpu().numpy())
+
+    def displacement(self):
+        """(n_nodes, 3) displacement on the device."""
+        return self.X
+
+    def _as_field(self, value, dst):
+        """Make sure the device buffer ``dst`` holds ``value`` (CellField or (N,3,3) tensor)."""
+        eng = self.engine
+        if isinstance(value, CellField):
+            if value.buf.data_ptr() != dst.data_ptr():
+                dst.copy_(value.buf)
+        elif value is not None:
+            v = to.as_tensor(value)
+            if v.ndim == 3:
+                v = tensor_to_voigt(v.double())
+            dst[:, :eng.N] = v.to(eng.device, dtype=to.float64).t()
+
+    # ------------------------------------------------------------------ linear solve
+    def _linear_solve(self):
+        eng, ksp = self.engine, self.solver
+        if ksp is None:
+            raise RuntimeError("no solver set (set_solver)")
+        if not ksp.initial_guess_nonzero:
+            self.X.zero_()                                   # PETSc default: zero initial guess
+        x = self.X.reshape(-1)
+        to.where(self.fixed.bool(), self.u_prescribed, x, out=x)
+        eng.block_jacobi(self.dinv, self.fixed)
+        rtol, atol, max_it = ksp.effective()
+        res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
+                            max_it=max_it, check_every=ksp.check_every)
+        ksp.record(res)
+        self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+        return res
+
+    def solve_elastic_response(self):
+        """MomentumEquation.py:892-923."""
+        self.engine.elastic_tangent()
+        self._elastic_tangent_live = True
+        self._linear_solve()
+
+    def solve(self, stress_k, t, dt):
+        """MomentumEquation.py:978-1028: tangent + eps_rhs, assemble, solve, run_after_solve."""
+        eng = self.engine
+        self._as_field(stress_k, eng.sig_k)
+        eng.tangent(dt, self.theta)                          # compute_CT + compute_eps_rhs
+        self._elastic_tangent_live = False
+        self._kelvin_phi2 = dt * (1.0 - self.theta)
+        self._linear_solve()
+        self.run_after_solve()
+
+    def compute_CT(self, stress_k, dt):
+        """MomentumEquation.py:799-820 (fused with compute_eps_rhs on the device)."""
+        self._as_field(stress_k, self.engine.sig_k)
+        self.engine.tangent(dt, self.theta)
+        self._elastic_tangent_live = False
+        self._kelvin_phi2 = dt * (1.0 - self.theta)
+
+    def compute_eps_rhs(self, dt, stress_k):
+        """MomentumEquation.py:868-890: produced by compute_CT's kernel; kept for API compatibility."""
+        return CellField(self.engine, self.engine.eps_rhs)
+
+    # ------------------------------------------------------------------ post-solve phase
+    def compute_total_strain(self):
+        """MomentumEquation.py:326-341."""
+        self.engine.post(self.X, 0.0, self.theta, self._kelvin_phi2, L.POST_STRAIN)
+        return CellField(self.engine, self.engine.eps)
+
+    def compute_elastic_stress(self, eps_e):
+        """MomentumEquation.py:822-842: sigma = C : eps."""
+        eng = self.engine
+        self._as_field(eps_e, eng.eps)
+        if not self._elastic_tangent_live:
+            eng.elastic_tangent()
+            self._elastic_tangent_live = True
+        eng.post(None, 0.0, self.theta, self._kelvin_phi2, L.POST_STRESS)
+        return CellField(eng, eng.sig)
+
+    def compute_stress(self, eps_tot, *_):
+        """MomentumEquation.py:844-866: sigma = C_T : (eps - eps_rhs)."""
+        eng = self.engine
+        self._as_field(eps_tot, eng.eps)
+        eng.post(None, 0.0, self.theta, self._kelvin_phi2, L.POST_STRESS)
+        return CellField(eng, eng.sig)
+
+    def increment_internal_variables(self, stress, stress_k, dt):
+        """MomentumEquation.py:428-443."""
+        eng = self.engine
+        self._as_field(stress, eng.sig)
+        self._as_field(stress_k, eng.sig_k)
+        eng.post(None, dt, self.theta, self._kelvin_phi2, L.POST_INCREMENT)
+
+    def compute_eps_ne_rate(self, stress, dt):
+        """MomentumEquation.py:379-395 (phi1 = dt*theta; Simulators.py:364 passes t here, T7)."""
+        eng = self.engine
+        self._as_field(stress, eng.sig)
+        eng.post(None, dt, self.theta, self._kelvin_phi2, L.POST_RATES)
+
+    def newton_post(self, dt, with_error=True):
+        """Fused post-solve phase of one Newton iteration (Simulators.py:416-436): strain, stress,
+        ISV increment, rates and the two sums of the convergence measure in ONE kernel.
+        Returns the error ||eps_k - eps|| / ||eps|| (or 0.0 if not requested)."""
+        eng = self.engine
+        flags = L.POST_STRAIN | L.POST_STRESS | L.POST_INCREMENT | L.POST_RATES
+        if with_error:
+            flags |= L.POST_ERROR
+        eng.post(self.X, dt, self.theta, self._kelvin_phi2, flags)
+        if not with_error:
+            return 0.0
+        num, den = eng.err_out.tolist()                      # device -> host read of the step result
+        if den == 0.0:
+            return float("nan") if num != 0.0 else 0.0
+        return float(np.sqrt(num) / np.sqrt(den))
+
+    def begin_iteration(self):
+        """eps_tot_k <- eps_tot, stress_k <- stress (Simulators.py:407-410) by swapping buffers."""
+        eng = self.engine
+        eng.sig, eng.sig_k = eng.sig_k, eng.sig
+        eng.eps, eng.eps_prev = eng.eps_prev, eng.eps
+        eng._prob = None
+        self.sig.buf, self.eps_tot.buf = eng.sig, eng.eps
+        # after the swap sig_k/eps_prev hold the current values; sig/eps are scratch until newton_post
+
+    def update_eps_ne_rate_old(self):
+        """MomentumEquation.py:397-406."""
+        self.engine.commit_rates()
+
+    def update_internal_variables(self):
+        """MomentumEquation.py:445-454 -- done by commit() together with the two updates below."""
+        self._pending_commit = True
+
+    def update_eps_ne_old(self, stress, stress_k, dt):
+        """MomentumEquation.py:408-426.  Runs the fused commit kernel (update_internal_variables,
+        update_eps_ne_rate_old and update_eps_ne_old, in the order of Simulators.py:509-517)."""
+        eng = self.engine
+        self._as_field(stress, eng.sig)
+        self._as_field(stress_k, eng.sig_k)
+        eng.commit(dt, self.theta)
+
+    def commit(self, dt):
+        self.engine.commit(dt, self.theta)
+
+    # ------------------------------------------------------------------ dt-retry snapshot
+    def save_internal_state(self):
+        """MomentumEquation.py:456-477."""
+        self._saved_state = [e.snapshot() for e in self.engine.elems]
+
+    def restore_internal_state(self):
+        """MomentumEquation.py:479-494."""
+        for e, s in zip(self.engine.elems, self._saved_state):
+            e.restore(s)
+
+    # ------------------------------------------------------------------ p / q output fields
+    def _pq(self):
+        eng = self.engine
+        s = eng.sig[:, :eng.N]
+        I1 = s[0] + s[1] + s[2]
+        I2 = s[0] * s[1] + s[1] * s[2] + s[0] * s[2] - s[3] ** 2 - s[4] ** 2 - s[5] ** 2
+        return I1 / 3.0, to.sqrt(3 * ((1 / 3) * I1 ** 2 - I2))
+
+    def _to_nodes(self, f):
+        """Volume-weighted node average (grid.A_csr, Grid.py:226-233)."""
+        eng = self.engine
+        vol = eng.vol[:eng.N]
+        if self._nodes_vol is None:
+            self._nodes_vol = to.zeros(eng.M, dtype=to.float64, device=eng.device)
+            for a in range(4):
+                self._nodes_vol.index_add_(0, eng.conn[a, :eng.N].long(), vol)
+        out = to.zeros(eng.M, dtype=to.float64, device=eng.device)
+        for a in range(4):
+            out.index_add_(0, eng.conn[a, :eng.N].long(), vol * f)
+        return out / self._nodes_vol
+
+    def _to_elems(self, fn):
+        eng = self.engine
+        return sum(fn[eng.conn[a, :eng.N].long()] for a in range(4)) / 4.0     # grid.B_csr, Grid.py:234-241
+
+    def compute_p_nodes(self):
+        self.p_nodes = self._to_nodes(self._pq()[0])
+
+    def compute_q_nodes(self):
+        self.q_nodes = self._to_nodes(self._pq()[1])
+
+    def compute_p_elems(self):
+        self.p_elems = self._to_elems(self._to_nodes(self._pq()[0]))
+
+    def compute_q_elems(self):
+        self.q_elems = self._to_elems(self._to_nodes(self._pq()[1]))

@@ -1,0 +1,140 @@
+"""``Simulator_M`` with the constructor / ``run()`` surface of the reference's
+safeincave/Simulators.py:273-541, re-hosted so that the loop body stays on the device.
+
+Loop structure, tolerances (1e-8, 40 iterations), the dt-halving retry (<= 3 cuts, T13: a retry keeps
+the step's target time and BC values), the NaN exit and the "commit only if converged" rule are the
+reference's.  What differs is where the data lives: ``eps_tot_k <- eps_tot`` / ``stress_k <- stress``
+are buffer swaps, the post-solve phase is one fused kernel, and the only per-iteration host traffic
+is the two doubles of the convergence measure.
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+
+
+class Simulator:
+    def run(self):
+        raise NotImplementedError
+
+
+class Simulator_M(Simulator):
+    def __init__(self, eq_mom, t_control, outputs, compute_elastic_response: bool = True, verbose: bool = True):
+        self.eq_mom = eq_mom
+        self.t_control = t_control
+        self.outputs = outputs if outputs is not None else []
+        self.compute_elastic_response = compute_elastic_response
+        self.verbose = verbose
+        self.tol, self.maxiter, self.max_dt_cuts = 1e-8, 40, 3
+        self.history = []        # one dict per time step: iterations, error, converged, ksp iterations, seconds
+        # optional callable(eq_mom, stress) run right after the initial stress is known and before the
+        # initial rates (where the reference's scripts call desai.compute_initial_hardening between stages)
+        self.after_initial_stress = None
+
+    # -- hook for benchmarking / tests
+    def on_step_end(self, record):
+        pass
+
+    def _print(self, *a):
+        if self.verbose and self.eq_mom.grid.mesh.comm.rank == 0:
+            print(*a)
+            sys.stdout.flush()
+
+    def initialize(self):
+        """Everything of run() before the time loop (Simulators.py:338-372)."""
+        eq, tc = self.eq_mom, self.t_control
+        for output in self.outputs:
+            output.initialize()
+        eq.bc.update_dirichlet(tc.t)
+        eq.bc.update_neumann(tc.t)
+        if self.compute_elastic_response:
+            eq.solve_elastic_response()
+            eps = eq.compute_total_strain()
+            stress = eq.compute_elastic_stress(eps)
+        else:
+            eq.compute_total_strain()
+            stress = eq.sig
+        if self.after_initial_stress is not None:
+            self.after_initial_stress(eq, stress)
+        eq.compute_eps_ne_rate(stress, tc.t)         # NB passes t, not dt (T7)
+        eq.update_eps_ne_rate_old()
+        self._save(0)
+
+    def _save(self, t):
+        if not self.outputs:
+            return
+        eq = self.eq_mom
+        eq.compute_p_elems()
+        eq.compute_q_elems()
+        eq.compute_p_nodes()
+        eq.compute_q_nodes()
+        for output in self.outputs:
+            output.save_fields(t)
+
+    def step(self):
+        """One pass of the time loop body (Simulators.py:378-536)."""
+        eq, tc = self.eq_mom, self.t_control
+        eng = eq.engine
+        t0 = time.perf_counter()
+        tc.advance_time()
+        t, dt = tc.t, tc.dt
+        sig_bak, eps_bak = eng.sig.clone(), eng.eps.clone()
+        eq.save_internal_state()
+        n_ne = len(eq.mat.elems_ne)
+        dt_current, dt_cut, converged = dt, 0, False
+        ite, error, ksp_its = 0, 0.0, 0
+        while not converged and dt_cut <= self.max_dt_cuts:
+            eq.bc.update_dirichlet(t)
+            eq.bc.update_neumann(t)
+            error, ite = 2 * self.tol, 0
+            while error > self.tol and ite < self.maxiter:
+                eq.begin_iteration()                       # eps_tot_k <- eps_tot ; stress_k <- stress
+                eq.solve(None, t, dt_current)
+                ksp_its += eq.ksp_log[-1][0]
+                want_err = not (eq.theta == 1.0 or n_ne == 0)
+                error = eq.newton_post(dt_current, with_error=want_err)
+                ite += 1
+                if np.isnan(error):
+                    break
+            if not np.isnan(error) and error <= self.tol:
+                converged = True
+            else:
+                dt_cut += 1
+                eng.sig.copy_(sig_bak)
+                eng.eps.copy_(eps_bak)
+                eq.restore_internal_state()
+                if dt_cut <= self.max_dt_cuts:
+                    print(f"[SOLVER] Step {tc.step_counter}: {'NaN' if np.isnan(error) else 'no convergence'} "
+                          f"after {ite} iters — halving dt ({dt_current / tc.time_conversion:.4f} -> "
+                          f"{dt_current / 2 / tc.time_conversion:.4f} hours), retry {dt_cut}/{self.max_dt_cuts}",
+                          file=sys.stderr)
+                    dt_current = dt_current / 2
+                else:
+                    eng.sig_k.copy_(sig_bak)
+                    print(f"[SOLVER] All {self.max_dt_cuts} retries failed at step {tc.step_counter} "
+                          f"(t={t / tc.time_conversion:.1f}h); state restored, step not committed", file=sys.stderr)
+        if converged:
+            eq.commit(dt_current)      # update_internal_variables; update_eps_ne_rate_old; update_eps_ne_old
+        rec = dict(step=tc.step_counter, t=t, dt=dt, dt_used=dt_current, iterations=ite, error=float(error),
+                   converged=converged, ksp_iterations=ksp_its, seconds=time.perf_counter() - t0)
+        self.history.append(rec)
+        self.on_step_end(rec)
+        return rec
+
+    def run(self):
+        tc = self.t_control
+        self.initialize()
+        if self.verbose:
+            self._print(f"{'step':>6} {'dt':>10} {'t / t_final':>24} {'iters':>6} {'error':>12} {'ksp its':>8}")
+        while tc.keep_looping():
+            rec = self.step()
+            self._save(rec["t"])
+            self._print(f"{rec['step']:>6d} {tc.dt / tc.time_conversion:>10.4f} "
+                        f"{rec['t'] / tc.time_conversion:>11.3f} / {tc.t_final / tc.time_conversion:<10.3f} "
+                        f"{rec['iterations']:>6d} {rec['error']:>12.4e} {rec['ksp_iterations']:>8d}")
+        for output in self.outputs:
+            if hasattr(output, "save_mesh"):
+                output.save_mesh()
+        return self.history

@@ -1,0 +1,104 @@
+"""Facade with the petsc4py.PETSc.KSP methods the reference's scripts touch:
+``KSP().create(comm)``, ``setType``, ``getPC().setType``, ``setTolerances``, ``getType``,
+``getPC().getType``, ``getTolerances``, ``setOperators``, ``getIterationNumber``,
+``getResidualNorm``, ``getConvergedReason``.  It only records the configuration; the solve itself
+is ``sic_ksp_solve`` (block-Jacobi CG / BiCGStab on the matrix-free operator):
+
+    cg                       -> SIC_KSP_CG
+    bicg, bcgs, gmres, ...   -> SIC_KSP_BICGSTAB   (non-symmetric tangents)
+    preonly (+ lu)           -> SIC_KSP_BICGSTAB with rtol 1e-13
+    any PC type              -> nodal 3x3 block Jacobi
+
+T10: the examples' max_it = 100 silently truncates PETSc solves on large meshes; here the solve runs
+to the requested rtol (``min_max_it``) unless ``respect_max_it`` is set.
+"""
+from . import _lib as L
+
+
+class PC:
+    def __init__(self):
+        self._type = "bjacobi"
+
+    def setType(self, t):
+        self._type = str(t)
+
+    def getType(self):
+        return self._type
+
+
+class KSP:
+    def __init__(self):
+        self._type = "cg"
+        self._pc = PC()
+        self.rtol, self.atol, self.divtol, self.max_it = 1e-5, 1e-50, 1e4, 10000
+        self.respect_max_it = False
+        self.min_max_it = 200000
+        self.check_every = 25
+        self.initial_guess_nonzero = False
+        self._its, self._rnorm, self._reason = 0, 0.0, 0
+        self.total_iterations = 0
+
+    def create(self, comm=None):
+        self.comm = comm
+        return self
+
+    def setType(self, t):
+        self._type = str(t)
+
+    def getType(self):
+        return self._type
+
+    def getPC(self):
+        return self._pc
+
+    def setTolerances(self, rtol=None, atol=None, divtol=None, max_it=None):
+        if rtol is not None:
+            self.rtol = float(rtol)
+        if atol is not None:
+            self.atol = float(atol)
+        if divtol is not None:
+            self.divtol = float(divtol)
+        if max_it is not None:
+            self.max_it = int(max_it)
+
+    def getTolerances(self):
+        return self.rtol, self.atol, self.divtol, self.max_it
+
+    def setInitialGuessNonzero(self, flag):
+        self.initial_guess_nonzero = bool(flag)
+
+    def setOperators(self, *a, **k):
+        pass
+
+    def setFromOptions(self):
+        pass
+
+    def getIterationNumber(self):
+        return self._its
+
+    def getResidualNorm(self):
+        return self._rnorm
+
+    def getConvergedReason(self):
+        return self._reason
+
+    # ---- used by LinearMomentum
+    def method(self):
+        return L.KSP_CG if self._type.lower() == "cg" else L.KSP_BICGSTAB
+
+    def effective(self):
+        rtol = 1e-13 if self._type.lower() == "preonly" else self.rtol
+        max_it = self.max_it if self.respect_max_it else max(self.max_it, self.min_max_it)
+        return rtol, max(self.atol, 0.0) if self.atol > 1e-40 else 0.0, max_it
+
+    def record(self, ksp):
+        self._its, self._rnorm, self._reason = int(ksp.iterations), float(ksp.rnorm), int(ksp.reason)
+        self.total_iterations += int(ksp.iterations)
+
+
+class _PETScNamespace:
+    """``from safeincave_b200.Solver import PETSc`` stands in for ``from petsc4py import PETSc``."""
+    KSP = KSP
+
+
+PETSc = _PETScNamespace()

@@ -7,3 +7,9 @@ __version__ = "0.1.0"
 
 from .MaterialProps import (Material, NonElasticElement, Spring, Thermoelastic, Viscoelastic,  # noqa: F401
                             DislocationCreep, PressureSolutionCreep, ViscoplasticDesai)
+from .Grid import GridHandlerGMSH  # noqa: F401
+from .MomentumEquation import LinearMomentumBase, LinearMomentum, CellField  # noqa: F401
+from .Simulators import Simulator_M  # noqa: F401
+from .TimeHandler import TimeControllerBase, TimeController, TimeControllerParabolic  # noqa: F401
+from .Solver import KSP, PETSc  # noqa: F401
+from . import MomentumBC, Utils  # noqa: F401

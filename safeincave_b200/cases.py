@@ -1,0 +1,145 @@
+"""The BASELINE.json configurations as plain data + a builder for the device-side objects.
+
+A case is a dict (no torch / CUDA objects) so that tests can build the CPU oracle from the very
+same numbers:
+
+    triaxial_case(grid)   config 1: unit-cube triaxial creep, Spring + Kelvin + DislocationCreep
+                          (+ Desai), loads / BCs of examples/mechanics/1_triaxial/main.py:36-147
+    cavern_case(grid)     configs 2/3/5: single-region cavern grid, cyclic gas pressure; BC pattern of
+                          examples/mechanics/nobian/Simulation/Run.py:1414-1430, materials of
+                          examples/mechanics/4_cavern/main.py:55-79, geothermal T (:90-97)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as to
+
+from . import MomentumBC as momBC
+from .Utils import GPa, MPa, day, hour
+
+DESAI_TRIAXIAL = dict(mu_1=5.3665857009859815e-11, N_1=3.1, a_1=1.965018496922832e-05,
+                      eta=0.8275682807874163, n=3.0, beta_1=0.0048, beta=0.995, m=-0.5,
+                      gamma=0.095, sigma_t=5.0, alpha_0=0.0022)         # 1_triaxial/main.py:78-89
+
+ELEMENT_LIBRARY = {
+    "kelvin": dict(kind="kelvin", eta=105e11, E=10 * GPa, nu=0.32),                    # 1_triaxial/main.py:66-69
+    "dislocation": dict(kind="dislocation", A=1.9e-20, Q=51600.0, n=3.0),              # :72-75
+    "pressure_solution": dict(kind="pressure_solution", A=1.29e-19, d=0.01, Q=13184.0),  # thermomechanics/2_cavern/main.py:82-87
+    "desai": dict(kind="desai", **DESAI_TRIAXIAL),
+}
+
+
+def triaxial_case(grid, elements=("kelvin", "dislocation"), n_steps=None):
+    t_final = 24 * hour
+    names = grid.get_boundary_names()
+    up = {n.upper(): n for n in names}
+    case = dict(
+        name="triaxial", theta=0.5, dt=0.5 * hour, t_final=t_final, time_unit="hour",
+        density=2000.0, g=[0.0, 0.0, 0.0], T=293.0,
+        spring=dict(E=102 * GPa, nu=0.3),
+        elements=[dict(ELEMENT_LIBRARY[e]) for e in elements],
+        dirichlet=[dict(boundary=up["WEST"], component=0, values=[0.0, 0.0], time_values=[0.0, t_final]),
+                   dict(boundary=up["BOTTOM"], component=2, values=[0.0, 0.0], time_values=[0.0, t_final]),
+                   dict(boundary=up["SOUTH"], component=1, values=[0.0, 0.0], time_values=[0.0, t_final])],
+        neumann=[dict(boundary=up["EAST"], direction=2, density=0.0, ref_pos=0.0, gravity=0.0,
+                      values=[4.0 * MPa, 4.0 * MPa], time_values=[0.0, t_final]),
+                 dict(boundary=up["NORTH"], direction=2, density=0.0, ref_pos=0.0, gravity=0.0,
+                      values=[4.0 * MPa, 4.0 * MPa], time_values=[0.0, t_final]),
+                 dict(boundary=up["TOP"], direction=2, density=0.0, ref_pos=0.0, gravity=0.0,
+                      values=[4.1 * MPa, 16 * MPa, 16 * MPa, 6 * MPa, 6 * MPa],
+                      time_values=[0 * hour, 2 * hour, 14 * hour, 16 * hour, 24 * hour])],
+        ksp=dict(type="bicg", rtol=1e-12), desai_initial_hardening=False,
+    )
+    if n_steps is not None:
+        case["t_final_run"] = n_steps * case["dt"]
+    return case
+
+
+def cavern_case(grid, elements=("dislocation",), theta=0.0, dt_hours=2.0, p_ref=17.5 * MPa, n_steps=None,
+                ksp_type="cg", rtol=1e-12):
+    x = grid.mesh.geometry.x
+    z_top = float(x[:, 2].max())
+    tm = grid.tetmesh
+    cav_tag = grid.get_boundary_tag("Cavern")
+    z_max = float(x[np.unique(tm.tris[tm.tri_tags == cav_tag]), 2].max())     # cavern roof
+    salt_density, gas_density, g = 2200.0, 0.082, -9.81
+    p_roof = p_ref + salt_density * abs(g) * (z_top - z_max)
+    t_final = 240 * hour
+    case = dict(
+        name="cavern", theta=theta, dt=dt_hours * hour, t_final=t_final, time_unit="hour",
+        density=salt_density, g=[0.0, 0.0, g],
+        T=dict(surface=293.0, gradient=27.0 / 1000.0, z_surface=z_top),           # 4_cavern/main.py:90-97
+        spring=dict(E=102 * GPa, nu=0.3),
+        elements=[dict(ELEMENT_LIBRARY[e]) for e in elements],
+        dirichlet=[dict(boundary="West", component=0, values=[0.0, 0.0], time_values=[0.0, t_final]),
+                   dict(boundary="Bottom", component=2, values=[0.0, 0.0], time_values=[0.0, t_final]),
+                   dict(boundary="South", component=1, values=[0.0, 0.0], time_values=[0.0, t_final])],
+        neumann=[dict(boundary="East", direction=2, density=salt_density, ref_pos=z_top, gravity=g,
+                      values=[p_ref, p_ref], time_values=[0.0, t_final]),
+                 dict(boundary="North", direction=2, density=salt_density, ref_pos=z_top, gravity=g,
+                      values=[p_ref, p_ref], time_values=[0.0, t_final]),
+                 dict(boundary="Top", direction=2, density=0.0, ref_pos=0.0, gravity=g,
+                      values=[p_ref, p_ref], time_values=[0.0, t_final]),
+                 dict(boundary="Cavern", direction=2, density=gas_density, ref_pos=z_max, gravity=g,
+                      values=[0.8 * p_roof, 0.2 * p_roof, 0.2 * p_roof, 0.8 * p_roof, 0.8 * p_roof],
+                      time_values=[0 * day, 2 * day, 6 * day, 8 * day, 10 * day])],
+        ksp=dict(type=ksp_type, rtol=rtol), desai_initial_hardening=("desai" in elements),
+    )
+    if n_steps is not None:
+        case["t_final_run"] = n_steps * case["dt"]
+    return case
+
+
+def cell_temperature(case, coords, cells):
+    """Per-cell temperature (N,) float64 numpy."""
+    T = case["T"]
+    if isinstance(T, dict):
+        zc = coords[cells][:, :, 2].mean(axis=1)
+        return T["surface"] + T["gradient"] * (T["z_surface"] - zc)
+    return np.full(cells.shape[0], float(T))
+
+
+def build(case, grid, verbose=False, outputs=None, device="cuda"):
+    """Instantiate LinearMomentum + Material + BCs + Simulator_M for a case on the GPU, the way the
+    reference's example scripts wire them."""
+    import safeincave_b200 as sf
+    n = grid.n_elems
+    one = to.ones(n, dtype=to.float64)
+    eq = sf.LinearMomentum(grid, theta=case["theta"], device=device)
+    ksp = sf.PETSc.KSP().create(grid.mesh.comm)
+    ksp.setType(case["ksp"]["type"])
+    ksp.getPC().setType("asm")
+    ksp.setTolerances(rtol=case["ksp"]["rtol"], max_it=case["ksp"].get("max_it", 100))
+    eq.set_solver(ksp)
+    mat = sf.Material(n)
+    mat.set_density(case["density"] * one)
+    mat.add_to_elastic(sf.Spring(case["spring"]["E"] * one, case["spring"]["nu"] * one, "spring"))
+    for e in case["elements"]:
+        k = e["kind"]
+        if k == "kelvin":
+            el = sf.Viscoelastic(e["eta"] * one, e["E"] * one, e["nu"] * one, "kelvin")
+        elif k == "dislocation":
+            el = sf.DislocationCreep(e["A"] * one, e["Q"] * one, e["n"] * one, "creep")
+        elif k == "pressure_solution":
+            el = sf.PressureSolutionCreep(e["A"] * one, e["d"] * one, e["Q"] * one, "pressure_solution")
+        elif k == "desai":
+            el = sf.ViscoplasticDesai(*[e[p] * one for p in sf.ViscoplasticDesai.param_names], e["alpha_0"] * one, "desai")
+        else:
+            raise ValueError(k)
+        mat.add_to_non_elastic(el)
+    eq.set_material(mat)
+    eq.build_body_force(case["g"])
+    T = to.tensor(cell_temperature(case, grid.tetmesh.coords, grid.tetmesh.cells), dtype=to.float64)
+    eq.set_T0(T)
+    eq.set_T(T)
+    bc = momBC.BcHandler(eq)
+    for d in case["dirichlet"]:
+        bc.add_boundary_condition(momBC.DirichletBC(d["boundary"], d["component"], d["values"], d["time_values"]))
+    for nb in case["neumann"]:
+        bc.add_boundary_condition(momBC.NeumannBC(nb["boundary"], nb["direction"], nb["density"], nb["ref_pos"],
+                                                  nb["values"], nb["time_values"], g=nb["gravity"]))
+    eq.set_boundary_conditions(bc)
+    t_final = case.get("t_final_run", case["t_final"])
+    tc = sf.TimeController(dt=case["dt"], initial_time=0.0, final_time=t_final, time_unit="second")
+    sim = sf.Simulator_M(eq, tc, outputs or [], compute_elastic_response=True, verbose=verbose)
+    return eq, sim

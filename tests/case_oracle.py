@@ -1,0 +1,43 @@
+"""Build the CPU oracle (OracleMaterial + OracleSimulatorM) from a safeincave_b200.cases dict."""
+import numpy as np
+
+from oracle import constitutive as oc
+from oracle import fem
+from safeincave_b200.cases import cell_temperature
+
+
+def oracle_material(case, n):
+    one = np.ones(n)
+    mat = oc.OracleMaterial(n)
+    mat.add_spring(case["spring"]["E"] * one, case["spring"]["nu"] * one)
+    for e in case["elements"]:
+        k = e["kind"]
+        if k == "kelvin":
+            mat.add(oc.Kelvin(e["eta"] * one, e["E"] * one, e["nu"] * one))
+        elif k == "dislocation":
+            mat.add(oc.Dislocation(e["A"] * one, e["Q"] * one, e["n"] * one))
+        elif k == "pressure_solution":
+            mat.add(oc.PressureSolution(e["A"] * one, e["d"] * one, e["Q"] * one))
+        elif k == "desai":
+            mat.add(oc.Desai(e["alpha_0"] * one, **{p: e[p] * one for p in oc.DesaiParams.names}))
+    return mat
+
+
+def oracle_simulator(case, tm):
+    n = tm.n_cells
+    mat = oracle_material(case, n)
+    T = cell_temperature(case, tm.coords, tm.cells)
+    tag = lambda name: tm.names[2][name]
+    dirichlet = [dict(tag=tag(d["boundary"]), component=d["component"], values=d["values"],
+                      time_values=d["time_values"]) for d in case["dirichlet"]]
+    neumann = [dict(tag=tag(b["boundary"]), direction=b["direction"], density=b["density"], ref_pos=b["ref_pos"],
+                    gravity=b["gravity"], values=b["values"], time_values=b["time_values"]) for b in case["neumann"]]
+    sim = fem.OracleSimulatorM(tm.coords, tm.cells, tm.tris, tm.tri_tags, mat, case["theta"], T, T,
+                               case["density"] * np.ones(n), case["g"], dirichlet, neumann)
+    if case.get("desai_initial_hardening"):
+        def hook(m, sig):
+            for e in m.elems:
+                if e.kind == "desai":
+                    e.initial_hardening(sig, 0.0)
+        sim.after_initial_stress = hook
+    return sim

@@ -1,0 +1,200 @@
+"""GPU parity tests of hot-path parts (2) assembly and (3) solve, and of the whole time step,
+through the C ABI, against oracle/fem.py (assembled CSR + sparse LU) on the reference's grids.
+
+Tolerances: operator / RHS / preconditioner blocks / loads 1e-12 (pure FP64 reassociation);
+linear solves 1e-9 against the direct solve; fields after N time steps <= 1e-8 relative
+(north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import constitutive as oc
+from oracle import fem
+from tests.case_oracle import oracle_simulator
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def sf():
+    import safeincave_b200 as sf
+    return sf
+
+
+def load_grid(sf, name, levels=0):
+    from safeincave_b200.mesh import TetMesh, red_refine
+    tm = TetMesh.load_npz(os.path.join(GOLD, f"mesh_{name}.npz"))
+    for _ in range(levels):
+        tm = red_refine(tm)
+    return sf.GridHandlerGMSH.from_mesh(tm)
+
+
+def random_tangent(n, seed, sym=False):
+    rng = np.random.default_rng(seed)
+    CT = oc.iso_matrix(102e9 * (1 + 0.3 * rng.random(n)), 0.3 * np.ones(n))
+    pert = 2e9 * rng.standard_normal((n, 6, 6))
+    if sym:                      # major symmetry in the 4th-order sense: W C symmetric
+        w = np.array([1, 1, 1, 2, 2, 2.0])
+        S = pert + pert.transpose(0, 2, 1)
+        pert = S / w[None, :, None]
+    return CT + pert
+
+
+@pytest.mark.parametrize("grid_name", ["cube_coarse", "cavern_regular"])
+def test_operator_rhs_blocks_strain(sf, grid_name):
+    grid = load_grid(sf, grid_name)
+    tm = grid.tetmesh
+    eq = sf.LinearMomentum(grid, theta=0.5)
+    eng = eq.engine
+    N, M = eng.N, eng.M
+    rng = np.random.default_rng(1)
+    CT = random_tangent(N, 2)
+    eps_rhs = 1e-4 * rng.standard_normal((N, 6))
+    eng.CT[:, :N] = torch.as_tensor(CT.reshape(N, 36)).t().to(eng.device)
+    eng.put6(eng.eps_rhs, eps_rhs)
+    K = fem.assemble_K(tm.coords, tm.cells, CT)
+    x = rng.standard_normal(3 * M) * 1e-3
+    fixed = np.zeros(3 * M, dtype=np.uint8)
+    fixed[rng.choice(3 * M, size=3 * M // 7, replace=False)] = 1
+    xd = torch.as_tensor(x).to(eng.device)
+    yd = torch.zeros_like(xd)
+    fd = torch.as_tensor(fixed).to(eng.device)
+    # y = K x, no mask
+    eng.apply(xd, yd, None)
+    assert relerr(yd.cpu().numpy(), K @ x) < 1e-12
+    # with mask: rows of fixed dofs are identity
+    eng.apply(xd, yd, fd)
+    ref = K @ x
+    ref[fixed == 1] = x[fixed == 1]
+    assert relerr(yd.cpu().numpy(), ref) < 1e-12
+    # residual r = b_ext + rhs_eps - K x0 on free dofs
+    b_ext = rng.standard_normal(3 * M) * 1e6
+    bd = torch.as_tensor(b_ext).to(eng.device)
+    rd = torch.zeros_like(xd)
+    eng.residual0(bd, xd, rd, fd)
+    ref = b_ext + fem.rhs_eps(tm.coords, tm.cells, CT, eps_rhs) - K @ x
+    ref[fixed == 1] = 0.0
+    assert relerr(rd.cpu().numpy(), ref) < 1e-12
+    # block-Jacobi blocks
+    dinv = torch.zeros((M, 9), dtype=torch.float64, device=eng.device)
+    eng.block_jacobi(dinv, fd)
+    Kd = K.tolil()
+    for n in rng.choice(M, size=min(M, 40), replace=False):
+        blk = K[3 * n:3 * n + 3, 3 * n:3 * n + 3].toarray()
+        for j in range(3):
+            if fixed[3 * n + j]:
+                blk[j, :] = 0
+                blk[:, j] = 0
+                blk[j, j] = 1
+        assert relerr(dinv[n].cpu().numpy().reshape(3, 3), np.linalg.inv(blk)) < 1e-10
+    # strain from a nodal field
+    eq.X.copy_(xd.reshape(M, 3))
+    e = eq.compute_total_strain().voigt().numpy()
+    assert relerr(e, fem.strain(tm.coords, tm.cells, x)) < 1e-12
+    # Newton error measure (Simulators.py:433-435)
+    prev = 1e-3 * rng.standard_normal((N, 6))
+    eng.put6(eng.eps_prev, prev)
+    eng.post(eq.X, 0.0, 0.5, -1.0, 1 | 16)
+    num, den = eng.err_out.tolist()
+    assert np.sqrt(num / den) == pytest.approx(oc.newton_error(prev, e), rel=1e-12)
+
+
+def test_neumann_and_body_force(sf):
+    from safeincave_b200 import cases
+    grid = load_grid(sf, "cavern_regular")
+    tm = grid.tetmesh
+    case = cases.cavern_case(grid)
+    eq, sim = cases.build(case, grid)
+    osim = oracle_simulator(case, tm)
+    for t in (0.0, 1.3 * 86400, 7 * 86400.0):
+        eq.bc.update_dirichlet(t)
+        eq.bc.update_neumann(t)
+        dofs, vals, b_ext = osim._bc(t)
+        assert relerr(eq.b_ext.reshape(-1).cpu().numpy(), b_ext) < 1e-12
+        mask = np.zeros(3 * tm.n_nodes, dtype=np.uint8)
+        mask[dofs] = 1
+        assert (eq.fixed.cpu().numpy() == mask).all()
+
+
+@pytest.mark.parametrize("method,sym", [("cg", True), ("bicg", False)])
+def test_krylov_solve_matches_direct(sf, method, sym):
+    from safeincave_b200 import cases
+    grid = load_grid(sf, "cavern_regular")
+    tm = grid.tetmesh
+    case = cases.cavern_case(grid, ksp_type=method, rtol=1e-13)
+    eq, sim = cases.build(case, grid)
+    osim = oracle_simulator(case, tm)
+    eng = eq.engine
+    N = eng.N
+    CT = random_tangent(N, 5, sym=sym) if not sym else oc.iso_matrix(102e9 * np.ones(N), 0.3 * np.ones(N))
+    eps_rhs = 1e-5 * np.random.default_rng(3).standard_normal((N, 6))
+    eng.CT[:, :N] = torch.as_tensor(CT.reshape(N, 36)).t().to(eng.device)
+    eng.put6(eng.eps_rhs, eps_rhs)
+    eq.bc.update_dirichlet(0.0)
+    eq.bc.update_neumann(0.0)
+    res = eq._linear_solve()
+    assert res.reason > 0, f"not converged: {res.reason} after {res.iterations}"
+    u_ref = osim._solve(CT, eps_rhs, 0.0)
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), u_ref) < 1e-9
+
+
+def run_both(sf, grid_name, case_fn, n_steps, levels=0, **kw):
+    from safeincave_b200 import cases
+    grid = load_grid(sf, grid_name, levels)
+    tm = grid.tetmesh
+    case = case_fn(grid, n_steps=n_steps, **kw)
+    eq, sim = cases.build(case, grid)
+    if case.get("desai_initial_hardening"):
+        def hook(eq_, stress):
+            for e in eq_.mat.elems_ne:
+                if hasattr(e, "compute_initial_hardening"):
+                    e.compute_initial_hardening(None, 0.0)
+        sim.after_initial_stress = hook
+    hist = sim.run()
+    osim = oracle_simulator(case, tm)
+    ohist = osim.run(0.0, [case["dt"]] * n_steps)
+    return eq, sim, hist, osim, ohist
+
+
+def check_fields(eq, osim, ohist, tol=1e-8):
+    eng = eq.engine
+    last = ohist[-1]
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), last["u"]) < tol
+    assert relerr(eng.get6(eng.sig), last["sig"]) < tol
+    assert relerr(eng.get6(eng.eps), last["eps"]) < tol
+    for e_gpu, e_or in zip(eng.elems, osim.mat.elems):
+        assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol
+        assert relerr(eng.get6(e_gpu.rate_old), e_or.rate_old) < tol
+
+
+def test_time_steps_triaxial_cube(sf):
+    """BASELINE config 1 on the reference's cube_coarse grid (48 cells): Spring + Kelvin + DC."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 6)
+    assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+    assert all(h["converged"] for h in hist)
+    check_fields(eq, osim, ohist)
+
+
+def test_time_steps_triaxial_cube_with_desai(sf):
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 3, levels=1,
+                                          elements=("kelvin", "dislocation", "desai"))
+    check_fields(eq, osim, ohist, tol=1e-7)
+
+
+def test_time_steps_cavern_regular(sf):
+    """BASELINE config 2: cavern_regular (14 346 cells), fully implicit, cyclic gas pressure."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, 2, ksp_type="bicg")
+    assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+    check_fields(eq, osim, ohist)

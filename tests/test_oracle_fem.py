@@ -1,0 +1,159 @@
+"""Self-evident checks that pin oracle/fem.py (the reference's own tests never touch assembly,
+BCs or the solve -- SURVEY 4, 8c: "parity unpinned") and the mesh services."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import constitutive as oc
+from oracle import fem
+from safeincave_b200.mesh import TetMesh, morton_order, red_refine, tri_area_normals
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def cube():
+    return TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz"))
+
+
+@pytest.fixture(scope="module")
+def cavern():
+    return TetMesh.load_npz(os.path.join(GOLD, "mesh_cavern_regular.npz"))
+
+
+def iso(n, E=102e9, nu=0.3):
+    return oc.iso_matrix(E * np.ones(n), nu * np.ones(n))
+
+
+def test_mesh_fixture_counts(cube, cavern):
+    assert (cube.n_nodes, cube.n_cells) == (23, 48)
+    assert (cavern.n_nodes, cavern.n_cells) == (3577, 14346)
+    assert set(cube.names[2]) == {"NORTH", "SOUTH", "WEST", "EAST", "BOTTOM", "TOP"}
+    assert set(cube.names[3]) == {"OMEGA_A", "OMEGA_B"}
+
+
+def test_volumes_and_outward_normals(cube, cavern):
+    _, vol = fem.tet_geometry(cube.coords, cube.cells)
+    assert vol.sum() == pytest.approx(1.0, rel=1e-13)
+    an = tri_area_normals(cube)
+    assert np.abs(an.sum(axis=0)).max() < 1e-13               # closed surface
+    top = cube.tri_tags == cube.names[2]["TOP"]
+    assert an[top][:, 2].sum() == pytest.approx(1.0, rel=1e-13)    # outward (+z), area 1
+    west = cube.tri_tags == cube.names[2]["WEST"]
+    assert an[west][:, 0].sum() == pytest.approx(-1.0, rel=1e-13)
+    # divergence theorem on the cavern grid: closed surface, volume = 1/3 oint x.n dS
+    an = tri_area_normals(cavern)
+    assert np.abs(an.sum(axis=0)).max() < 1e-6
+    cen = cavern.coords[cavern.tris].mean(axis=1)
+    _, vol = fem.tet_geometry(cavern.coords, cavern.cells)
+    assert (cen * an).sum() / 3.0 == pytest.approx(vol.sum(), rel=1e-12)
+
+
+def test_patch_test_uniform_strain(cube):
+    """A linear displacement field is reproduced exactly and gives the uniform strain/stress."""
+    x = cube.coords
+    Gm = np.array([[1e-3, 2e-4, -1e-4], [3e-4, -5e-4, 2e-4], [0.0, 1e-4, 7e-4]])
+    u = (x @ Gm.T).ravel()
+    eps = fem.strain(x, cube.cells, u)
+    sym = 0.5 * (Gm + Gm.T)
+    expect = np.array([sym[0, 0], sym[1, 1], sym[2, 2], sym[0, 1], sym[0, 2], sym[1, 2]])
+    assert np.abs(eps - expect).max() < 1e-18 + 1e-13 * np.abs(expect).max()
+    # with all boundary nodes prescribed to the linear field the solve returns it in the interior
+    K = fem.assemble_K(x, cube.cells, iso(cube.n_cells))
+    bnodes = np.unique(cube.tris)
+    dofs = (3 * bnodes[:, None] + np.arange(3)).ravel()
+    sol = fem.solve(K, np.zeros(K.shape[0]), dofs, u[dofs])
+    assert np.abs(sol - u).max() < 1e-12 * np.abs(u).max()
+
+
+def test_rigid_body_null_space_and_symmetry(cube):
+    x = cube.coords
+    K = fem.assemble_K(x, cube.cells, iso(cube.n_cells))
+    assert abs(K - K.T).max() < 1e-6 * abs(K).max()          # elastic C -> symmetric K
+    for mode in range(6):
+        u = np.zeros_like(x)
+        if mode < 3:
+            u[:, mode] = 1.0
+        else:
+            w = np.eye(3)[mode - 3]
+            u = np.cross(w, x)
+        assert np.abs(K @ u.ravel()).max() < 1e-4 * abs(K).max() * 1e-9 + 1e-3
+    # the shear doubling W makes K symmetric only if C_T has major symmetry in the 4th-order sense
+    CT = iso(cube.n_cells)
+    CT[:, 0, 3] += 1e9           # (the reference's FD tangent is of this kind)
+    K2 = fem.assemble_K(x, cube.cells, CT)
+    assert abs(K2 - K2.T).max() > 1e-3 * abs(K2).max()
+
+
+def test_neumann_total_force_and_hydrostatic(cube):
+    top = cube.names[2]["TOP"]
+    bc = dict(tag=top, direction=2, density=0.0, ref_pos=0.0, gravity=-9.81, values=[5e6, 5e6], time_values=[0, 1])
+    b = fem.neumann_load(cube.coords, cube.tris, cube.tri_tags, [bc], 0.5).reshape(-1, 3)
+    # p = -interp(t) (MomentumBC.py:275); outward normal +z; area 1 -> total force -5e6 in z
+    assert b[:, 2].sum() == pytest.approx(-5e6, rel=1e-13)
+    assert np.abs(b[:, :2]).max() < 1e-6
+    # hydrostatic part rho g (H - z) on EAST (x = 1 face): integral of rho g (H - z) over [0,1]^2
+    east = cube.names[2]["EAST"]
+    bc = dict(tag=east, direction=2, density=2000.0, ref_pos=1.0, gravity=-9.81, values=[0, 0], time_values=[0, 1])
+    b = fem.neumann_load(cube.coords, cube.tris, cube.tri_tags, [bc], 0.0).reshape(-1, 3)
+    assert b[:, 0].sum() == pytest.approx(2000.0 * -9.81 * 0.5, rel=1e-13)
+
+
+def test_uniaxial_compression_solution(cube):
+    """Rollers on WEST/SOUTH/BOTTOM, pressure on TOP: sigma_zz = -p everywhere, exact for P1."""
+    x, nm = cube.coords, cube.names[2]
+    N = cube.n_cells
+    E, nu, p = 102e9, 0.3, 4e6
+    K = fem.assemble_K(x, cube.cells, iso(N, E, nu))
+    bc = dict(tag=nm["TOP"], direction=2, density=0.0, ref_pos=0.0, gravity=0.0, values=[p, p], time_values=[0, 1])
+    b = fem.neumann_load(x, cube.tris, cube.tri_tags, [bc], 0.0)
+    dofs = np.concatenate([fem.dirichlet_dofs(cube.tris, cube.tri_tags, nm[n], c)
+                           for n, c in (("WEST", 0), ("SOUTH", 1), ("BOTTOM", 2))])
+    u = fem.solve(K, b, dofs, np.zeros(dofs.size))
+    eps = fem.strain(x, cube.cells, u)
+    sig = oc.ddot(iso(N, E, nu), eps)
+    assert np.abs(sig[:, 2] + p).max() < 1e-7 * p
+    assert np.abs(np.delete(sig, 2, axis=1)).max() < 1e-7 * p
+    assert np.abs(eps[:, 2] + p / E).max() < 1e-9 * p / E * 1e2
+
+
+def test_rhs_eps_is_consistent_with_K(cube):
+    """int (C:eps0):eps(v) with eps0 = eps(u0) equals K u0."""
+    x = cube.coords
+    rng = np.random.default_rng(0)
+    u0 = rng.standard_normal(3 * cube.n_nodes) * 1e-4
+    CT = iso(cube.n_cells) + 1e9 * rng.standard_normal((cube.n_cells, 6, 6))
+    K = fem.assemble_K(x, cube.cells, CT)
+    b = fem.rhs_eps(x, cube.cells, CT, fem.strain(x, cube.cells, u0))
+    assert np.abs(b - K @ u0).max() < 1e-12 * np.abs(b).max()
+
+
+def test_red_refinement_is_conforming(cube):
+    fine = red_refine(cube)
+    assert fine.n_cells == 8 * cube.n_cells and fine.tris.shape[0] == 4 * cube.tris.shape[0]
+    _, vol = fem.tet_geometry(fine.coords, fine.cells)
+    assert vol.min() > 0 and vol.sum() == pytest.approx(1.0, rel=1e-13)
+    an = tri_area_normals(fine)
+    top = fine.tri_tags == fine.names[2]["TOP"]
+    assert an[top][:, 2].sum() == pytest.approx(1.0, rel=1e-13)      # orientation inherited
+    # conforming: every interior face is shared by exactly two cells, boundary faces by one
+    c = fine.cells
+    faces = np.sort(np.concatenate([c[:, [1, 2, 3]], c[:, [0, 2, 3]], c[:, [0, 1, 3]], c[:, [0, 1, 2]]]), axis=1)
+    _, counts = np.unique(faces, axis=0, return_counts=True)
+    assert set(counts.tolist()) <= {1, 2}
+    assert (counts == 1).sum() == fine.tris.shape[0]
+    # Euler characteristic of a ball: V - E + F - C = 1
+    edges = np.sort(np.concatenate([c[:, [a, b]] for a in range(4) for b in range(a + 1, 4)]), axis=1)
+    n_e = np.unique(edges, axis=0).shape[0]
+    assert fine.n_nodes - n_e + counts.size - fine.n_cells == 1
+    # two levels and Morton renumbering keep the physics: same uniaxial solution
+    m2 = morton_order(red_refine(fine))
+    _, vol2 = fem.tet_geometry(m2.coords, m2.cells)
+    assert vol2.sum() == pytest.approx(1.0, rel=1e-12) and m2.n_cells == 64 * cube.n_cells
+
+
+def test_smoother_preserves_constants(cube):
+    f = fem.p_q_fields(cube.coords, cube.cells, np.tile([-3e6, -3e6, -3e6, 0, 0, 0], (cube.n_cells, 1)))
+    assert np.allclose(f["p_nodes"], -3e6) and np.allclose(f["p_elems"], -3e6)
+    assert np.abs(f["q_elems"]).max() < 1e-3
