@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SafeInCave mechanics hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--levels L] [--impl b200|reference]
+
+A "step" is one pass of Simulator_M's time-loop body (Simulators.py:378-517 of the reference):
+all Newton iterations of one time step -- tangent phase, matrix-free tangent/RHS, Krylov solve,
+post-solve phase, convergence measure -- plus the commit, excluding p/q smoothing and file output.
+
+Workload: BASELINE.json configs[1] physics (grids/cavern_regular, cyclic gas pressure, fully implicit
+theta = 0, Spring + DislocationCreep, dt = 2 h) on the cavern_regular grid red-refined `--levels`
+times (configs[4]: 14 346 * 8^L cells; L = 0 is the reference's own grid).  Synthetic refinement,
+random nothing: loads, materials and BCs are the example's.
+
+metric  cell-updates/s = n_cells * (Newton iterations executed) / (time of the steps), whole job.
+value   steps timed with CUDA events, state resident in HBM.
+e2e     the same through the public API with host buffers: every step uploads the per-cell
+        temperature field from pinned host memory (set_T, what Simulator_TM does every step) and
+        reads back displacement + stress into pinned host memory.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell_updates_per_s"
+UNIT = "cell-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--levels", type=int, default=2, help="red-refinement levels of cavern_regular (14 346 * 8^L cells)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ksp", default="cg")
+    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--warm-start", type=int, default=0, help="1: Krylov initial guess = previous solution")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(levels, n_cells):
+    return (f"grids/cavern_regular cyclic gas-pressure creep, fully implicit (theta=0), Spring+DislocationCreep, "
+            f"dt=2h; red-refined x8^{levels} = {n_cells} cells")
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is Python over DOLFINx/PETSc and cannot run on this box)
+# ----------------------------------------------------------------------------------------------
+class _HostGrid:
+    """Just enough of GridHandlerGMSH for cases.cavern_case, without touching CUDA."""
+
+    def __init__(self, tm):
+        self.tetmesh = tm
+
+        class _M:
+            pass
+        self.mesh = _M()
+        self.mesh.geometry = _M()
+        self.mesh.geometry.x = tm.coords
+
+    def get_boundary_tag(self, name):
+        return self.tetmesh.names[2][name]
+
+
+def cpu_reference_steps(n_steps, warmup):
+    """Time `n_steps` time steps of the CPU oracle (oracle/fem.py OracleSimulatorM: numpy constitutive
+    update + scipy CSR assembly + sparse LU) on the UNREFINED cavern_regular grid (14 346 cells), same
+    loads/materials as the GPU arm.  Returns (cell_updates_per_s, ms_per_step, newton_iterations, cores)."""
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200 import cases
+    from tests.case_oracle import oracle_simulator
+    tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
+    case = cases.cavern_case(_HostGrid(tm), n_steps=n_steps + warmup)
+    sim = oracle_simulator(case, tm)
+    marks = []
+    orig = sim.mat.commit
+
+    def commit(*a, **k):
+        orig(*a, **k)
+        marks.append(time.perf_counter())
+    sim.mat.commit = commit
+    t_begin = time.perf_counter()
+    hist = sim.run(0.0, [case["dt"]] * (n_steps + warmup))
+    marks = [t_begin] + marks
+    # marks[0] -> after init+step boundaries; step i spans marks[i]..marks[i+1] (init folded into step 0)
+    t0 = marks[warmup] if warmup > 0 else marks[0]
+    elapsed = marks[-1] - t0
+    iters = sum(h["iters"] for h in hist[1 + warmup:])
+    return tm.n_cells * iters / elapsed, 1e3 * elapsed / n_steps, iters, 1, tm.n_cells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))      # each oracle step is ~25 s of CPU work
+    warm = 0                                # no JIT / cache to warm on the CPU port
+    v, ms, iters, cores, n_cells = cpu_reference_steps(steps, warm)
+    sample = (f"{steps} time step(s) of the oracle port (numpy + scipy sparse LU) on cavern_regular unrefined "
+              f"({n_cells} cells), {iters} Newton iterations")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(0, n_cells), "note": "CPU port of the reference path; the reference's "
+                   "own FEniCSx/PETSc stack is not installable here (SURVEY 8c)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.samples.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases
+    from safeincave_b200.mesh import TetMesh, morton_order, red_refine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU partition (halo exchange + allreduce over NCCL) is not "
+                         "implemented yet in this round; run with --gpus 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
+    for _ in range(args.levels):
+        tm = red_refine(tm, device=dev)
+    tm = morton_order(tm, device=dev)
+    grid = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
+    case = cases.cavern_case(grid, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
+    eq, sim = cases.build(case, grid, device=dev)
+    eq.solver.initial_guess_nonzero = bool(args.warm_start)
+    eng = eq.engine
+    N, M = eng.N, eng.M
+    sim.initialize()                                     # elastic response + initial rates (setup, untimed)
+    torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    clocks = ClockSampler(local)
+    clocks.start()
+    eng.time_operator = True
+    eng.op_ms, eng.op_samples, eng.op_launches = 0.0, 0, 0
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    recs = [sim.step() for _ in range(args.steps)]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = eng.launches - launches0
+    iters = sum(r["iterations"] for r in recs)
+    ksp_its = sum(r["ksp_iterations"] for r in recs)
+    value = N * iters / (ms * 1e-3)
+    op_ms = eng.op_ms / max(eng.op_samples, 1)
+    op_launches = eng.op_launches
+    eng.time_operator = False
+
+    # ---- end-to-end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        T_host = eng.T[:N].cpu().pin_memory()
+        u_host = torch.empty((M, 3), dtype=torch.float64).pin_memory()
+        sig_host = torch.empty((6, N), dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        it2 = 0
+        for _ in range(args.steps):
+            eq.set_T(T_host)                                             # H2D: the step's input field
+            r = sim.step()
+            it2 += r["iterations"]
+            u_host.copy_(eq.X, non_blocking=True)                        # D2H: the step's results
+            sig_host.copy_(eng.sig[:, :N], non_blocking=True)
+            torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
+        e2e = {"value": N * it2 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * N,
+               "d2h_bytes_per_step": 8 * (3 * M + 6 * N), "ms_per_step": 1e3 * dt_e2e / args.steps}
+
+    # ---- roofline of the dominant kernel (the matrix-free operator inside the Krylov loop)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = N * (36 * 8 + 12 * 8 + 8 + 16) + M * (24 + 48)
+    achieved = bytes_per_launch / (op_ms * 1e-3) / 1e9 if op_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get(str(N))
+    roofline = {"bound": "hbm", "kernel": "k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": op_ms, "launches_sampled": eng.op_samples, "launches_in_timed_region": op_launches,
+                "share_of_step_time": op_ms * op_launches / ms if ms > 0 else None}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.levels, N), "n_cells": N, "n_nodes": M,
+                   "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp, "rtol": args.rtol,
+                   "preconditioner": "nodal 3x3 block Jacobi", "warm_start": bool(args.warm_start),
+                   "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
+        "clocks": clk, "gpu_launches": launches, "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        v, cms, citers, cores, n0 = cpu_reference_steps(1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"1 time step of the oracle port (numpy + scipy sparse LU) on cavern_regular "
+                                          f"unrefined ({n0} cells), {citers} Newton iterations, {cms / 1e3:.1f} s"}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

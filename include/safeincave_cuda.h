@@ -169,6 +169,11 @@ typedef struct {
   int32_t iterations;
   int32_t reason;         /* >0 converged (2 rtol, 3 atol), <0 diverged (-3 max_it, -9 nan) as PETSc */
   double rnorm, rnorm0;
+  /* measurement: with time_operator != 0 the first operator launch of every batch is bracketed by
+   * CUDA events on the solve's stream; op_ms accumulates their durations over op_samples launches */
+  int32_t time_operator;
+  int32_t op_samples;
+  double op_ms;
 } sic_ksp_t;
 
 /* Workspace: sic_ksp_workspace_doubles(n_nodes, method) doubles, caller-allocated. */

@@ -52,7 +52,8 @@ class SicProblem(ctypes.Structure):
 class SicKsp(ctypes.Structure):
     _fields_ = [("method", c_int32), ("max_it", c_int32), ("rtol", c_double), ("atol", c_double),
                 ("check_every", c_int32), ("use_graph", c_int32), ("iterations", c_int32), ("reason", c_int32),
-                ("rnorm", c_double), ("rnorm0", c_double)]
+                ("rnorm", c_double), ("rnorm0", c_double),
+                ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double)]
 
 
 class SicError(RuntimeError):

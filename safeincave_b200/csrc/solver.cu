@@ -347,6 +347,27 @@ extern "C" int64_t sic_ksp_workspace_doubles(int n_nodes, int method) {
 }
 
 static Scal* g_host_scal = nullptr;  // pinned mirror of the device scalars
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+
+// Brackets one operator launch per batch with CUDA events (measurement only).
+struct OpTimer {
+  sic_ksp_t* ksp;
+  cudaStream_t st;
+  bool armed = false;
+  OpTimer(sic_ksp_t* k, cudaStream_t s) : ksp(k), st(s) {
+    ksp->op_samples = 0;
+    ksp->op_ms = 0.0;
+    if (ksp->time_operator && !g_ev[0]) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); }
+  }
+  void begin(int k) { if (ksp->time_operator && k == 0) { cudaEventRecord(g_ev[0], st); armed = true; } }
+  void end(int k) { if (armed && k == 0) cudaEventRecord(g_ev[1], st); }
+  void collect() {  // call after the stream has been synchronised
+    if (!armed) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) { ksp->op_ms += ms; ksp->op_samples += 1; }
+    armed = false;
+  }
+};
 
 extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
                              const uint8_t* fixed, const double* dinv, double* work, void* stream) {
@@ -370,6 +391,7 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
             db = blocks_for(nd, SIC_VEC_THREADS);
   const int check = ksp->check_every > 0 ? ksp->check_every : 25;
   int launched = 0;
+  OpTimer timer(ksp, st);
   if (ksp->method == SIC_KSP_CG) {
     double *r = vec, *z = vec + nd, *pp = vec + 2 * (size_t)nd, *q = vec + 3 * (size_t)nd;
     if (int rc = sic_residual0(p, b_ext, x, r, fixed, stream)) return rc;
@@ -377,10 +399,13 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
     while (true) {
       cudaMemcpyAsync(g_host_scal, S, sizeof(Scal), cudaMemcpyDeviceToHost, st);
       if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "ksp sync")) return rc;
+      timer.collect();
       if (g_host_scal->done || launched >= ksp->max_it) break;
       int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
+        timer.begin(k);
         k_ebe_dot<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, pp, q, S, partials, counter);
+        timer.end(k);
         k_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, z, pp, q, dinv, fixed, S, partials, counter + 1);
         k_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, S);
       }
@@ -395,10 +420,13 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
     while (true) {
       cudaMemcpyAsync(g_host_scal, S, sizeof(Scal), cudaMemcpyDeviceToHost, st);
       if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "ksp sync")) return rc;
+      timer.collect();
       if (g_host_scal->done || launched >= ksp->max_it) break;
       int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
+        timer.begin(k);
         k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, y, v, S);
+        timer.end(k);
         k_bi_dot1<<<db, SIC_VEC_THREADS, 0, st>>>(nd, rh, v, fixed, S, partials, counter);
         k_bi_s<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, v, s, z, t, dinv, fixed, S);
         k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, z, t, S);

@@ -109,6 +109,8 @@ class Engine:
         self._ksp_work = {}
         self._prob = None
         self.launches = 0   # kernels launched through this engine (bench.py's gpu_launches)
+        self.time_operator = False          # bracket one operator launch per Krylov batch with CUDA events
+        self.op_ms, self.op_samples, self.op_launches = 0.0, 0, 0
 
     # ------------------------------------------------------------------ material
     def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False):
@@ -216,10 +218,14 @@ class Engine:
         ksp = L.SicKsp()
         ksp.method, ksp.max_it, ksp.rtol, ksp.atol = int(method), int(max_it), float(rtol), float(atol)
         ksp.check_every, ksp.use_graph = int(check_every), 0
+        ksp.time_operator = 1 if self.time_operator else 0
         L.check(self.lib.sic_ksp_solve(self._pp(), ctypes.byref(ksp), _ptr(b_ext), _ptr(x), _ptr(fixed), _ptr(dinv),
                                        _ptr(w), self._stream()), "sic_ksp_solve")
         per_it = 3 if method == L.KSP_CG else 7
         self.launches += 3 + per_it * int(ksp.iterations)
+        self.op_ms += float(ksp.op_ms)
+        self.op_samples += int(ksp.op_samples)
+        self.op_launches += (1 if method == L.KSP_CG else 2) * int(ksp.iterations)
         return ksp
 
     def fp64_peak(self):
