@@ -172,32 +172,36 @@ def run_b200(args):
     from safeincave_b200 import cases
     from safeincave_b200.mesh import TetMesh, morton_order, red_refine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("bench.py: the multi-GPU partition (halo exchange + allreduce over NCCL) is not "
-                         "implemented yet in this round; run with --gpus 1")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    from safeincave_b200 import distributed
+    ctx = distributed.init()
+    world, rank, dev = ctx.world, ctx.rank, ctx.device
+    local = dev.index or 0
 
     tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
     for _ in range(args.levels):
         tm = red_refine(tm, device=dev)
     tm = morton_order(tm, device=dev)
-    grid = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    grid_global = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
     n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
-    case = cases.cavern_case(grid, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
-    eq, sim = cases.build(case, grid, device=dev)
+    case = cases.cavern_case(grid_global, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
+    if world > 1:            # strong scaling: the SAME mesh, cells partitioned along the Morton curve
+        grid, part = distributed.partition_grid(ctx, tm)
+        eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
+    else:
+        grid, part = grid_global, None
+        eq, sim = cases.build(case, grid, device=dev)
+    sim.verbose = False
     eq.solver.initial_guess_nonzero = bool(args.warm_start)
     eng = eq.engine
-    N, M = eng.N, eng.M
+    N, M = tm.n_cells, tm.n_nodes                        # global counts (the metric is whole-job)
+    N_loc, M_loc = eng.N, eng.M
     sim.initialize()                                     # elastic response + initial rates (setup, untimed)
     torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         sim.step()
     torch.cuda.synchronize()
+    ctx.barrier()
 
     # ---- device-resident timing
     clocks = ClockSampler(local)
@@ -211,7 +215,8 @@ def run_b200(args):
     recs = [sim.step() for _ in range(args.steps)]
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ctx.barrier()
+    ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
     clk = clocks.stop()
     launches = eng.launches - launches0
     iters = sum(r["iterations"] for r in recs)
@@ -224,10 +229,11 @@ def run_b200(args):
     # ---- end-to-end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        T_host = eng.T[:N].cpu().pin_memory()
-        u_host = torch.empty((M, 3), dtype=torch.float64).pin_memory()
-        sig_host = torch.empty((6, N), dtype=torch.float64).pin_memory()
+        T_host = eng.T[:N_loc].cpu().pin_memory()
+        u_host = torch.empty((M_loc, 3), dtype=torch.float64).pin_memory()
+        sig_host = torch.empty((6, N_loc), dtype=torch.float64).pin_memory()
         torch.cuda.synchronize()
+        ctx.barrier()
         t0 = time.perf_counter()
         it2 = 0
         for _ in range(args.steps):
@@ -235,9 +241,10 @@ def run_b200(args):
             r = sim.step()
             it2 += r["iterations"]
             u_host.copy_(eq.X, non_blocking=True)                        # D2H: the step's results
-            sig_host.copy_(eng.sig[:, :N], non_blocking=True)
+            sig_host.copy_(eng.sig[:, :N_loc], non_blocking=True)
             torch.cuda.synchronize()
-        dt_e2e = time.perf_counter() - t0
+        ctx.barrier()
+        dt_e2e = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": N * it2 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * N,
                "d2h_bytes_per_step": 8 * (3 * M + 6 * N), "ms_per_step": 1e3 * dt_e2e / args.steps}
 
@@ -247,7 +254,7 @@ def run_b200(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bytes_per_launch = N * (36 * 8 + 12 * 8 + 8 + 16) + M * (24 + 48)
+    bytes_per_launch = N_loc * (36 * 8 + 12 * 8 + 8 + 16) + M_loc * (24 + 48)      # this rank's launch
     achieved = bytes_per_launch / (op_ms * 1e-3) / 1e9 if op_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -264,6 +271,8 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.levels, N), "n_cells": N, "n_nodes": M,
+                   "cells_per_gpu": N_loc, "partition": "Morton-curve chunks, interface nodes duplicated, NCCL halo sum "
+                   "+ 2 scalar allreduces per CG iteration" if world > 1 else "single GPU",
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp, "rtol": args.rtol,
                    "preconditioner": "nodal 3x3 block Jacobi", "warm_start": bool(args.warm_start),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
@@ -271,7 +280,9 @@ def run_b200(args):
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if rank != 0:
+        return
+    if not args.no_cpu_baseline and world == 1:
         v, cms, citers, cores, n0 = cpu_reference_steps(1, 0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"1 time step of the oracle port (numpy + scipy sparse LU) on cavern_regular "

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 1
+#define SIC_ABI_VERSION 2
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -134,9 +134,36 @@ int sic_commit_rates(const sic_problem_t* p, void* stream);
 int sic_desai_initial_hardening(const sic_problem_t* p, int elem, double Fvp_0, int32_t* n_clamped,
                                 void* stream);
 
+/* ---- multi-GPU: one process per GPU, cells partitioned, interface nodes duplicated ------------- */
+#define SIC_MAX_PEERS 16
+
+/* Halo plan of one rank.  Replaces the ghost updates of MomentumEquation.py:915-922, 1018-1025 and the MPI
+ * reductions inside PETSc's KSP.  NULL everywhere below means "single GPU". */
+typedef struct {
+  int32_t n_ranks, rank, n_peers, n_shared_total;
+  int32_t peer[SIC_MAX_PEERS];           /* neighbour ranks */
+  int32_t peer_off[SIC_MAX_PEERS + 1];   /* [n_peers+1] offsets (in nodes) of each neighbour's slice of idx/buffers */
+  const int32_t* idx;      /* [n_shared_total] local node ids shared with each neighbour, same global order on both sides */
+  const double* owner_w;   /* [n_nodes] 1.0 where this rank owns the node (lowest rank touching it), else 0.0 */
+  double* send_buf;        /* >= 9 * n_shared_total doubles */
+  double* recv_buf;        /* >= 9 * n_shared_total doubles */
+  void* comm;              /* from sic_comm_init */
+} sic_halo_t;
+
+/* NCCL communicator over NVLink/NVSwitch (libnccl.so.2 is dlopen'ed on first use; single-GPU runs never touch it).
+ * Rank 0 calls sic_comm_unique_id and broadcasts the 128 bytes (e.g. through torch.distributed). */
+int sic_comm_unique_id(uint8_t* id128);
+int sic_comm_init(const uint8_t* id128, int rank, int n_ranks, void** comm);
+int sic_comm_destroy(void* comm);
+/* vec[(node)*ncomp + c] += sum over the other ranks' copies, for every interface node (ncclSend/ncclRecv in one group). */
+int sic_halo_sum(const sic_halo_t* h, double* vec, int ncomp, void* stream);
+/* in-place sum over ranks of `count` device doubles. */
+int sic_allreduce_sum(void* comm, double* dev_buf, int count, void* stream);
+
 /* ---- part (2): matrix-free tangent / RHS "assembly" -------------------------------------- */
 
-/* y = K x with K = sum_e V_e B^T W CT_e B  (a(u,v) of MomentumEquation.py:1008-1011), rows and
+/* y = K x (LOCAL cells only; on several GPUs follow with sic_halo_sum) with K = sum_e V_e B^T W CT_e B
+ * (a(u,v) of MomentumEquation.py:1008-1011), rows and
  * columns of constrained dofs treated as in assemble_matrix(bcs): fixed[dof] != 0 -> y[dof] = x[dof].
  * x must already be zero on fixed dofs for the symmetric elimination to hold (the solvers do that). */
 int sic_apply(const sic_problem_t* p, const double* x, double* y, const uint8_t* fixed, void* stream);
@@ -144,10 +171,10 @@ int sic_apply(const sic_problem_t* p, const double* x, double* y, const uint8_t*
 /* r = b_ext - sum_e V_e B^T W CT_e (B x0 - eps_rhs_e), then r[fixed] = 0:
  * linear form of MomentumEquation.py:1014-1020 (b_rhs + body + Neumann) with apply_lifting/set_bc. */
 int sic_residual0(const sic_problem_t* p, const double* b_ext, const double* x0, double* r,
-                  const uint8_t* fixed, void* stream);
+                  const uint8_t* fixed, const sic_halo_t* halo, void* stream);
 
 /* nodal 3x3 diagonal blocks of K, inverted, fixed dofs decoupled: dinv[9*node..] (block Jacobi) */
-int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint8_t* fixed, void* stream);
+int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint8_t* fixed, const sic_halo_t* halo, void* stream);
 
 /* Neumann load of MomentumBC.py:247-277: b[3*node+c] += int_F (p_bc + rho_bc g_bc (H_bc - x_dir)) n_c phi ds.
  *   tri      [3][n_tri] node ids;  area_n [3][n_tri] outward normal * area;  bc_of_tri [n_tri] -> bc or -1
@@ -165,6 +192,8 @@ typedef struct {
   double atol;
   int32_t check_every;    /* host looks at the residual every this many iterations */
   int32_t use_graph;      /* capture check_every iterations into one CUDA graph */
+  int32_t guess_nonzero;  /* x holds an initial guess on the free dofs; rtol is then relative to the residual of the
+                             ZERO guess (PETSc's default ||r|| < rtol ||b||), so a warm start saves iterations */
   /* results */
   int32_t iterations;
   int32_t reason;         /* >0 converged (2 rtol, 3 atol), <0 diverged (-3 max_it, -9 nan) as PETSc */
@@ -183,7 +212,7 @@ int64_t sic_ksp_workspace_doubles(int n_nodes, int method);
  * dofs; out: solution).  Replaces solver.solve of MomentumEquation.py:1023-1025 / 920-922.
  * dinv: block-Jacobi blocks from sic_block_jacobi. */
 int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
-                  const uint8_t* fixed, const double* dinv, double* work, void* stream);
+                  const uint8_t* fixed, const double* dinv, double* work, const sic_halo_t* halo, void* stream);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-free DFMA chains; returns achieved FLOP/s in *flops (used to record the FP64 peak) */

@@ -74,7 +74,10 @@ class BcHandler:
         dofs = []
         for bc in self.dirichlet_boundaries:
             tag = grid.get_boundary_tag(bc.boundary_name)
-            nodes = np.unique(tm.tris[tm.tri_tags == tag])
+            if getattr(tm, "boundary_nodes", None) is not None:     # partitioned mesh: node sets from the global mesh
+                nodes = np.asarray(tm.boundary_nodes.get(int(tag), np.zeros(0, dtype=np.int64)))
+            else:
+                nodes = np.unique(tm.tris[tm.tri_tags == tag])
             dofs.append(to.as_tensor(3 * nodes + int(bc.component), dtype=to.int64, device=dev))
         neu = []
         if self.neumann_boundaries:
@@ -111,6 +114,8 @@ class BcHandler:
             p = -float(np.interp(t, bc.time_values, bc.values))
             par = to.tensor([[p, bc.density * bc.gravity, bc.ref_pos, float(bc.direction)]], dtype=to.float64,
                             device=eq.engine.device)
-            eq.engine.neumann(self._tri, self._area_n, sel, par, eq.b_neumann)
+            if self._tri.shape[1] > 0:
+                eq.engine.neumann(self._tri, self._area_n, sel, par, eq.b_neumann)
             self.neumann_bcs.append((bc, p))
+        eq.engine.halo_sum(eq.b_neumann, 3)          # several GPUs: complete the interface nodes
         to.add(eq.b_body, eq.b_neumann, out=eq.b_ext)

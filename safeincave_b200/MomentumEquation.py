@@ -88,6 +88,7 @@ class LinearMomentum(LinearMomentumBase):
         self.sig = CellField(eng, eng.sig)  # views that follow the engine's buffers
         self.eps_tot = CellField(eng, eng.eps)
         self._nodes_vol = None
+        self.dist = None                    # safeincave_b200.distributed.DistContext when partitioned
 
     # ------------------------------------------------------------------ configuration
     def set_material(self, material: Material):
@@ -129,6 +130,7 @@ class LinearMomentum(LinearMomentumBase):
         self.b_body.zero_()
         for a in range(4):
             self.b_body.index_add_(0, eng.conn[a, :eng.N].long(), w[:, None] * gv[None, :])
+        eng.halo_sum(self.b_body, 3)                 # several GPUs: cells are partitioned, nodes duplicated
         to.add(self.b_body, self.b_neumann, out=self.b_ext)
 
     # ------------------------------------------------------------------ fields
@@ -164,7 +166,7 @@ class LinearMomentum(LinearMomentumBase):
         eng.block_jacobi(self.dinv, self.fixed)
         rtol, atol, max_it = ksp.effective()
         res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
-                            max_it=max_it, check_every=ksp.check_every)
+                            max_it=max_it, check_every=ksp.check_every, guess_nonzero=ksp.initial_guess_nonzero)
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
         return res
@@ -243,6 +245,8 @@ class LinearMomentum(LinearMomentumBase):
         eng.post(self.X, dt, self.theta, self._kelvin_phi2, flags)
         if not with_error:
             return 0.0
+        if self.dist is not None and self.dist.world > 1:    # cells are partitioned: plain sums over ranks
+            self.dist.all_reduce_sum(eng.err_out)
         num, den = eng.err_out.tolist()                      # device -> host read of the step result
         if den == 0.0:
             return float("nan") if num != 0.0 else 0.0

@@ -11,9 +11,10 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsafeincave_cuda.so")
 
-SIC_ABI_VERSION = 1
+SIC_ABI_VERSION = 2
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
+SIC_MAX_PEERS = 16
 
 ELEM_KELVIN, ELEM_DISLOCATION, ELEM_PRESSURE_SOL, ELEM_DESAI = 1, 2, 3, 4
 DS_ALPHA, DS_ALPHA0, DS_QSI, DS_QSI_OLD, DS_FVP, DS_R, DS_H, DS_HSMALL, DS_P, DS_ALPHA_K, DS_Q = (
@@ -27,7 +28,8 @@ EXPORTS = (
     "sic_last_error", "sic_abi_version", "sic_device_info", "sic_tangent", "sic_elastic_tangent",
     "sic_post", "sic_post_blocks", "sic_commit", "sic_commit_rates", "sic_desai_initial_hardening",
     "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
-    "sic_ksp_solve", "sic_fp64_peak",
+    "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
+    "sic_allreduce_sum",
 )
 
 
@@ -51,9 +53,17 @@ class SicProblem(ctypes.Structure):
 
 class SicKsp(ctypes.Structure):
     _fields_ = [("method", c_int32), ("max_it", c_int32), ("rtol", c_double), ("atol", c_double),
-                ("check_every", c_int32), ("use_graph", c_int32), ("iterations", c_int32), ("reason", c_int32),
+                ("check_every", c_int32), ("use_graph", c_int32), ("guess_nonzero", c_int32),
+                ("iterations", c_int32), ("reason", c_int32),
                 ("rnorm", c_double), ("rnorm0", c_double),
                 ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double)]
+
+
+class SicHalo(ctypes.Structure):
+    _fields_ = [("n_ranks", c_int32), ("rank", c_int32), ("n_peers", c_int32), ("n_shared_total", c_int32),
+                ("peer", c_int32 * SIC_MAX_PEERS), ("peer_off", c_int32 * (SIC_MAX_PEERS + 1)),
+                ("idx", c_void_p), ("owner_w", c_void_p), ("send_buf", c_void_p), ("recv_buf", c_void_p),
+                ("comm", c_void_p)]
 
 
 class SicError(RuntimeError):
@@ -90,12 +100,18 @@ def load():
     lib.sic_commit_rates.argtypes = [PP, c_void_p]
     lib.sic_desai_initial_hardening.argtypes = [PP, c_int, c_double, c_void_p, c_void_p]
     lib.sic_apply.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p]
-    lib.sic_residual0.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
-    lib.sic_block_jacobi.argtypes = [PP, c_void_p, c_void_p, c_void_p]
+    PH = POINTER(SicHalo)
+    lib.sic_residual0.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_block_jacobi.argtypes = [PP, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_comm_unique_id.argtypes = [c_void_p]
+    lib.sic_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
+    lib.sic_comm_destroy.argtypes = [c_void_p]
+    lib.sic_halo_sum.argtypes = [PH, c_void_p, c_int, c_void_p]
+    lib.sic_allreduce_sum.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     lib.sic_neumann.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
     lib.sic_ksp_workspace_doubles.restype = c_int64
-    lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
     lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
     _lib = lib
     return lib

@@ -19,6 +19,7 @@ UNITS = [
     ("constitutive.cu", ["-fmad=false"]),
     ("fem.cu", []),
     ("solver.cu", []),
+    ("comm.cu", []),
 ]
 
 
@@ -53,7 +54,7 @@ def build(force=False, verbose=False):
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

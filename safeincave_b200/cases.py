@@ -99,13 +99,17 @@ def cell_temperature(case, coords, cells):
     return np.full(cells.shape[0], float(T))
 
 
-def build(case, grid, verbose=False, outputs=None, device="cuda"):
+def build(case, grid, verbose=False, outputs=None, device="cuda", part=None, ctx=None):
     """Instantiate LinearMomentum + Material + BCs + Simulator_M for a case on the GPU, the way the
-    reference's example scripts wire them."""
+    reference's example scripts wire them.  ``grid`` may be a rank's local grid (then pass the
+    Partition and DistContext; ``case`` must have been made from the GLOBAL grid)."""
     import safeincave_b200 as sf
     n = grid.n_elems
     one = to.ones(n, dtype=to.float64)
     eq = sf.LinearMomentum(grid, theta=case["theta"], device=device)
+    if ctx is not None:
+        from . import distributed
+        distributed.attach(eq, part, ctx)
     ksp = sf.PETSc.KSP().create(grid.mesh.comm)
     ksp.setType(case["ksp"]["type"])
     ksp.getPC().setType("asm")

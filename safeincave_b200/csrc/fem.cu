@@ -38,6 +38,13 @@ __global__ void k_mask_copy(int n, double* __restrict__ y, const double* __restr
   if (d < n && fixed[d]) y[d] = x ? x[d] : 0.0;
 }
 
+// r = fixed ? 0 : r + b
+__global__ void k_add_mask(int n, double* __restrict__ r, const double* __restrict__ b,
+                           const uint8_t* __restrict__ fixed) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < n) r[d] = (fixed && fixed[d]) ? 0.0 : r[d] + b[d];
+}
+
 // nodal 3x3 diagonal blocks of K: column l of K_aa is the force on node a caused by a unit
 // displacement of node a along l.
 __global__ void __launch_bounds__(SIC_EBE_THREADS) k_diag_blocks(sic_problem_t P, double* __restrict__ dblk) {
@@ -153,23 +160,27 @@ extern "C" int sic_apply(const sic_problem_t* p, const double* x, double* y, con
 }
 
 extern "C" int sic_residual0(const sic_problem_t* p, const double* b_ext, const double* x0, double* r,
-                             const uint8_t* fixed, void* stream) {
+                             const uint8_t* fixed, const sic_halo_t* halo, void* stream) {
   if (!p || !b_ext || !x0 || !r) return sic_fail("sic_residual0: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int nd = 3 * p->n_nodes;
-  if (int rc = sic_check_cuda(cudaMemcpyAsync(r, b_ext, sizeof(double) * nd, cudaMemcpyDeviceToDevice, st), "copy b"))
-    return rc;
+  // element part first (partial on interface nodes -> summed over ranks), then the consistent b_ext
+  if (int rc = sic_check_cuda(cudaMemsetAsync(r, 0, sizeof(double) * nd, st), "memset r")) return rc;
   if (p->n_cells > 0) k_ebe<1><<<blocks_for(p->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*p, x0, r);
-  if (fixed && nd > 0)
-    k_mask_copy<<<blocks_for(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, r, nullptr, fixed);
+  if (int rc = sic_check_launch("k_ebe<1>")) return rc;
+  if (int rc = sic_halo_sum(halo, r, 3, stream)) return rc;
+  if (nd > 0) k_add_mask<<<blocks_for(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, r, b_ext, fixed);
   return sic_check_launch("sic_residual0");
 }
 
-extern "C" int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint8_t* fixed, void* stream) {
+extern "C" int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint8_t* fixed, const sic_halo_t* halo,
+                                void* stream) {
   if (!p || !dinv || !fixed) return sic_fail("sic_block_jacobi: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = sic_check_cuda(cudaMemsetAsync(dinv, 0, sizeof(double) * 9 * p->n_nodes, st), "memset dinv")) return rc;
   if (p->n_cells > 0) k_diag_blocks<<<blocks_for(p->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*p, dinv);
+  if (int rc = sic_check_launch("k_diag_blocks")) return rc;
+  if (int rc = sic_halo_sum(halo, dinv, 9, stream)) return rc;
   if (p->n_nodes > 0)
     k_invert_blocks<<<blocks_for(p->n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(p->n_nodes, dinv, fixed);
   return sic_check_launch("sic_block_jacobi");

@@ -4,11 +4,16 @@
 // reference is a user-configured PETSc KSP (cg / bicg / bcgs / gmres + asm).
 // B200 design: the whole iteration lives on the device.  Scalars (alpha, beta, rho, omega, norms)
 // stay in device memory, every dot product is fused into the kernel that produces its operand
-// (p.Kp is accumulated per CELL inside the operator kernel at no extra memory traffic) and is
-// finished by the last block to arrive, the convergence test sets a device flag that turns the
-// remaining launches of a batch into no-ops, and the host only looks every `check_every`
-// iterations.  Dirichlet rows/columns are handled by keeping search directions zero on constrained
-// dofs (equivalent to assemble_matrix(bcs) + apply_lifting + set_bc, MomentumEquation.py:1010-1020).
+// (p.Kp is accumulated per CELL inside the operator kernel at no extra memory traffic -- and, cells
+// being partitioned, it needs no owner weights on several GPUs) and is finished by the last block to
+// arrive, the convergence test sets a device flag that turns the remaining launches of a batch into
+// no-ops, and the host only looks every `check_every` iterations.  Dirichlet rows/columns are handled
+// by keeping search directions zero on constrained dofs (equivalent to assemble_matrix(bcs) +
+// apply_lifting + set_bc, MomentumEquation.py:1010-1020).
+//
+// Several GPUs (halo != NULL): vectors are kept CONSISTENT on interface nodes; the operator result is
+// halo-summed (ncclSend/ncclRecv), node dot products use owner weights, and the per-rank sums go through
+// ncclAllReduce on the device buffer S->sum followed by a one-thread scalar kernel -- still no host sync.
 #include <math.h>
 #include <string.h>
 
@@ -19,12 +24,16 @@ namespace sic {
 struct Scal {
   double rz, pq, rr, rr0, alpha, beta, tol2;
   double rho, rhv, omega, ts, tt;
+  double sum[4];   // per-rank partial sums, all-reduced in place on several GPUs
+  double rr_ref;   // ||r||^2 of the zero initial guess (reference for rtol when warm-starting)
   int done, iters, nanflag, reason;
 };
 static_assert(sizeof(Scal) <= 64 * sizeof(double), "Scal must fit the reserved workspace header");
 
 #define SIC_WS_HEADER 64   /* doubles reserved for Scal */
 #define SIC_WS_COUNTERS 8  /* doubles reserved for ticket counters */
+
+enum { OP_REF = 0, OP_CG_INIT, OP_CG_ALPHA, OP_CG_BETA, OP_BI_INIT, OP_BI_ALPHA, OP_BI_OMEGA, OP_BI_BETA };
 
 __device__ __forceinline__ void check_convergence(Scal* S, double rr) {
   S->rr = rr;
@@ -33,47 +42,56 @@ __device__ __forceinline__ void check_convergence(Scal* S, double rr) {
   else if (rr <= S->tol2) { S->done = 1; }
 }
 
-// ---- operator kernel with the fused p.Kp reduction --------------------------------------------
-__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
-                                                            double* __restrict__ y, Scal* S,
-                                                            double* __restrict__ partials, unsigned* counter) {
-  if (S->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double v[1] = {0.0};
-  if (i < P.n_cells) {
-    CellGeom c;
-    load_geom(P, i, c);
-    double ua[12];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) ua[3 * a + j] = __ldg(x + 3 * (size_t)c.node[a] + j);
-    }
-    double eps[6], sig[6], f[12];
-    strain_from_nodal(c, ua, eps);
-    stress_from_CT(P, i, eps, sig);
-    forces(c, sig, f);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) atomicAdd(y + 3 * (size_t)c.node[a] + j, f[3 * a + j]);
-    }
-    // x_e^T K_e x_e = V eps : sigma  (shear terms counted twice)
-    v[0] = c.vol * ((eps[0] * sig[0] + eps[1] * sig[1] + eps[2] * sig[2]) +
-                    2.0 * (eps[3] * sig[3] + eps[4] * sig[4] + eps[5] * sig[5]));
-  }
-  grid_reduce<1, SIC_EBE_THREADS>(v, partials, counter, [&](const double* tot) {
-    S->pq = tot[0];
-    S->alpha = S->rz / tot[0];
-  });
+__device__ __forceinline__ void init_tolerance(Scal* S, double rr, double rtol, double atol, int guess) {
+  S->rr = rr;
+  S->rr0 = rr;
+  const double ref = guess ? S->rr_ref : rr;
+  const double t = rtol * rtol * ref, a2 = atol * atol;
+  S->tol2 = (t > a2) ? t : a2;
+  S->iters = 0; S->nanflag = 0; S->reason = 0; S->done = 0;
+  if (!(rr == rr) || isinf(rr)) { S->nanflag = 1; S->done = 1; S->reason = -9; }
+  else if (rr <= S->tol2 || rr == 0.0) { S->done = 1; S->reason = (rr <= a2) ? 3 : 2; }
 }
 
-// plain operator (no dot), skipping when converged
-__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
-                                                              double* __restrict__ y, const Scal* S) {
-  if (S->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_cells) return;
+// The scalar recurrences.  Runs in the last block of the producing kernel (one GPU) or in k_scal after
+// the allreduce (several GPUs).  Input: S->sum[].
+__device__ __forceinline__ void scal_step(Scal* S, int op, double rtol, double atol, int guess) {
+  switch (op) {
+    case OP_REF: S->rr_ref = S->sum[0]; break;
+    case OP_CG_INIT: S->rz = S->sum[0]; init_tolerance(S, S->sum[1], rtol, atol, guess); break;
+    case OP_CG_ALPHA: S->pq = S->sum[0]; S->alpha = S->rz / S->sum[0]; break;
+    case OP_CG_BETA: S->beta = S->sum[0] / S->rz; S->rz = S->sum[0]; check_convergence(S, S->sum[1]); break;
+    case OP_BI_INIT:
+      S->rho = S->sum[0]; S->alpha = 1.0; S->omega = 1.0;
+      init_tolerance(S, S->sum[0], rtol, atol, guess);
+      break;
+    case OP_BI_ALPHA: S->rhv = S->sum[0]; S->alpha = S->rho / S->sum[0]; break;
+    case OP_BI_OMEGA: S->ts = S->sum[0]; S->tt = S->sum[1]; S->omega = S->sum[0] / S->sum[1]; break;
+    case OP_BI_BETA:
+      S->beta = (S->sum[0] / S->rho) * (S->alpha / S->omega);
+      S->rho = S->sum[0];
+      check_convergence(S, S->sum[1]);
+      break;
+  }
+}
+
+__global__ void k_scal(Scal* S, int op, double rtol, double atol, int guess, int skip_if_done) {
+  if (skip_if_done && S->done) return;
+  scal_step(S, op, rtol, atol, guess);
+}
+
+struct Fin {  // what the last block does with the grid totals
+  Scal* S; int op; double rtol, atol; int guess; int multi;
+  template <int NV>
+  __device__ __forceinline__ void run(const double* tot) const {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) S->sum[k] = tot[k];
+    if (!multi) scal_step(S, op, rtol, atol, guess);
+  }
+};
+
+__device__ __forceinline__ void ebe_cell(const sic_problem_t& P, int i, const double* __restrict__ x,
+                                         double* __restrict__ y, double* energy) {
   CellGeom c;
   load_geom(P, i, c);
   double ua[12];
@@ -91,6 +109,29 @@ __global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_plain(sic_problem_t P, 
 #pragma unroll
     for (int j = 0; j < 3; ++j) atomicAdd(y + 3 * (size_t)c.node[a] + j, f[3 * a + j]);
   }
+  // x_e^T K_e x_e = V eps : sigma  (shear terms counted twice)
+  if (energy)
+    *energy = c.vol * ((eps[0] * sig[0] + eps[1] * sig[1] + eps[2] * sig[2]) +
+                       2.0 * (eps[3] * sig[3] + eps[4] * sig[4] + eps[5] * sig[5]));
+}
+
+// ---- operator kernel with the fused p.Kp reduction --------------------------------------------
+__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+                                                            double* __restrict__ y, Fin fin,
+                                                            double* __restrict__ partials, unsigned* counter) {
+  if (fin.S->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (i < P.n_cells) ebe_cell(P, i, x, y, &v[0]);
+  grid_reduce<1, SIC_EBE_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
+}
+
+// plain operator (no dot), skipping when converged
+__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
+                                                              double* __restrict__ y, const Scal* S) {
+  if (S->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n_cells) ebe_cell(P, i, x, y, nullptr);
 }
 
 __device__ __forceinline__ void precond3(const double* __restrict__ dinv, size_t n, const double r[3], double z[3]) {
@@ -99,11 +140,32 @@ __device__ __forceinline__ void precond3(const double* __restrict__ dinv, size_t
   for (int j = 0; j < 3; ++j) z[j] = __ldg(d + 3 * j) * r[0] + __ldg(d + 3 * j + 1) * r[1] + __ldg(d + 3 * j + 2) * r[2];
 }
 
+// z = fixed ? x : 0   (the zero initial guess that still carries the prescribed values)
+__global__ void k_zero_free(int nd, double* __restrict__ z, const double* __restrict__ x,
+                            const uint8_t* __restrict__ fixed) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < nd) z[d] = fixed[d] ? x[d] : 0.0;
+}
+
+// sum_owned r.r
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_norm2(int n_nodes, const double* __restrict__ r,
+                                                          const double* __restrict__ w, Fin fin,
+                                                          double* __restrict__ partials, unsigned* counter) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const double a = r[3 * (size_t)n + j]; v[0] += wn * a * a; }
+  }
+  grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
+}
+
 // ---- PCG ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_init(int n_nodes, const double* __restrict__ r,
                                                             double* __restrict__ z, double* __restrict__ p,
                                                             double* __restrict__ q, const double* __restrict__ dinv,
-                                                            Scal* S, double rtol, double atol,
+                                                            const double* __restrict__ w, Fin fin,
                                                             double* __restrict__ partials, unsigned* counter) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
@@ -112,29 +174,17 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_init(int n_nodes, const 
 #pragma unroll
     for (int j = 0; j < 3; ++j) rn[j] = r[3 * (size_t)n + j];
     precond3(dinv, n, rn, zn);
+    const double wn = w ? w[n] : 1.0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       z[3 * (size_t)n + j] = zn[j];
       p[3 * (size_t)n + j] = zn[j];
       q[3 * (size_t)n + j] = 0.0;
-      v[0] += rn[j] * zn[j];
-      v[1] += rn[j] * rn[j];
+      v[0] += wn * rn[j] * zn[j];
+      v[1] += wn * rn[j] * rn[j];
     }
   }
-  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) {
-    S->rz = tot[0];
-    S->rr = tot[1];
-    S->rr0 = tot[1];
-    double t = rtol * rtol * tot[1];
-    double a2 = atol * atol;
-    S->tol2 = (t > a2) ? t : a2;
-    S->iters = 0;
-    S->nanflag = 0;
-    S->reason = 0;
-    S->done = 0;
-    if (!(tot[1] == tot[1]) || isinf(tot[1])) { S->nanflag = 1; S->done = 1; S->reason = -9; }
-    else if (tot[1] <= a2 || tot[1] == 0.0) { S->done = 1; S->reason = 3; }
-  });
+  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
 }
 
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_update(int n_nodes, double* __restrict__ x,
@@ -142,11 +192,12 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_update(int n_nodes, doub
                                                               const double* __restrict__ p,
                                                               const double* __restrict__ q,
                                                               const double* __restrict__ dinv,
-                                                              const uint8_t* __restrict__ fixed, Scal* S,
+                                                              const uint8_t* __restrict__ fixed,
+                                                              const double* __restrict__ w, Fin fin,
                                                               double* __restrict__ partials, unsigned* counter) {
-  if (S->done) return;
+  if (fin.S->done) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const double alpha = S->alpha;
+  const double alpha = fin.S->alpha;
   double v[2] = {0.0, 0.0};
   if (n < n_nodes) {
     double rn[3], zn[3];
@@ -161,18 +212,15 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_update(int n_nodes, doub
       r[d] = rn[j];
     }
     precond3(dinv, n, rn, zn);
+    const double wn = w ? w[n] : 1.0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       z[3 * (size_t)n + j] = zn[j];
-      v[0] += rn[j] * zn[j];
-      v[1] += rn[j] * rn[j];
+      v[0] += wn * rn[j] * zn[j];
+      v[1] += wn * rn[j] * rn[j];
     }
   }
-  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) {
-    S->beta = tot[0] / S->rz;
-    S->rz = tot[0];
-    check_convergence(S, tot[1]);
-  });
+  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
 }
 
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_p(int nd, double* __restrict__ p, const double* __restrict__ z,
@@ -189,7 +237,7 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_init(int n_nodes, const 
                                                             double* __restrict__ rh, double* __restrict__ p,
                                                             double* __restrict__ y, double* __restrict__ v,
                                                             double* __restrict__ t, const double* __restrict__ dinv,
-                                                            Scal* S, double rtol, double atol,
+                                                            const double* __restrict__ w, Fin fin,
                                                             double* __restrict__ partials, unsigned* counter) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[1] = {0.0};
@@ -198,40 +246,35 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_init(int n_nodes, const 
 #pragma unroll
     for (int j = 0; j < 3; ++j) rn[j] = r[3 * (size_t)n + j];
     precond3(dinv, n, rn, yn);
+    const double wn = w ? w[n] : 1.0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const size_t d = 3 * (size_t)n + j;
       rh[d] = rn[j]; p[d] = rn[j]; y[d] = yn[j]; v[d] = 0.0; t[d] = 0.0;
-      acc[0] += rn[j] * rn[j];
+      acc[0] += wn * rn[j] * rn[j];
     }
   }
-  grid_reduce<1, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) {
-    S->rho = tot[0];
-    S->rr = tot[0];
-    S->rr0 = tot[0];
-    double tt = rtol * rtol * tot[0];
-    double a2 = atol * atol;
-    S->tol2 = (tt > a2) ? tt : a2;
-    S->iters = 0; S->nanflag = 0; S->reason = 0; S->done = 0;
-    S->alpha = 1.0; S->omega = 1.0;
-    if (!(tot[0] == tot[0]) || isinf(tot[0])) { S->nanflag = 1; S->done = 1; S->reason = -9; }
-    else if (tot[0] <= a2 || tot[0] == 0.0) { S->done = 1; S->reason = 3; }
-  });
+  grid_reduce<1, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
 }
 
 // rhv = rh . v (free dofs)  ->  alpha = rho / rhv
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_dot1(int nd, const double* __restrict__ rh,
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_dot1(int n_nodes, const double* __restrict__ rh,
                                                             const double* __restrict__ v,
-                                                            const uint8_t* __restrict__ fixed, Scal* S,
+                                                            const uint8_t* __restrict__ fixed,
+                                                            const double* __restrict__ w, Fin fin,
                                                             double* __restrict__ partials, unsigned* counter) {
-  if (S->done) return;
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[1] = {0.0};
-  if (d < nd && !fixed[d]) acc[0] = rh[d] * v[d];
-  grid_reduce<1, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) {
-    S->rhv = tot[0];
-    S->alpha = S->rho / tot[0];
-  });
+  if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      if (!fixed[d]) acc[0] += wn * rh[d] * v[d];
+    }
+  }
+  grid_reduce<1, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
 }
 
 // s = r - alpha v ; z = M^-1 s ; t = 0
@@ -258,49 +301,55 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_s(int n_nodes, const dou
 }
 
 // ts = t.s, tt = t.t (free dofs) -> omega
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_dot2(int nd, const double* __restrict__ t,
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_dot2(int n_nodes, const double* __restrict__ t,
                                                             const double* __restrict__ s,
-                                                            const uint8_t* __restrict__ fixed, Scal* S,
+                                                            const uint8_t* __restrict__ fixed,
+                                                            const double* __restrict__ w, Fin fin,
                                                             double* __restrict__ partials, unsigned* counter) {
-  if (S->done) return;
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[2] = {0.0, 0.0};
-  if (d < nd && !fixed[d]) { acc[0] = t[d] * s[d]; acc[1] = t[d] * t[d]; }
-  grid_reduce<2, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) {
-    S->ts = tot[0];
-    S->tt = tot[1];
-    S->omega = tot[0] / tot[1];
-  });
+  if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      if (!fixed[d]) { acc[0] += wn * t[d] * s[d]; acc[1] += wn * t[d] * t[d]; }
+    }
+  }
+  grid_reduce<2, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
 }
 
 // x += alpha y + omega z ; r = s - omega t ; rho_new = rh.r ; rr = r.r -> beta
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_update(int nd, double* __restrict__ x, double* __restrict__ r,
-                                                              const double* __restrict__ s,
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_update(int n_nodes, double* __restrict__ x,
+                                                              double* __restrict__ r, const double* __restrict__ s,
                                                               const double* __restrict__ t,
                                                               const double* __restrict__ y,
                                                               const double* __restrict__ z,
                                                               const double* __restrict__ rh,
-                                                              const uint8_t* __restrict__ fixed, Scal* S,
+                                                              const uint8_t* __restrict__ fixed,
+                                                              const double* __restrict__ w, Fin fin,
                                                               double* __restrict__ partials, unsigned* counter) {
-  if (S->done) return;
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const double alpha = S->alpha, omega = S->omega;
+  if (fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const double alpha = fin.S->alpha, omega = fin.S->omega;
   double acc[2] = {0.0, 0.0};
-  if (d < nd) {
-    double rn = 0.0;
-    if (!fixed[d]) {
-      x[d] += alpha * y[d] + omega * z[d];
-      rn = s[d] - omega * t[d];
+  if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      double rn = 0.0;
+      if (!fixed[d]) {
+        x[d] += alpha * y[d] + omega * z[d];
+        rn = s[d] - omega * t[d];
+      }
+      r[d] = rn;
+      acc[0] += wn * rh[d] * rn;
+      acc[1] += wn * rn * rn;
     }
-    r[d] = rn;
-    acc[0] = rh[d] * rn;
-    acc[1] = rn * rn;
   }
-  grid_reduce<2, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) {
-    S->beta = (tot[0] / S->rho) * (S->alpha / S->omega);
-    S->rho = tot[0];
-    check_convergence(S, tot[1]);
-  });
+  grid_reduce<2, SIC_VEC_THREADS>(acc, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
 }
 
 // p = r + beta (p - omega v) ; y = M^-1 p ; v = 0
@@ -331,19 +380,15 @@ using namespace sic;
 
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
-static int64_t partial_doubles(int n_cells, int n_nodes) {
-  int nb = blocks_for(n_cells, SIC_EBE_THREADS);
-  int nv = blocks_for(3 * n_nodes, SIC_VEC_THREADS);
-  int m = nb > nv ? nb : nv;
-  return 2 * (int64_t)(m + 1);
+static int64_t partial_slots(int n_nodes) {
+  return 2 * ((int64_t)n_nodes * 8 / SIC_EBE_THREADS + 3 * (int64_t)n_nodes / SIC_VEC_THREADS + 4);
 }
 
 extern "C" int64_t sic_ksp_workspace_doubles(int n_nodes, int method) {
-  // header + counters + partials (sized for the worst case of 8 cells per node) + vectors
-  int64_t nd = 3 * (int64_t)n_nodes;
-  int64_t nvec = (method == SIC_KSP_BICGSTAB) ? 8 : 4;
-  int64_t part = 2 * ((int64_t)n_nodes * 8 / SIC_EBE_THREADS + nd / SIC_VEC_THREADS + 4);
-  return SIC_WS_HEADER + SIC_WS_COUNTERS + part + nvec * nd;
+  // header + counters + partials (sized for up to 8 cells per node) + vectors
+  const int64_t nd = 3 * (int64_t)n_nodes;
+  const int64_t nvec = (method == SIC_KSP_BICGSTAB) ? 8 : 4;
+  return SIC_WS_HEADER + SIC_WS_COUNTERS + partial_slots(n_nodes) + nvec * nd;
 }
 
 static Scal* g_host_scal = nullptr;  // pinned mirror of the device scalars
@@ -370,16 +415,22 @@ struct OpTimer {
 };
 
 extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
-                             const uint8_t* fixed, const double* dinv, double* work, void* stream) {
+                             const uint8_t* fixed, const double* dinv, double* work, const sic_halo_t* halo,
+                             void* stream) {
   if (!p || !ksp || !b_ext || !x || !fixed || !dinv || !work) return sic_fail("sic_ksp_solve: null argument");
   if (ksp->method != SIC_KSP_CG && ksp->method != SIC_KSP_BICGSTAB) return sic_fail("sic_ksp_solve: unknown method");
   cudaStream_t st = (cudaStream_t)stream;
   const int nn = p->n_nodes, nd = 3 * nn, nc = p->n_cells;
-  const int64_t part = 2 * ((int64_t)nn * 8 / SIC_EBE_THREADS + (int64_t)nd / SIC_VEC_THREADS + 4);
-  if (partial_doubles(nc, nn) > part) return sic_fail("sic_ksp_solve: more than 8 cells per node on average");
+  const int64_t part = partial_slots(nn);
+  if (2 * ((int64_t)blocks_for(nc, SIC_EBE_THREADS) + 1) > part)
+    return sic_fail("sic_ksp_solve: more than 8 cells per node on average");
   if (!g_host_scal) {
     if (int rc = sic_check_cuda(cudaMallocHost((void**)&g_host_scal, sizeof(Scal)), "cudaMallocHost")) return rc;
   }
+  const int multi = (halo && halo->n_ranks > 1) ? 1 : 0;
+  if (multi && (!halo->comm || !halo->owner_w)) return sic_fail("sic_ksp_solve: halo without communicator / owner weights");
+  const double* w = multi ? halo->owner_w : nullptr;
+  void* comm = multi ? halo->comm : nullptr;
   Scal* S = (Scal*)work;
   unsigned* counter = (unsigned*)(work + SIC_WS_HEADER);
   double* partials = work + SIC_WS_HEADER + SIC_WS_COUNTERS;
@@ -390,48 +441,80 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
   const int cb = blocks_for(nc, SIC_EBE_THREADS), nb = blocks_for(nn, SIC_VEC_THREADS),
             db = blocks_for(nd, SIC_VEC_THREADS);
   const int check = ksp->check_every > 0 ? ksp->check_every : 25;
+  const int guess = ksp->guess_nonzero ? 1 : 0;
+  const double rtol = ksp->rtol, atol = ksp->atol;
+  auto fin = [&](int op) { return Fin{S, op, rtol, atol, guess, multi}; };
+  // several GPUs: all-reduce S->sum and run the scalar recurrence in a one-thread kernel
+  auto reduce = [&](int op, int count, int skip_if_done) -> int {
+    if (!multi) return 0;
+    if (int rc = sic_allreduce_sum(comm, S->sum, count, stream)) return rc;
+    k_scal<<<1, 1, 0, st>>>(S, op, rtol, atol, guess, skip_if_done);
+    return sic_check_launch("k_scal");
+  };
   int launched = 0;
   OpTimer timer(ksp, st);
+
+  double *r = vec, *v1 = vec + nd, *v2 = vec + 2 * (size_t)nd, *v3 = vec + 3 * (size_t)nd;
+  if (guess) {  // reference norm: residual of the zero guess (prescribed values only)
+    k_zero_free<<<db, SIC_VEC_THREADS, 0, st>>>(nd, v1, x, fixed);
+    if (int rc = sic_residual0(p, b_ext, v1, r, fixed, halo, stream)) return rc;
+    k_norm2<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, w, fin(OP_REF), partials, counter);
+    if (int rc = reduce(OP_REF, 1, 0)) return rc;
+  }
+  if (int rc = sic_residual0(p, b_ext, x, r, fixed, halo, stream)) return rc;
+
   if (ksp->method == SIC_KSP_CG) {
-    double *r = vec, *z = vec + nd, *pp = vec + 2 * (size_t)nd, *q = vec + 3 * (size_t)nd;
-    if (int rc = sic_residual0(p, b_ext, x, r, fixed, stream)) return rc;
-    k_cg_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, pp, q, dinv, S, ksp->rtol, ksp->atol, partials, counter);
+    double *z = v1, *pp = v2, *q = v3;
+    k_cg_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, pp, q, dinv, w, fin(OP_CG_INIT), partials, counter);
+    if (int rc = reduce(OP_CG_INIT, 2, 0)) return rc;
     while (true) {
       cudaMemcpyAsync(g_host_scal, S, sizeof(Scal), cudaMemcpyDeviceToHost, st);
       if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "ksp sync")) return rc;
       timer.collect();
       if (g_host_scal->done || launched >= ksp->max_it) break;
-      int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
+      const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
         timer.begin(k);
-        k_ebe_dot<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, pp, q, S, partials, counter);
+        k_ebe_dot<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, pp, q, fin(OP_CG_ALPHA), partials, counter);
         timer.end(k);
-        k_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, z, pp, q, dinv, fixed, S, partials, counter + 1);
+        if (multi) {
+          if (int rc = sic_halo_sum(halo, q, 3, stream)) return rc;
+          if (int rc = reduce(OP_CG_ALPHA, 1, 1)) return rc;
+        }
+        k_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, z, pp, q, dinv, fixed, w, fin(OP_CG_BETA), partials,
+                                                    counter + 1);
+        if (int rc = reduce(OP_CG_BETA, 2, 1)) return rc;
         k_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, S);
       }
       launched += batch;
       if (int rc = sic_check_launch("cg batch")) return rc;
     }
   } else {
-    double *r = vec, *rh = vec + nd, *pp = vec + 2 * (size_t)nd, *v = vec + 3 * (size_t)nd, *s = vec + 4 * (size_t)nd,
-           *t = vec + 5 * (size_t)nd, *y = vec + 6 * (size_t)nd, *z = vec + 7 * (size_t)nd;
-    if (int rc = sic_residual0(p, b_ext, x, r, fixed, stream)) return rc;
-    k_bi_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, rh, pp, y, v, t, dinv, S, ksp->rtol, ksp->atol, partials, counter);
+    double *rh = v1, *pp = v2, *v = v3, *s = vec + 4 * (size_t)nd, *t = vec + 5 * (size_t)nd,
+           *y = vec + 6 * (size_t)nd, *z = vec + 7 * (size_t)nd;
+    k_bi_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, rh, pp, y, v, t, dinv, w, fin(OP_BI_INIT), partials, counter);
+    if (int rc = reduce(OP_BI_INIT, 1, 0)) return rc;
     while (true) {
       cudaMemcpyAsync(g_host_scal, S, sizeof(Scal), cudaMemcpyDeviceToHost, st);
       if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "ksp sync")) return rc;
       timer.collect();
       if (g_host_scal->done || launched >= ksp->max_it) break;
-      int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
+      const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
         timer.begin(k);
         k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, y, v, S);
         timer.end(k);
-        k_bi_dot1<<<db, SIC_VEC_THREADS, 0, st>>>(nd, rh, v, fixed, S, partials, counter);
+        if (int rc = sic_halo_sum(halo, v, 3, stream)) return rc;
+        k_bi_dot1<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, rh, v, fixed, w, fin(OP_BI_ALPHA), partials, counter);
+        if (int rc = reduce(OP_BI_ALPHA, 1, 1)) return rc;
         k_bi_s<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, v, s, z, t, dinv, fixed, S);
         k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, z, t, S);
-        k_bi_dot2<<<db, SIC_VEC_THREADS, 0, st>>>(nd, t, s, fixed, S, partials, counter + 1);
-        k_bi_update<<<db, SIC_VEC_THREADS, 0, st>>>(nd, x, r, s, t, y, z, rh, fixed, S, partials, counter + 2);
+        if (int rc = sic_halo_sum(halo, t, 3, stream)) return rc;
+        k_bi_dot2<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, t, s, fixed, w, fin(OP_BI_OMEGA), partials, counter + 1);
+        if (int rc = reduce(OP_BI_OMEGA, 2, 1)) return rc;
+        k_bi_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, s, t, y, z, rh, fixed, w, fin(OP_BI_BETA), partials,
+                                                    counter + 2);
+        if (int rc = reduce(OP_BI_BETA, 2, 1)) return rc;
         k_bi_p<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, pp, r, v, y, dinv, fixed, S);
       }
       launched += batch;

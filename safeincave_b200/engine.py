@@ -110,6 +110,8 @@ class Engine:
         self._prob = None
         self.launches = 0   # kernels launched through this engine (bench.py's gpu_launches)
         self.time_operator = False          # bracket one operator launch per Krylov batch with CUDA events
+        self.halo = None                    # L.SicHalo when the mesh is partitioned over several GPUs
+        self._halo_keep = None
         self.op_ms, self.op_samples, self.op_launches = 0.0, 0, 0
 
     # ------------------------------------------------------------------ material
@@ -191,13 +193,51 @@ class Engine:
         L.check(self.lib.sic_apply(self._pp(), _ptr(x), _ptr(y), _ptr(fixed), self._stream()), "sic_apply")
         self.launches += 2
 
+    def _ph(self):
+        return ctypes.byref(self.halo) if self.halo is not None else None
+
     def residual0(self, b_ext, x0, r, fixed):
-        L.check(self.lib.sic_residual0(self._pp(), _ptr(b_ext), _ptr(x0), _ptr(r), _ptr(fixed), self._stream()),
-                "sic_residual0")
+        L.check(self.lib.sic_residual0(self._pp(), _ptr(b_ext), _ptr(x0), _ptr(r), _ptr(fixed), self._ph(),
+                                       self._stream()), "sic_residual0")
         self.launches += 2
 
     def block_jacobi(self, dinv, fixed):
-        L.check(self.lib.sic_block_jacobi(self._pp(), _ptr(dinv), _ptr(fixed), self._stream()), "sic_block_jacobi")
+        L.check(self.lib.sic_block_jacobi(self._pp(), _ptr(dinv), _ptr(fixed), self._ph(), self._stream()),
+                "sic_block_jacobi")
+        self.launches += 2
+
+    # ------------------------------------------------------------------ several GPUs
+    def set_partition(self, part, comm):
+        """Attach the halo plan of safeincave_b200.partition.Partition and an NCCL communicator handle."""
+        if part.n_ranks <= 1:
+            self.halo = None
+            return
+        if len(part.peers) > L.SIC_MAX_PEERS:
+            raise L.SicError("too many neighbouring ranks")
+        dev = self.device
+        idx = torch.cat([s.to(dev) for s in part.shared]).to(torch.int32).contiguous()
+        owner_w = part.owner_w.to(dev, dtype=torch.float64).contiguous()
+        total = int(idx.numel())
+        send = torch.zeros(9 * max(total, 1), dtype=torch.float64, device=dev)
+        recv = torch.zeros(9 * max(total, 1), dtype=torch.float64, device=dev)
+        h = L.SicHalo()
+        h.n_ranks, h.rank, h.n_peers, h.n_shared_total = part.n_ranks, part.rank, len(part.peers), total
+        off = 0
+        for i, (peer, sh) in enumerate(zip(part.peers, part.shared)):
+            h.peer[i] = int(peer)
+            h.peer_off[i] = off
+            off += int(sh.numel())
+        h.peer_off[len(part.peers)] = off
+        h.idx, h.owner_w, h.send_buf, h.recv_buf = _ptr(idx), _ptr(owner_w), _ptr(send), _ptr(recv)
+        h.comm = comm
+        self.halo = h
+        self._halo_keep = (idx, owner_w, send, recv)
+        self.owner_w = owner_w
+
+    def halo_sum(self, vec, ncomp):
+        if self.halo is None:
+            return
+        L.check(self.lib.sic_halo_sum(self._ph(), _ptr(vec), int(ncomp), self._stream()), "sic_halo_sum")
         self.launches += 2
 
     def neumann(self, tri, area_n, bc_of_tri, bc_par, b):
@@ -208,7 +248,8 @@ class Engine:
         self.launches += 1
 
     # ------------------------------------------------------------------ part (3)
-    def ksp_solve(self, method, b_ext, x, fixed, dinv, rtol=1e-10, atol=0.0, max_it=10000, check_every=25):
+    def ksp_solve(self, method, b_ext, x, fixed, dinv, rtol=1e-10, atol=0.0, max_it=10000, check_every=25,
+                  guess_nonzero=False):
         key = method
         need = int(self.lib.sic_ksp_workspace_doubles(self.M, method))
         w = self._ksp_work.get(key)
@@ -219,8 +260,9 @@ class Engine:
         ksp.method, ksp.max_it, ksp.rtol, ksp.atol = int(method), int(max_it), float(rtol), float(atol)
         ksp.check_every, ksp.use_graph = int(check_every), 0
         ksp.time_operator = 1 if self.time_operator else 0
+        ksp.guess_nonzero = 1 if guess_nonzero else 0
         L.check(self.lib.sic_ksp_solve(self._pp(), ctypes.byref(ksp), _ptr(b_ext), _ptr(x), _ptr(fixed), _ptr(dinv),
-                                       _ptr(w), self._stream()), "sic_ksp_solve")
+                                       _ptr(w), self._ph(), self._stream()), "sic_ksp_solve")
         per_it = 3 if method == L.KSP_CG else 7
         self.launches += 3 + per_it * int(ksp.iterations)
         self.op_ms += float(ksp.op_ms)
