@@ -14,8 +14,13 @@
  *   - all floating point is IEEE double.  Tensors are symmetric 3x3 stored as 6 Voigt
  *     components in the reference's order [xx, yy, zz, xy, xz, yz] with TENSORIAL shear
  *     (Utils.py:171-227, 251-283).
- *   - per-cell arrays are SoA: component c of cell i lives at a[c*cell_stride + i]
- *     (cell_stride >= n_cells, multiple of 32).  6x6 tangents are 36 rows, row-major (r*6+c).
+ *   - C_T and the operator's geometry are TILED (AoSoA): cells are grouped in tiles of SIC_TILE_CELLS = 128 and a
+ *     tile's data is one contiguous block, so that the operator can fetch a whole tile with ONE TMA bulk copy:
+ *       C_T entry (r,c) of cell i  at  CT[((i/128)*36 + r*6+c)*128 + i%128]          (SIC_CT_INDEX)
+ *       geometry of tile t         at  geom_tiles[t]  (sic_geom_tile_t: grad[12][128], vol[128], conn[4][128])
+ *     Warp accesses stay coalesced (32 consecutive cells of one row).
+ *   - all other per-cell arrays are SoA: component c of cell i lives at a[c*cell_stride + i]
+ *     (cell_stride >= n_cells, multiple of 128: whole tiles for the TMA-staged operator).  6x6 tangents are 36 rows, row-major (r*6+c).
  *   - nodal vectors (u, b, x, y ...) are interleaved: dof = 3*node + component, as in the
  *     reference's vector P1 space (MomentumEquation.py:219).
  */
@@ -28,9 +33,19 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 2
+#define SIC_ABI_VERSION 4
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
+
+#define SIC_TILE_CELLS 128
+#define SIC_CT_INDEX(rc, i) ((((size_t)(i) >> 7) * 36 + (size_t)(rc)) * 128 + ((size_t)(i) & 127))
+
+/* geometry of one tile of 128 cells, as the operator kernel stages it in shared memory (15 360 bytes) */
+typedef struct {
+  double grad[12][SIC_TILE_CELLS];   /* d(phi_a)/dx_j at row 3*a+j */
+  double vol[SIC_TILE_CELLS];
+  int32_t conn[4][SIC_TILE_CELLS];
+} sic_geom_tile_t;
 
 /* non-elastic element kinds (MaterialProps.py classes) */
 enum {
@@ -74,6 +89,16 @@ typedef struct {
   const int32_t* conn;   /* [4][cell_stride] node ids */
   const double* grad;    /* [12][cell_stride] d(phi_a)/dx_j at row 3*a+j */
   const double* vol;     /* [cell_stride] */
+  const sic_geom_tile_t* geom_tiles;  /* [cell_stride/128] the same conn/grad/vol, tiled for the operator kernel */
+  /* scatter plan of the operator: per tile of 128 cells, its unique nodes (tile-interior ones first) and, per
+   * unique node, the (cell,slot) references inside the tile.  The kernel stages the 12 nodal forces of every
+   * cell in shared memory, sums them per unique node there, and touches global memory once per unique node
+   * (plain store for tile-interior nodes, one FP64 atomic otherwise) instead of 12 atomics per cell. */
+  const int32_t* tile_ptr;    /* [n_tiles+1] offsets into tile_nodes */
+  const int32_t* tile_nint;   /* [n_tiles]   number of tile-interior nodes (listed first) */
+  const int32_t* tile_nodes;  /* [tile_ptr[n_tiles]] node ids */
+  const int32_t* ent_ptr;     /* [tile_ptr[n_tiles]+1] offsets into ent, per unique (tile,node) */
+  const uint16_t* ent;        /* [4*cell_stride] local_cell*4 + slot, grouped by unique (tile,node) */
   /* material: deduplicated parameter rows + per-cell row index */
   const int32_t* mat_id;     /* [cell_stride] */
   const double* mat_table;   /* [n_rows][row_len] */
@@ -90,7 +115,7 @@ typedef struct {
   double* sig_k;    /* [6][cell_stride] stress of the previous iteration  */
   double* eps;      /* [6][cell_stride] total strain                      */
   double* eps_prev; /* [6][cell_stride] total strain of previous iteration*/
-  double* CT;       /* [36][cell_stride] consistent tangent               */
+  double* CT;       /* [cell_stride/128][36][128] consistent tangent, tiled (SIC_CT_INDEX) */
   double* eps_rhs;  /* [6][cell_stride]                                   */
   int32_t* n_singular; /* device counter: cells whose tangent was singular (elastic fallback) */
 } sic_problem_t;

@@ -363,4 +363,4 @@ class Material:
     @property
     def CT(self):
         eng = self._engine
-        return eng.CT[:, :eng.N].t().reshape(eng.N, 6, 6).cpu()
+        return to.as_tensor(eng.get_CT())

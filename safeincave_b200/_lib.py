@@ -9,9 +9,9 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsafeincave_cuda.so")
+LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 2
+SIC_ABI_VERSION = 4
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -41,7 +41,8 @@ class SicElem(ctypes.Structure):
 class SicProblem(ctypes.Structure):
     _fields_ = [
         ("abi_version", c_int32), ("n_cells", c_int32), ("cell_stride", c_int32), ("n_nodes", c_int32),
-        ("conn", c_void_p), ("grad", c_void_p), ("vol", c_void_p),
+        ("conn", c_void_p), ("grad", c_void_p), ("vol", c_void_p), ("geom_tiles", c_void_p),
+        ("tile_ptr", c_void_p), ("tile_nint", c_void_p), ("tile_nodes", c_void_p), ("ent_ptr", c_void_p), ("ent", c_void_p),
         ("mat_id", c_void_p), ("mat_table", c_void_p), ("n_rows", c_int32), ("row_len", c_int32),
         ("spring_off", c_int32), ("n_thermo", c_int32), ("thermo_off", c_int32), ("n_elems", c_int32),
         ("elems", SicElem * SIC_MAX_ELEMS),

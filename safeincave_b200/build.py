@@ -37,9 +37,11 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """defines/suffix: build an experimental variant (e.g. -DSIC_EBE_IMPL=2) as libsafeincave_cuda<suffix>.so."""
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + suffix)
+    lib_path = LIB.replace(".so", suffix + ".so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "safeincave_cuda.h"))
@@ -49,16 +51,16 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + extra + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    if force or _stale(lib_path, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", lib_path] + objs + ["-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

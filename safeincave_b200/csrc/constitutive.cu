@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_tangent(sic_problem_t P, d
     if (P.n_singular) atomicAdd(P.n_singular, 1);
   }
 #pragma unroll
-  for (int j = 0; j < 36; ++j) P.CT[(size_t)j * ns + i] = G[j];
+  for (int j = 0; j < 36; ++j) P.CT[SIC_CT_INDEX(j, i)] = G[j];
 }
 
 // CT <- C, eps_rhs <- 0 (operator of solve_elastic_response, MomentumEquation.py:892-923)
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_elastic_tangent(sic_proble
       double v = 0.0;
       if (r == c) v = (r < 3) ? c11 : c44;
       else if (r < 3 && c < 3) v = c12;
-      P.CT[(size_t)(r * 6 + c) * ns + i] = v;
+      P.CT[SIC_CT_INDEX(r * 6 + c, i)] = v;
     }
   }
 #pragma unroll
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_post(sic_problem_t P, cons
 #pragma unroll
       for (int c = 0; c < 6; ++c) d[c] = eps[c] - er[c];
 #pragma unroll
-      for (int j = 0; j < 36; ++j) CT[j] = P.CT[(size_t)j * ns + i];
+      for (int j = 0; j < 36; ++j) CT[j] = P.CT[SIC_CT_INDEX(j, i)];
       ddot66(CT, d, sig);
       store6(P.sig, ns, i, sig);
     } else {

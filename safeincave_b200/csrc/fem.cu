@@ -1,36 +1,34 @@
 // fem.cu — hot-path part (2): matrix-free tangent operator, RHS, block-Jacobi blocks, Neumann loads.
-#include "fem.cuh"
+#include "ebe_tma.cuh"
 
 namespace sic {
 
-// y += K x  (MODE 0)   or   r += sum_e V B^T W CT (eps_rhs - B x0)  (MODE 1)
+// y += K x  (MODE 0)   or   r += sum_e V B^T W CT (eps_rhs - B x0)  (MODE 1); TMA-staged tiles (ebe_tma.cuh)
+#ifndef SIC_EBE_IMPL
+#define SIC_EBE_IMPL 3
+#endif
+#if SIC_EBE_IMPL == 3
 template <int MODE>
-__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe(sic_problem_t P, const double* __restrict__ x,
-                                                        double* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_cells) return;
-  CellGeom c;
-  load_geom(P, i, c);
-  double ua[12];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) ua[3 * a + j] = __ldg(x + 3 * (size_t)c.node[a] + j);
-  }
-  double eps[6], sig[6], f[12];
-  strain_from_nodal(c, ua, eps);
-  if (MODE == 1) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) eps[k] = P.eps_rhs[(size_t)k * P.cell_stride + i] - eps[k];
-  }
-  stress_from_CT(P, i, eps, sig);
-  forces(c, sig, f);
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) atomicAdd(y + 3 * (size_t)c.node[a] + j, f[3 * a + j]);
-  }
+__global__ void __launch_bounds__(128, 3) k_ebe(sic_problem_t P, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double f_s[12][SIC_TILE_CELLS];
+  ebe_tile_scatter<MODE>(P, x, y, f_s);
 }
+#define SIC_EBE_LAUNCH(MODE, p, xin, yout, st) \
+  k_ebe<MODE><<<blocks_for((p)->n_cells, 128), 128, 0, st>>>(*(p), xin, yout)
+#else
+template <int MODE>
+__global__ void __launch_bounds__(SIC_TILE, 2) k_ebe(sic_problem_t P, const double* __restrict__ x,
+                                                    double* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<MODE>& sm = *reinterpret_cast<TileSmem<MODE>*>(smem_raw);
+  ebe_tiles<MODE>(P, x, y, sm);
+}
+#define SIC_EBE_LAUNCH(MODE, p, xin, yout, st)                                                     \
+  do {                                                                                             \
+    ebe_allow_smem(k_ebe<MODE>, sizeof(TileSmem<MODE>));                                           \
+    k_ebe<MODE><<<ebe_grid((p)->n_cells), SIC_TILE, sizeof(TileSmem<MODE>), st>>>(*(p), xin, yout); \
+  } while (0)
+#endif
 
 __global__ void k_mask_copy(int n, double* __restrict__ y, const double* __restrict__ x,
                             const uint8_t* __restrict__ fixed) {
@@ -55,7 +53,7 @@ __global__ void __launch_bounds__(SIC_EBE_THREADS) k_diag_blocks(sic_problem_t P
   load_geom(P, i, c);
   double CT[36];
 #pragma unroll
-  for (int j = 0; j < 36; ++j) CT[j] = __ldg(P.CT + (size_t)j * ns + i);
+  for (int j = 0; j < 36; ++j) CT[j] = __ldg(P.CT + SIC_CT_INDEX(j, i));
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const double gx = c.g[3 * a], gy = c.g[3 * a + 1], gz = c.g[3 * a + 2];
@@ -154,7 +152,7 @@ extern "C" int sic_apply(const sic_problem_t* p, const double* x, double* y, con
   cudaStream_t st = (cudaStream_t)stream;
   const int nd = 3 * p->n_nodes;
   if (int rc = sic_check_cuda(cudaMemsetAsync(y, 0, sizeof(double) * nd, st), "memset y")) return rc;
-  if (p->n_cells > 0) k_ebe<0><<<blocks_for(p->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*p, x, y);
+  if (p->n_cells > 0) SIC_EBE_LAUNCH(0, p, x, y, st);
   if (fixed && nd > 0) k_mask_copy<<<blocks_for(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, y, x, fixed);
   return sic_check_launch("sic_apply");
 }
@@ -166,7 +164,7 @@ extern "C" int sic_residual0(const sic_problem_t* p, const double* b_ext, const 
   const int nd = 3 * p->n_nodes;
   // element part first (partial on interface nodes -> summed over ranks), then the consistent b_ext
   if (int rc = sic_check_cuda(cudaMemsetAsync(r, 0, sizeof(double) * nd, st), "memset r")) return rc;
-  if (p->n_cells > 0) k_ebe<1><<<blocks_for(p->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*p, x0, r);
+  if (p->n_cells > 0) SIC_EBE_LAUNCH(1, p, x0, r, st);
   if (int rc = sic_check_launch("k_ebe<1>")) return rc;
   if (int rc = sic_halo_sum(halo, r, 3, stream)) return rc;
   if (nd > 0) k_add_mask<<<blocks_for(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, r, b_ext, fixed);

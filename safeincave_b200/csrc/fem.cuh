@@ -53,7 +53,7 @@ __device__ __forceinline__ void stress_from_CT(const sic_problem_t& P, int i, co
   for (int r = 0; r < 6; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s += __ldg(P.CT + (size_t)(r * 6 + k) * ns + i) * eps[k];
+    for (int k = 0; k < 6; ++k) s += __ldg(P.CT + SIC_CT_INDEX(r * 6 + k, i)) * eps[k];
     sig[r] = s;
   }
 }
@@ -67,6 +67,129 @@ __device__ __forceinline__ void forces(const CellGeom& c, const double s[6], dou
     f[3 * a + 1] = c.vol * (s[3] * gx + s[1] * gy + s[5] * gz);
     f[3 * a + 2] = c.vol * (s[4] * gx + s[5] * gy + s[2] * gz);
   }
+}
+
+// ---- operator, version 3: one thread per cell with FRONT-BATCHED loads ---------------------------
+// ptxas, left alone, interleaves the 53 independent per-cell loads with the FP64 math that consumes
+// them (version 1: few loads in flight per warp, DRAM at 34 % of peak).  Here every load is an
+// `asm volatile` statement, which the compiler may not reorder against the others: the 4 node ids,
+// 12 gradients, the volume and all 36 C_T entries are issued back to back (53 loads = 13.5 KB in
+// flight per warp), then the 12 gathers of x, and only then the arithmetic.
+__device__ __forceinline__ double ldg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <int MODE>   // 0: y += K x ; 1: r += sum V B^T W CT (eps_rhs - B x0).  Returns V eps:sigma.
+__device__ __forceinline__ double ebe_cell_batched(const sic_problem_t& P, int i, const double* __restrict__ x,
+                                                   double* __restrict__ y, double* f_out = nullptr) {
+  const size_t ns = (size_t)P.cell_stride;
+  int node[4];
+  double g[12], CT[36], er[6], ua[12];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
+  const double vol = ldg_f64(P.vol + i);
+  const double* ct = P.CT + SIC_CT_INDEX(0, i);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) CT[k] = ldg_f64(ct + k * SIC_TILE_CELLS);
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+#ifdef SIC_DBG_NOGATHER
+    for (int j = 0; j < 3; ++j) ua[3 * a + j] = 1e-3 * (double)(node[a] & 7) + j;
+#else
+    for (int j = 0; j < 3; ++j) ua[3 * a + j] = ldg_f64(x + 3 * (size_t)node[a] + j);
+#endif
+  }
+  double exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
+    const double ux = ua[3 * a], uy = ua[3 * a + 1], uz = ua[3 * a + 2];
+    exx += ux * gx; eyy += uy * gy; ezz += uz * gz;
+    exy += ux * gy + uy * gx; exz += ux * gz + uz * gx; eyz += uy * gz + uz * gy;
+  }
+  double eps[6] = {exx, eyy, ezz, 0.5 * exy, 0.5 * exz, 0.5 * eyz};
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) eps[k] = er[k] - eps[k];
+  }
+  double s[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += CT[r * 6 + k] * eps[k];
+    s[r] = acc;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
+    const double fx = vol * (s[0] * gx + s[3] * gy + s[4] * gz);
+    const double fy = vol * (s[3] * gx + s[1] * gy + s[5] * gz);
+    const double fz = vol * (s[4] * gx + s[5] * gy + s[2] * gz);
+    if (f_out) {                       // staged scatter: the caller sums per unique node in shared memory
+      f_out[3 * a + 0] = fx; f_out[3 * a + 1] = fy; f_out[3 * a + 2] = fz;
+    } else {
+      double* ya = y + 3 * (size_t)node[a];
+      atomicAdd(ya + 0, fx); atomicAdd(ya + 1, fy); atomicAdd(ya + 2, fz);
+    }
+  }
+  return vol * ((eps[0] * s[0] + eps[1] * s[1] + eps[2] * s[2]) + 2.0 * (eps[3] * s[3] + eps[4] * s[4] + eps[5] * s[5]));
+}
+
+// ---- operator, version 4: version 3 + shared-memory staged scatter ------------------------------
+// A/B measurement on 918k cells (scripts/apply_microbench.py): the streaming part of version 3 runs at
+// 6.3 TB/s (96 % of the measured HBM peak) when the 12 global FP64 atomics per cell are removed, and at
+// 3.9 TB/s with them: the scatter, not the loads, bounds the kernel.  Here a CTA handles one tile of 128
+// cells, parks the 12 nodal forces of each cell in shared memory, and a second phase sums them per UNIQUE
+// node of the tile (precomputed plan, sic_problem_t.tile_*), issuing one plain store per tile-interior
+// node component and one atomic per shared node component: ~5-6x fewer global RMWs, and none contended
+// inside the tile.  blockDim.x must be SIC_TILE_CELLS; f_s is double[12][128] in shared memory.
+template <int MODE>
+__device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const double* __restrict__ x,
+                                                   double* __restrict__ y, double (*f_s)[SIC_TILE_CELLS]) {
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int i = tile * SIC_TILE_CELLS + tid;
+  double f[12], energy = 0.0;
+  if (i < P.n_cells) energy = ebe_cell_batched<MODE>(P, i, x, y, f);
+  else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) f[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) f_s[k][tid] = f[k];
+  __syncthreads();
+  const int q0 = __ldg(P.tile_ptr + tile), q1 = __ldg(P.tile_ptr + tile + 1);
+  const int nint = __ldg(P.tile_nint + tile);
+  for (int q = q0 + tid; q < q1; q += SIC_TILE_CELLS) {
+    const int node = __ldg(P.tile_nodes + q);
+    const int e0 = __ldg(P.ent_ptr + q), e1 = __ldg(P.ent_ptr + q + 1);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int e = e0; e < e1; ++e) {
+      const int c = (int)__ldg(P.ent + e);
+      const int cell = c >> 2, slot = c & 3;
+      sx += f_s[3 * slot + 0][cell];
+      sy += f_s[3 * slot + 1][cell];
+      sz += f_s[3 * slot + 2][cell];
+    }
+    double* yn = y + 3 * (size_t)node;
+    if (q - q0 < nint) { yn[0] = sx; yn[1] = sy; yn[2] = sz; }            // only this tile touches the node
+    else { atomicAdd(yn + 0, sx); atomicAdd(yn + 1, sy); atomicAdd(yn + 2, sz); }
+  }
+  return energy;
 }
 
 // Deterministic grid-wide reduction of NV values: every block deposits its partial sums, the last
@@ -121,6 +244,30 @@ __device__ __forceinline__ void grid_reduce(double v[NV], double* __restrict__ p
       tot[k] = s;
     }
     fin(tot);
+  }
+}
+
+// Block partial sums only (no ticket): the operator kernel runs ~50 waves of small CTAs, and making each
+// CTA wait for an atomic round trip (grid_reduce's ticket) held its SM slot ~1.5 us per wave.  The partials
+// are summed by k_sum_partials below, in block order (deterministic).
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_partials(double v[NV], double* __restrict__ partials) {
+  __shared__ double shp[NV][THREADS / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (l == 0) shp[k][w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < THREADS / 32; ++j) s += shp[k][j];
+      partials[(size_t)blockIdx.x * NV + k] = s;
+    }
   }
 }
 

@@ -17,7 +17,7 @@
 #include <math.h>
 #include <string.h>
 
-#include "fem.cuh"
+#include "ebe_tma.cuh"
 
 namespace sic {
 
@@ -90,49 +90,64 @@ struct Fin {  // what the last block does with the grid totals
   }
 };
 
-__device__ __forceinline__ void ebe_cell(const sic_problem_t& P, int i, const double* __restrict__ x,
-                                         double* __restrict__ y, double* energy) {
-  CellGeom c;
-  load_geom(P, i, c);
-  double ua[12];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) ua[3 * a + j] = __ldg(x + 3 * (size_t)c.node[a] + j);
-  }
-  double eps[6], sig[6], f[12];
-  strain_from_nodal(c, ua, eps);
-  stress_from_CT(P, i, eps, sig);
-  forces(c, sig, f);
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) atomicAdd(y + 3 * (size_t)c.node[a] + j, f[3 * a + j]);
-  }
-  // x_e^T K_e x_e = V eps : sigma  (shear terms counted twice)
-  if (energy)
-    *energy = c.vol * ((eps[0] * sig[0] + eps[1] * sig[1] + eps[2] * sig[2]) +
-                       2.0 * (eps[3] * sig[3] + eps[4] * sig[4] + eps[5] * sig[5]));
+#ifndef SIC_EBE_IMPL
+#define SIC_EBE_IMPL 3   /* 3: one thread per cell, front-batched loads (fem.cuh); 2: TMA-staged tiles (ebe_tma.cuh) */
+#endif
+
+#if SIC_EBE_IMPL == 3
+#define SIC_EBE_BLOCK 128
+__global__ void __launch_bounds__(SIC_EBE_BLOCK, 3) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+                                                             double* __restrict__ y, Fin fin,
+                                                             double* __restrict__ partials, unsigned* counter) {
+  if (fin.S->done) return;
+  __shared__ double f_s[12][SIC_TILE_CELLS];
+  double v[1] = {ebe_tile_scatter<0>(P, x, y, f_s)};
+  block_partials<1, SIC_EBE_BLOCK>(v, partials);     // summed by k_sum_partials (no per-CTA ticket wait)
 }
 
-// ---- operator kernel with the fused p.Kp reduction --------------------------------------------
-__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
-                                                            double* __restrict__ y, Fin fin,
-                                                            double* __restrict__ partials, unsigned* counter) {
+// one block: sum n block partials in order, then run the scalar recurrence
+__global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict__ partials, int n, Fin fin) {
   if (fin.S->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double v[1] = {0.0};
-  if (i < P.n_cells) ebe_cell(P, i, x, y, &v[0]);
-  grid_reduce<1, SIC_EBE_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n; k += 1024) a += partials[k];
+  a = warp_sum(a);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[1] = {0.0};
+    for (int k = 0; k < 32; ++k) tot[0] += sh[k];
+    fin.run<1>(tot);
+  }
+}
+__global__ void __launch_bounds__(SIC_EBE_BLOCK, 3) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
+                                                               double* __restrict__ y, const Scal* S) {
+  if (S->done) return;
+  __shared__ double f_s[12][SIC_TILE_CELLS];
+  ebe_tile_scatter<0>(P, x, y, f_s);
+}
+#else
+// ---- operator kernel (TMA-staged persistent tiles, ebe_tma.cuh) with the fused p.Kp reduction ----
+__global__ void __launch_bounds__(SIC_TILE, 2) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+                                                        double* __restrict__ y, Fin fin,
+                                                        double* __restrict__ partials, unsigned* counter) {
+  if (fin.S->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<0>& sm = *reinterpret_cast<TileSmem<0>*>(smem_raw);
+  double v[1] = {ebe_tiles<0>(P, x, y, sm)};
+  grid_reduce<1, SIC_TILE>(v, partials, counter, [&](const double* tot) { fin.run<1>(tot); });
 }
 
 // plain operator (no dot), skipping when converged
-__global__ void __launch_bounds__(SIC_EBE_THREADS) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
-                                                              double* __restrict__ y, const Scal* S) {
+__global__ void __launch_bounds__(SIC_TILE, 2) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
+                                                          double* __restrict__ y, const Scal* S) {
   if (S->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n_cells) ebe_cell(P, i, x, y, nullptr);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<0>& sm = *reinterpret_cast<TileSmem<0>*>(smem_raw);
+  ebe_tiles<0>(P, x, y, sm);
 }
+#endif
 
 __device__ __forceinline__ void precond3(const double* __restrict__ dinv, size_t n, const double r[3], double z[3]) {
   const double* d = dinv + 9 * n;
@@ -422,8 +437,6 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   const int nn = p->n_nodes, nd = 3 * nn, nc = p->n_cells;
   const int64_t part = partial_slots(nn);
-  if (2 * ((int64_t)blocks_for(nc, SIC_EBE_THREADS) + 1) > part)
-    return sic_fail("sic_ksp_solve: more than 8 cells per node on average");
   if (!g_host_scal) {
     if (int rc = sic_check_cuda(cudaMallocHost((void**)&g_host_scal, sizeof(Scal)), "cudaMallocHost")) return rc;
   }
@@ -438,8 +451,23 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
   if (int rc = sic_check_cuda(cudaMemsetAsync(work, 0, sizeof(double) * (SIC_WS_HEADER + SIC_WS_COUNTERS), st),
                               "memset ksp header"))
     return rc;
-  const int cb = blocks_for(nc, SIC_EBE_THREADS), nb = blocks_for(nn, SIC_VEC_THREADS),
-            db = blocks_for(nd, SIC_VEC_THREADS);
+  const int nb = blocks_for(nn, SIC_VEC_THREADS), db = blocks_for(nd, SIC_VEC_THREADS);
+#if SIC_EBE_IMPL == 3
+  const int cb = blocks_for(nc, SIC_EBE_BLOCK);
+  const size_t esm = 0;
+  const int ebt = SIC_EBE_BLOCK;
+  static bool smem_ok = true;
+#else
+  const int cb = ebe_grid(nc);
+  const size_t esm = sizeof(TileSmem<0>);
+  const int ebt = SIC_TILE;
+  static bool smem_ok = false;
+#endif
+  if (!smem_ok) {
+    if (int rc = sic_check_cuda(ebe_allow_smem(k_ebe_dot, esm), "smem attr k_ebe_dot")) return rc;
+    if (int rc = sic_check_cuda(ebe_allow_smem(k_ebe_plain, esm), "smem attr k_ebe_plain")) return rc;
+    smem_ok = true;
+  }
   const int check = ksp->check_every > 0 ? ksp->check_every : 25;
   const int guess = ksp->guess_nonzero ? 1 : 0;
   const double rtol = ksp->rtol, atol = ksp->atol;
@@ -475,8 +503,11 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
       const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
         timer.begin(k);
-        k_ebe_dot<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, pp, q, fin(OP_CG_ALPHA), partials, counter);
+        k_ebe_dot<<<cb, ebt, esm, st>>>(*p, pp, q, fin(OP_CG_ALPHA), partials, counter);
         timer.end(k);
+#if SIC_EBE_IMPL == 3
+        k_sum_partials<<<1, 1024, 0, st>>>(partials, cb, fin(OP_CG_ALPHA));
+#endif
         if (multi) {
           if (int rc = sic_halo_sum(halo, q, 3, stream)) return rc;
           if (int rc = reduce(OP_CG_ALPHA, 1, 1)) return rc;
@@ -502,13 +533,13 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
       const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
       for (int k = 0; k < batch; ++k) {
         timer.begin(k);
-        k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, y, v, S);
+        k_ebe_plain<<<cb, ebt, esm, st>>>(*p, y, v, S);
         timer.end(k);
         if (int rc = sic_halo_sum(halo, v, 3, stream)) return rc;
         k_bi_dot1<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, rh, v, fixed, w, fin(OP_BI_ALPHA), partials, counter);
         if (int rc = reduce(OP_BI_ALPHA, 1, 1)) return rc;
         k_bi_s<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, v, s, z, t, dinv, fixed, S);
-        k_ebe_plain<<<cb, SIC_EBE_THREADS, 0, st>>>(*p, z, t, S);
+        k_ebe_plain<<<cb, ebt, esm, st>>>(*p, z, t, S);
         if (int rc = sic_halo_sum(halo, t, 3, stream)) return rc;
         k_bi_dot2<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, t, s, fixed, w, fin(OP_BI_OMEGA), partials, counter + 1);
         if (int rc = reduce(OP_BI_OMEGA, 2, 1)) return rc;

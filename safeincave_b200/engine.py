@@ -79,7 +79,7 @@ class Engine:
         coords = torch.as_tensor(coords, dtype=torch.float64).to(self.device).contiguous()
         cells = torch.as_tensor(cells).to(self.device, dtype=torch.int64).contiguous()
         self.N, self.M = int(cells.shape[0]), int(coords.shape[0])
-        self.ns = max(32, (self.N + 31) // 32 * 32)
+        self.ns = max(128, (self.N + 127) // 128 * 128)   # whole 128-cell tiles for the TMA-staged operator
         self.coords = coords
         grad, vol = tet_geometry(coords, cells)
         # orientation does not matter for P1 gradients; degenerate cells are a mesh error
@@ -92,9 +92,17 @@ class Engine:
         self.grad[:, :self.N] = grad.reshape(self.N, 12).t()
         self.vol = torch.zeros(ns, dtype=torch.float64, device=dev)
         self.vol[:self.N] = vol
+        # the same geometry, tiled for the operator kernel (sic_geom_tile_t: grad[12][128], vol[128], conn[4][128])
+        nt = ns // 128
+        self.geom_tiles = torch.zeros((nt, 1920), dtype=torch.float64, device=dev)
+        self.geom_tiles[:, :1536] = self.grad.reshape(12, nt, 128).permute(1, 0, 2).reshape(nt, 1536)
+        self.geom_tiles[:, 1536:1664] = self.vol.reshape(nt, 128)
+        self.geom_tiles[:, 1664:].view(torch.int32).copy_(self.conn.reshape(4, nt, 128).permute(1, 0, 2).reshape(nt, 512))
+        self._build_scatter_plan()
         z = lambda rows: torch.zeros((rows, ns), dtype=torch.float64, device=dev)
         self.sig, self.sig_k, self.eps, self.eps_prev = z(6), z(6), z(6), z(6)
-        self.CT, self.eps_rhs = z(36), z(6)
+        self.eps_rhs = z(6)
+        self.CT = torch.zeros((ns // 128, 36, 128), dtype=torch.float64, device=dev)    # tiled, SIC_CT_INDEX
         self.T = torch.zeros(ns, dtype=torch.float64, device=dev)     # MomentumEquation.py:116-117
         self.T0 = torch.zeros(ns, dtype=torch.float64, device=dev)
         self.n_singular = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -113,6 +121,38 @@ class Engine:
         self.halo = None                    # L.SicHalo when the mesh is partitioned over several GPUs
         self._halo_keep = None
         self.op_ms, self.op_samples, self.op_launches = 0.0, 0, 0
+
+    def _build_scatter_plan(self):
+        """Per tile of 128 cells: unique nodes (tile-interior first) and, per unique node, its (cell, slot)
+        references inside the tile (sic_problem_t.tile_ptr / tile_nint / tile_nodes / ent_ptr / ent)."""
+        dev, ns, M = self.device, self.ns, max(self.M, 1)
+        nt = ns // 128
+        conn = self.conn.long()                                   # (4, ns); padded cells reference node 0
+        cell = torch.arange(ns, device=dev)
+        tile = (cell // 128).repeat(4)                            # ref order: slot-major
+        local = ((cell % 128) * 4).repeat(4) + torch.arange(4, device=dev).repeat_interleave(ns)
+        node = conn.reshape(-1)
+        total_refs = torch.bincount(node, minlength=M)            # references of each node in the whole mesh
+        pair = tile * M + node
+        upair, inv, cnt = torch.unique(pair, return_inverse=True, return_counts=True)
+        utile, unode = upair // M, upair % M
+        interior = cnt == total_refs[unode]
+        # order the unique (tile,node) pairs: by tile, interior first, then node id
+        key = (utile * 2 + (~interior).long()) * M + unode
+        order = torch.argsort(key)
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.numel(), device=dev)
+        new_inv = rank[inv]                                       # unique index of every reference, in the new order
+        ref_order = torch.argsort(new_inv, stable=True)
+        self.ent = local[ref_order].to(torch.int16).contiguous()  # values < 512 fit; read back as uint16
+        cnt_o = cnt[order]
+        self.ent_ptr = torch.zeros(order.numel() + 1, dtype=torch.int32, device=dev)
+        self.ent_ptr[1:] = torch.cumsum(cnt_o, 0).to(torch.int32)
+        self.tile_nodes = unode[order].to(torch.int32).contiguous()
+        per_tile = torch.bincount(utile, minlength=nt)
+        self.tile_ptr = torch.zeros(nt + 1, dtype=torch.int32, device=dev)
+        self.tile_ptr[1:] = torch.cumsum(per_tile, 0).to(torch.int32)
+        self.tile_nint = torch.bincount(utile[interior], minlength=nt).to(torch.int32).contiguous()
 
     # ------------------------------------------------------------------ material
     def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False):
@@ -136,6 +176,9 @@ class Engine:
         P.abi_version = L.SIC_ABI_VERSION
         P.n_cells, P.cell_stride, P.n_nodes = self.N, self.ns, self.M
         P.conn, P.grad, P.vol = _ptr(self.conn), _ptr(self.grad), _ptr(self.vol)
+        P.geom_tiles = _ptr(self.geom_tiles)
+        P.tile_ptr, P.tile_nint, P.tile_nodes = _ptr(self.tile_ptr), _ptr(self.tile_nint), _ptr(self.tile_nodes)
+        P.ent_ptr, P.ent = _ptr(self.ent_ptr), _ptr(self.ent)
         P.mat_id, P.mat_table = _ptr(self.mat_id), _ptr(self.mat_table)
         P.n_rows, P.row_len = int(self.mat_table.shape[0]), int(self.mat_table.shape[1])
         P.spring_off, P.n_thermo, P.thermo_off = self.spring_off, self.n_thermo, self.thermo_off
@@ -263,7 +306,7 @@ class Engine:
         ksp.guess_nonzero = 1 if guess_nonzero else 0
         L.check(self.lib.sic_ksp_solve(self._pp(), ctypes.byref(ksp), _ptr(b_ext), _ptr(x), _ptr(fixed), _ptr(dinv),
                                        _ptr(w), self._ph(), self._stream()), "sic_ksp_solve")
-        per_it = 3 if method == L.KSP_CG else 7
+        per_it = 4 if method == L.KSP_CG else 7
         self.launches += 3 + per_it * int(ksp.iterations)
         self.op_ms += float(ksp.op_ms)
         self.op_samples += int(ksp.op_samples)
@@ -276,6 +319,16 @@ class Engine:
         return out.value
 
     # ------------------------------------------------------------------ host <-> device helpers
+    def get_CT(self):
+        """(N,6,6) host numpy copy of the tiled tangent."""
+        return self.CT.permute(0, 2, 1).reshape(self.ns, 36)[:self.N].reshape(self.N, 6, 6).cpu().numpy()
+
+    def put_CT(self, ct):
+        """Upload an (N,6,6) tangent into the tiled device layout."""
+        t = torch.zeros((self.ns, 36), dtype=torch.float64, device=self.device)
+        t[:self.N] = torch.as_tensor(np.ascontiguousarray(ct), dtype=torch.float64).reshape(self.N, 36).to(self.device)
+        self.CT.copy_(t.reshape(self.ns // 128, 128, 36).permute(0, 2, 1))
+
     def put6(self, dst, v6):
         """(N,6) host/any array -> SoA (6, ns) device tensor."""
         t = torch.as_tensor(np.ascontiguousarray(v6), dtype=torch.float64).to(self.device)

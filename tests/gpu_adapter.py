@@ -108,12 +108,12 @@ class GpuMaterial:
     @property
     def CT(self):
         e = self.eng
-        return e.CT[:, :e.N].t().reshape(e.N, 6, 6).cpu().numpy()
+        return e.get_CT()
 
     @CT.setter
     def CT(self, v):
         e = self.eng
-        e.CT[:, :e.N] = torch.as_tensor(np.asarray(v).reshape(e.N, 36), dtype=torch.float64).t().to(e.device)
+        e.put_CT(np.asarray(v))
 
     @property
     def eps_rhs(self):

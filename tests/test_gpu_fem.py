@@ -59,7 +59,7 @@ def test_operator_rhs_blocks_strain(sf, grid_name):
     rng = np.random.default_rng(1)
     CT = random_tangent(N, 2)
     eps_rhs = 1e-4 * rng.standard_normal((N, 6))
-    eng.CT[:, :N] = torch.as_tensor(CT.reshape(N, 36)).t().to(eng.device)
+    eng.put_CT(CT)
     eng.put6(eng.eps_rhs, eps_rhs)
     K = fem.assemble_K(tm.coords, tm.cells, CT)
     x = rng.standard_normal(3 * M) * 1e-3
@@ -137,7 +137,7 @@ def test_krylov_solve_matches_direct(sf, method, sym):
     N = eng.N
     CT = random_tangent(N, 5, sym=sym) if not sym else oc.iso_matrix(102e9 * np.ones(N), 0.3 * np.ones(N))
     eps_rhs = 1e-5 * np.random.default_rng(3).standard_normal((N, 6))
-    eng.CT[:, :N] = torch.as_tensor(CT.reshape(N, 36)).t().to(eng.device)
+    eng.put_CT(CT)
     eng.put6(eng.eps_rhs, eps_rhs)
     eq.bc.update_dirichlet(0.0)
     eq.bc.update_neumann(0.0)
