@@ -9,7 +9,7 @@ post-solve phase, convergence measure -- plus the commit, excluding p/q smoothin
 
 Workload: BASELINE.json configs[1] physics (grids/cavern_regular, cyclic gas pressure, fully implicit
 theta = 0, Spring + DislocationCreep, dt = 2 h) on the cavern_regular grid red-refined `--levels`
-times (configs[4]: 14 346 * 8^L cells; L = 0 is the reference's own grid).  Synthetic refinement,
+times (configs[4]: 14 346 * 8^L cells; L = 0 is the reference's own grid; default L = 3 = 7 345 152 cells).  Synthetic refinement,
 random nothing: loads, materials and BCs are the example's.
 
 metric  cell-updates/s = n_cells * (Newton iterations executed) / (time of the steps), whole job.
@@ -38,11 +38,13 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--levels", type=int, default=2, help="red-refinement levels of cavern_regular (14 346 * 8^L cells)")
+    ap.add_argument("--levels", type=int, default=3, help="red-refinement levels of cavern_regular (14 346 * 8^L cells)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ksp", default="cg")
     ap.add_argument("--rtol", type=float, default=1e-10)
-    ap.add_argument("--warm-start", type=int, default=0, help="1: Krylov initial guess = previous solution")
+    ap.add_argument("--warm-start", type=int, default=1,
+                    help="1: Krylov initial guess = previous Newton iterate (KSP.setInitialGuessNonzero), rtol still "
+                         "relative to the zero-guess residual as in PETSc; 0: zero guess every solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -258,8 +260,9 @@ def run_b200(args):
     achieved = bytes_per_launch / (op_ms * 1e-3) / 1e9 if op_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.isfile(tpath):
-        traffic = json.load(open(tpath)).get(str(N))
+    if os.path.isfile(tpath):        # ncu --set full capture at 918 144 cells; DRAM traffic scales with the cell count
+        ref = json.load(open(tpath))
+        traffic = int(ref["918144"] * N_loc / 918144)
     roofline = {"bound": "hbm", "kernel": "k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,

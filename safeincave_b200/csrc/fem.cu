@@ -9,9 +9,12 @@ namespace sic {
 #endif
 #if SIC_EBE_IMPL == 3
 template <int MODE>
-__global__ void __launch_bounds__(128, 3) k_ebe(sic_problem_t P, const double* __restrict__ x, double* __restrict__ y) {
-  __shared__ double f_s[12][SIC_TILE_CELLS];
-  ebe_tile_scatter<MODE>(P, x, y, f_s);
+#ifndef SIC_EBE_MINBLOCKS
+#define SIC_EBE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, SIC_EBE_MINBLOCKS) k_ebe(sic_problem_t P, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ TileScratch sc;
+  ebe_tile_scatter<MODE>(P, x, y, sc);
 }
 #define SIC_EBE_LAUNCH(MODE, p, xin, yout, st) \
   k_ebe<MODE><<<blocks_for((p)->n_cells, 128), 128, 0, st>>>(*(p), xin, yout)

@@ -158,35 +158,105 @@ __device__ __forceinline__ double ebe_cell_batched(const sic_problem_t& P, int i
 // node of the tile (precomputed plan, sic_problem_t.tile_*), issuing one plain store per tile-interior
 // node component and one atomic per shared node component: ~5-6x fewer global RMWs, and none contended
 // inside the tile.  blockDim.x must be SIC_TILE_CELLS; f_s is double[12][128] in shared memory.
+struct TileScratch {                      // shared memory of one operator CTA (17.4 KB)
+  double f[12][SIC_TILE_CELLS];           // nodal forces of the tile's cells
+  unsigned short ent[4 * SIC_TILE_CELLS]; // the tile's (cell,slot) references, grouped by unique node
+  int nodes[4 * SIC_TILE_CELLS];          // unique node ids (tile-interior first)
+  int eoff[4 * SIC_TILE_CELLS + 1];       // per unique node: offset into ent
+};
+
 template <int MODE>
 __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const double* __restrict__ x,
-                                                   double* __restrict__ y, double (*f_s)[SIC_TILE_CELLS]) {
+                                                   double* __restrict__ y, TileScratch& sc,
+                                                   const int* done_flag = nullptr) {
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int i = tile * SIC_TILE_CELLS + tid;
-  double f[12], energy = 0.0;
-  if (i < P.n_cells) energy = ebe_cell_batched<MODE>(P, i, x, y, f);
-  else {
+  const size_t ns = (size_t)P.cell_stride;
+  // ---- phase 0: every load of the tile is issued up front (asm volatile keeps program order) ----------
+  int q0, q1, nint, done = 0;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(q0) : "l"(P.tile_ptr + tile));
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(q1) : "l"(P.tile_ptr + tile + 1));
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(nint) : "l"(P.tile_nint + tile));
+  if (done_flag) asm volatile("ld.global.s32 %0, [%1];" : "=r"(done) : "l"(done_flag));
+  unsigned ent_lo, ent_hi;   // this thread's 4 of the tile's 512 scatter references (8 bytes)
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(ent_lo), "=r"(ent_hi)
+               : "l"(P.ent + (size_t)tile * 4 * SIC_TILE_CELLS + 4 * tid));
+  int node[4];
+  double g[12], CT[36], er[6], ua[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) f[k] = 0.0;
+  for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
+  const double vol = ldg_f64(P.vol + i);
+  const double* ct = P.CT + SIC_CT_INDEX(0, i);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) CT[k] = ldg_f64(ct + k * SIC_TILE_CELLS);
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
   }
 #pragma unroll
-  for (int k = 0; k < 12; ++k) f_s[k][tid] = f[k];
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ua[3 * a + j] = ldg_f64(x + 3 * (size_t)node[a] + j);
+  }
+  // scatter plan of the tile -> shared memory (depends only on q0, requested first)
+  const int nq = q1 - q0, ebase = tile * 4 * SIC_TILE_CELLS;
+  for (int k = tid; k < nq; k += SIC_TILE_CELLS) {
+    int nd, eo;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(nd) : "l"(P.tile_nodes + q0 + k));
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(eo) : "l"(P.ent_ptr + q0 + k));
+    sc.nodes[k] = nd;
+    sc.eoff[k] = eo - ebase;
+  }
+  if (tid == 0) sc.eoff[nq] = 4 * SIC_TILE_CELLS;
+  reinterpret_cast<uint2*>(sc.ent)[tid] = make_uint2(ent_lo, ent_hi);
+  // ---- phase 1: the cell's arithmetic (cells of the padding compute zeros: their C_T, grad, vol are 0) --
+  double exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
+    const double ux = ua[3 * a], uy = ua[3 * a + 1], uz = ua[3 * a + 2];
+    exx += ux * gx; eyy += uy * gy; ezz += uz * gz;
+    exy += ux * gy + uy * gx; exz += ux * gz + uz * gx; eyz += uy * gz + uz * gy;
+  }
+  double eps[6] = {exx, eyy, ezz, 0.5 * exy, 0.5 * exz, 0.5 * eyz};
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) eps[k] = er[k] - eps[k];
+  }
+  double s[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += CT[r * 6 + k] * eps[k];
+    s[r] = acc;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
+    sc.f[3 * a + 0][tid] = vol * (s[0] * gx + s[3] * gy + s[4] * gz);
+    sc.f[3 * a + 1][tid] = vol * (s[3] * gx + s[1] * gy + s[5] * gz);
+    sc.f[3 * a + 2][tid] = vol * (s[4] * gx + s[5] * gy + s[2] * gz);
+  }
+  const double energy =
+      vol * ((eps[0] * s[0] + eps[1] * s[1] + eps[2] * s[2]) + 2.0 * (eps[3] * s[3] + eps[4] * s[4] + eps[5] * s[5]));
   __syncthreads();
-  const int q0 = __ldg(P.tile_ptr + tile), q1 = __ldg(P.tile_ptr + tile + 1);
-  const int nint = __ldg(P.tile_nint + tile);
-  for (int q = q0 + tid; q < q1; q += SIC_TILE_CELLS) {
-    const int node = __ldg(P.tile_nodes + q);
-    const int e0 = __ldg(P.ent_ptr + q), e1 = __ldg(P.ent_ptr + q + 1);
+  if (done) return 0.0;   // uniform over the grid: nothing is written once the solve has converged
+  // ---- phase 2: one global write per unique node of the tile, everything read from shared memory ------
+  for (int k = tid; k < nq; k += SIC_TILE_CELLS) {
+    const int e0 = sc.eoff[k], e1 = sc.eoff[k + 1];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int e = e0; e < e1; ++e) {
-      const int c = (int)__ldg(P.ent + e);
+      const int c = (int)sc.ent[e];
       const int cell = c >> 2, slot = c & 3;
-      sx += f_s[3 * slot + 0][cell];
-      sy += f_s[3 * slot + 1][cell];
-      sz += f_s[3 * slot + 2][cell];
+      sx += sc.f[3 * slot + 0][cell];
+      sy += sc.f[3 * slot + 1][cell];
+      sz += sc.f[3 * slot + 2][cell];
     }
-    double* yn = y + 3 * (size_t)node;
-    if (q - q0 < nint) { yn[0] = sx; yn[1] = sy; yn[2] = sz; }            // only this tile touches the node
+    double* yn = y + 3 * (size_t)sc.nodes[k];
+    if (k < nint) { yn[0] = sx; yn[1] = sy; yn[2] = sz; }                 // only this tile touches the node
     else { atomicAdd(yn + 0, sx); atomicAdd(yn + 1, sy); atomicAdd(yn + 2, sz); }
   }
   return energy;

@@ -96,12 +96,14 @@ struct Fin {  // what the last block does with the grid totals
 
 #if SIC_EBE_IMPL == 3
 #define SIC_EBE_BLOCK 128
-__global__ void __launch_bounds__(SIC_EBE_BLOCK, 3) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+#ifndef SIC_EBE_MINBLOCKS
+#define SIC_EBE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(SIC_EBE_BLOCK, SIC_EBE_MINBLOCKS) k_ebe_dot(sic_problem_t P, const double* __restrict__ x,
                                                              double* __restrict__ y, Fin fin,
                                                              double* __restrict__ partials, unsigned* counter) {
-  if (fin.S->done) return;
-  __shared__ double f_s[12][SIC_TILE_CELLS];
-  double v[1] = {ebe_tile_scatter<0>(P, x, y, f_s)};
+  __shared__ TileScratch sc;
+  double v[1] = {ebe_tile_scatter<0>(P, x, y, sc, &fin.S->done)};
   block_partials<1, SIC_EBE_BLOCK>(v, partials);     // summed by k_sum_partials (no per-CTA ticket wait)
 }
 
@@ -121,11 +123,10 @@ __global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict_
     fin.run<1>(tot);
   }
 }
-__global__ void __launch_bounds__(SIC_EBE_BLOCK, 3) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
+__global__ void __launch_bounds__(SIC_EBE_BLOCK, SIC_EBE_MINBLOCKS) k_ebe_plain(sic_problem_t P, const double* __restrict__ x,
                                                                double* __restrict__ y, const Scal* S) {
-  if (S->done) return;
-  __shared__ double f_s[12][SIC_TILE_CELLS];
-  ebe_tile_scatter<0>(P, x, y, f_s);
+  __shared__ TileScratch sc;
+  ebe_tile_scatter<0>(P, x, y, sc, &S->done);
 }
 #else
 // ---- operator kernel (TMA-staged persistent tiles, ebe_tma.cuh) with the fused p.Kp reduction ----
