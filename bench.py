@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--warm-start", type=int, default=1,
                     help="1: Krylov initial guess = previous Newton iterate (KSP.setInitialGuessNonzero), rtol still "
                          "relative to the zero-guess residual as in PETSc; 0: zero guess every solve")
+    ap.add_argument("--cgcg", type=int, default=0,
+                    help="1: Chronopoulos-Gear CG (one reduction per iteration); only sound for SYMMETRIC tangents -- it "
+                         "diverges on the reference's non-symmetric finite-difference tangent (SURVEY T3), hence off")
+    ap.add_argument("--max-it", type=int, default=0, help="debug: cap Krylov iterations per solve (timing experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,6 +198,10 @@ def run_b200(args):
         eq, sim = cases.build(case, grid, device=dev)
     sim.verbose = False
     eq.solver.initial_guess_nonzero = bool(args.warm_start)
+    eq.solver.single_reduction = bool(args.cgcg)
+    if args.max_it > 0:
+        eq.solver.respect_max_it, eq.solver.max_it = True, args.max_it
+        sim.maxiter = 3
     eng = eq.engine
     N, M = tm.n_cells, tm.n_nodes                        # global counts (the metric is whole-job)
     N_loc, M_loc = eng.N, eng.M
@@ -276,7 +284,7 @@ def run_b200(args):
         "config": {"workload": workload_name(args.levels, N), "n_cells": N, "n_nodes": M,
                    "cells_per_gpu": N_loc, "partition": "Morton-curve chunks, interface nodes duplicated, NCCL halo sum "
                    "+ 2 scalar allreduces per CG iteration" if world > 1 else "single GPU",
-                   "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp, "rtol": args.rtol,
+                   "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
                    "preconditioner": "nodal 3x3 block Jacobi", "warm_start": bool(args.warm_start),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
         "clocks": clk, "gpu_launches": launches, "roofline": roofline,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 4
+#define SIC_ABI_VERSION 5
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -172,7 +172,9 @@ typedef struct {
   const double* owner_w;   /* [n_nodes] 1.0 where this rank owns the node (lowest rank touching it), else 0.0 */
   double* send_buf;        /* >= 9 * n_shared_total doubles */
   double* recv_buf;        /* >= 9 * n_shared_total doubles */
-  void* comm;              /* from sic_comm_init */
+  void* comm;              /* from sic_comm_init (NCCL path) */
+  void* p2p;               /* from sic_p2p_create/connect, or NULL: if set, halo sums and scalar all-reduces are ONE
+                              kernel that stores straight into the peers' mailboxes over NVLink (no NCCL call) */
 } sic_halo_t;
 
 /* NCCL communicator over NVLink/NVSwitch (libnccl.so.2 is dlopen'ed on first use; single-GPU runs never touch it).
@@ -180,6 +182,21 @@ typedef struct {
 int sic_comm_unique_id(uint8_t* id128);
 int sic_comm_init(const uint8_t* id128, int rank, int n_ranks, void** comm);
 int sic_comm_destroy(void* comm);
+/* Peer-to-peer exchange over NVLink without NCCL.  Every rank owns a mailbox in its own HBM (cudaMalloc +
+ * cudaIpcGetMemHandle); peers map it (cudaIpcOpenMemHandle) and write their interface partial sums and their
+ * scalar partial sums directly into it, then raise a flag; the same kernel waits for the peers' flags and adds
+ * what arrived.  One launch replaces pack + ncclSend/ncclRecv group + unpack + ncclAllReduce.
+ *   sic_p2p_create  : allocate this rank's mailbox (capacity: cap_nodes interface nodes per peer), return its
+ *                     64-byte IPC handle in handle64
+ *   sic_p2p_connect : all_handles = n_ranks * 64 bytes gathered from every rank (e.g. torch.distributed.all_gather) */
+int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, uint8_t* handle64);
+int sic_p2p_connect(void* p2p, const uint8_t* all_handles);
+int sic_p2p_destroy(void* p2p);
+int sic_p2p_error(void* p2p);   /* 1 if a wait on a peer's flag timed out (synchronises the device) */
+/* halo sum of vec (ncomp values per node; ncomp = 0: none) fused with the sum over ranks of n_scal doubles at
+ * `scal` (device, in place; n_scal = 0: none). */
+int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double* scal, int n_scal, void* stream);
+
 /* vec[(node)*ncomp + c] += sum over the other ranks' copies, for every interface node (ncclSend/ncclRecv in one group). */
 int sic_halo_sum(const sic_halo_t* h, double* vec, int ncomp, void* stream);
 /* in-place sum over ranks of `count` device doubles. */
@@ -208,7 +225,14 @@ int sic_neumann(int n_tri, const int32_t* tri, const double* area_n, const int32
                 const double* coords, int n_bc, const double* bc_par, double* b, void* stream);
 
 /* ---- part (3): Krylov solve ---------------------------------------------------------------- */
-enum { SIC_KSP_CG = 1, SIC_KSP_BICGSTAB = 2 };
+enum {
+  SIC_KSP_CG = 1,        /* textbook preconditioned CG: two reductions per iteration */
+  SIC_KSP_BICGSTAB = 2,
+  SIC_KSP_CGCG = 3       /* Chronopoulos-Gear CG: the same iterates in exact arithmetic with ONE fused reduction per
+                            iteration (gamma = r.u, delta = u.Ku, ||r||^2).  SYMMETRIC operators only: measured to diverge
+                            on the non-symmetric finite-difference tangent of the creep elements, where
+                            textbook CG still converges; opt-in (KSP.single_reduction), never a default */
+};
 
 typedef struct {
   int32_t method;         /* SIC_KSP_* */

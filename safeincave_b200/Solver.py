@@ -35,6 +35,7 @@ class KSP:
         self.min_max_it = 200000
         self.check_every = 25
         self.initial_guess_nonzero = False
+        self.single_reduction = False      # cg -> Chronopoulos-Gear CG; symmetric (elastic) tangents only, see header
         self._its, self._rnorm, self._reason = 0, 0.0, 0
         self.total_iterations = 0
 
@@ -84,7 +85,10 @@ class KSP:
 
     # ---- used by LinearMomentum
     def method(self):
-        return L.KSP_CG if self._type.lower() == "cg" else L.KSP_BICGSTAB
+        t = self._type.lower()
+        if t == "cg":
+            return L.KSP_CGCG if self.single_reduction else L.KSP_CG
+        return L.KSP_BICGSTAB
 
     def effective(self):
         rtol = 1e-13 if self._type.lower() == "preonly" else self.rtol

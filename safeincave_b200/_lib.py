@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 4
+SIC_ABI_VERSION = 5
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -21,7 +21,7 @@ DS_ALPHA, DS_ALPHA0, DS_QSI, DS_QSI_OLD, DS_FVP, DS_R, DS_H, DS_HSMALL, DS_P, DS
     0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15)
 DESAI_ROWS = 21
 POST_STRAIN, POST_STRESS, POST_INCREMENT, POST_RATES, POST_ERROR = 1, 2, 4, 8, 16
-KSP_CG, KSP_BICGSTAB = 1, 2
+KSP_CG, KSP_BICGSTAB, KSP_CGCG = 1, 2, 3
 
 # every symbol include/safeincave_cuda.h declares
 EXPORTS = (
@@ -29,7 +29,7 @@ EXPORTS = (
     "sic_post", "sic_post_blocks", "sic_commit", "sic_commit_rates", "sic_desai_initial_hardening",
     "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
     "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
-    "sic_allreduce_sum",
+    "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
 )
 
 
@@ -64,7 +64,7 @@ class SicHalo(ctypes.Structure):
     _fields_ = [("n_ranks", c_int32), ("rank", c_int32), ("n_peers", c_int32), ("n_shared_total", c_int32),
                 ("peer", c_int32 * SIC_MAX_PEERS), ("peer_off", c_int32 * (SIC_MAX_PEERS + 1)),
                 ("idx", c_void_p), ("owner_w", c_void_p), ("send_buf", c_void_p), ("recv_buf", c_void_p),
-                ("comm", c_void_p)]
+                ("comm", c_void_p), ("p2p", c_void_p)]
 
 
 class SicError(RuntimeError):
@@ -109,6 +109,11 @@ def load():
     lib.sic_comm_destroy.argtypes = [c_void_p]
     lib.sic_halo_sum.argtypes = [PH, c_void_p, c_int, c_void_p]
     lib.sic_allreduce_sum.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    lib.sic_p2p_create.argtypes = [c_int, c_int, c_int, POINTER(c_void_p), c_void_p]
+    lib.sic_p2p_connect.argtypes = [c_void_p, c_void_p]
+    lib.sic_p2p_destroy.argtypes = [c_void_p]
+    lib.sic_p2p_error.argtypes = [c_void_p]
+    lib.sic_exchange.argtypes = [PH, c_void_p, c_int, c_void_p, c_int, c_void_p]
     lib.sic_neumann.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
     lib.sic_ksp_workspace_doubles.restype = c_int64

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/safeincave_cuda.h"
@@ -133,4 +134,184 @@ extern "C" int sic_halo_sum(const sic_halo_t* h, double* vec, int ncomp, void* s
   if (int rc = nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd")) return rc;
   sic::k_halo_unpack_add<<<blocks, threads, 0, st>>>(h->n_shared_total, ncomp, h->idx, vec, h->recv_buf);
   return sic_check_launch("k_halo_unpack_add");
+}
+
+// =====================================================================================================
+// Peer-to-peer exchange over NVLink (no NCCL): halo sum + scalar all-reduce in ONE kernel
+// =====================================================================================================
+namespace sic {
+
+#define SIC_P2P_MAX_RANKS 16
+#define SIC_P2P_BPP 4          /* blocks per peer */
+#define SIC_P2P_THREADS 256
+#define SIC_P2P_NSCAL 8
+
+struct P2P {
+  int rank, n_ranks, cap;                 // cap: interface nodes per peer the mailbox can hold
+  size_t slot_doubles;                    // doubles per (source rank, parity) slot: 9*cap data + NSCAL scalars + 1 flag
+  double* local;                          // this rank's mailbox (cudaMalloc)
+  double* remote[SIC_P2P_MAX_RANKS];      // peers' mailboxes mapped into this process (remote[rank] == local)
+  unsigned* counters;                     // [n_ranks] blocks-done counters (device)
+  int* error;                             // device flag: a wait timed out
+  unsigned long long epoch;               // exchanges issued so far (identical on every rank)
+};
+
+__device__ __forceinline__ double* p2p_slot(double* mailbox, size_t slot_doubles, int src, int parity) {
+  return mailbox + ((size_t)src * 2 + parity) * slot_doubles;
+}
+
+// grid = n_peers * BPP blocks.  Block (p, c) handles chunk c of the data exchanged with peer p.
+__global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, P2P ctx, double* __restrict__ vec, int ncomp,
+                                                                 double* __restrict__ scal, int n_scal,
+                                                                 unsigned long long epoch) {
+  const int p = blockIdx.x / SIC_P2P_BPP, chunk = blockIdx.x % SIC_P2P_BPP;
+  const int peer = H.peer[p];
+  const int parity = (int)(epoch & 1ull);
+  const int off = H.peer_off[p], cnt = H.peer_off[p + 1] - off;
+  const int n = cnt * ncomp;            // ncomp == 0: scalars only, no nodal data
+  const int per = (n + SIC_P2P_BPP - 1) / SIC_P2P_BPP;
+  const int lo = chunk * per, hi = min(n, lo + per);
+  // ---- send: my partial sums for the nodes shared with `peer` go straight into ITS mailbox -------------
+  double* out = p2p_slot(ctx.remote[peer], ctx.slot_doubles, ctx.rank, parity);
+  for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
+    const int k = t / ncomp, c = t - k * ncomp;
+    out[t] = vec[(size_t)H.idx[off + k] * ncomp + c];
+  }
+  if (chunk == 0 && threadIdx.x < n_scal) out[9 * (size_t)ctx.cap + threadIdx.x] = scal[threadIdx.x];
+  __syncthreads();                           // CTA-scope ordering of everybody's stores before thread 0's fence
+  if (threadIdx.x == 0) {
+    __threadfence_system();                  // cumulative: covers the whole CTA's remote stores
+    const unsigned done = atomicAdd(ctx.counters + p, 1u);
+    if (done == SIC_P2P_BPP - 1) {           // last chunk for this peer: publish
+      ctx.counters[p] = 0;
+      __threadfence_system();
+      volatile unsigned long long* flag = (volatile unsigned long long*)(out + 9 * (size_t)ctx.cap + SIC_P2P_NSCAL);
+      *flag = epoch + 1;
+    }
+  }
+  // ---- receive: wait for the peer's flag in MY mailbox, then add its partial sums ----------------------
+  double* in = p2p_slot(ctx.local, ctx.slot_doubles, peer, parity);
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* flag = (volatile unsigned long long*)(in + 9 * (size_t)ctx.cap + SIC_P2P_NSCAL);
+    const long long t0 = clock64();
+    int good = 1;
+    while (*flag != epoch + 1) {
+      if (clock64() - t0 > 20000000000ll) { good = 0; atomicExch(ctx.error, 1); break; }   // ~10 s
+    }
+    __threadfence_system();
+    ok = good;
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
+    const int k = t / ncomp, c = t - k * ncomp;
+    atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, __ldcv(in + t));
+  }
+}
+
+// after k_p2p_exchange: scal[j] = sum over ranks (own value + every peer's, in rank order: identical on all ranks)
+__global__ void k_p2p_scalars(P2P ctx, double* __restrict__ scal, int n_scal, unsigned long long epoch) {
+  const int j = threadIdx.x;
+  if (j >= n_scal) return;
+  const int parity = (int)(epoch & 1ull);
+  double acc = 0.0;
+  for (int r = 0; r < ctx.n_ranks; ++r) {
+    if (r == ctx.rank) acc += scal[j];
+    else acc += __ldcv(p2p_slot(ctx.local, ctx.slot_doubles, r, parity) + 9 * (size_t)ctx.cap + j);
+  }
+  scal[j] = acc;
+}
+}  // namespace sic
+
+extern "C" int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, uint8_t* handle64) {
+  if (!p2p || !handle64) return sic_fail("sic_p2p_create: null");
+  if (n_ranks < 2 || n_ranks > SIC_P2P_MAX_RANKS) return sic_fail("sic_p2p_create: 2..16 ranks");
+  sic::P2P* c = new sic::P2P();
+  c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1; c->epoch = 0;
+  c->slot_doubles = 9 * (size_t)c->cap + SIC_P2P_NSCAL + 1;
+  const size_t bytes = sizeof(double) * c->slot_doubles * 2 * n_ranks;
+  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->local, bytes), "cudaMalloc mailbox")) return rc;
+  if (int rc = sic_check_cuda(cudaMemset(c->local, 0, bytes), "memset mailbox")) return rc;
+  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->counters, sizeof(unsigned) * SIC_P2P_MAX_RANKS + sizeof(int)), "cudaMalloc"))
+    return rc;
+  cudaMemset(c->counters, 0, sizeof(unsigned) * SIC_P2P_MAX_RANKS + sizeof(int));
+  c->error = (int*)(c->counters + SIC_P2P_MAX_RANKS);
+  cudaIpcMemHandle_t h;
+  if (int rc = sic_check_cuda(cudaIpcGetMemHandle(&h, c->local), "cudaIpcGetMemHandle")) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  memcpy(handle64, &h, 64);
+  for (int r = 0; r < SIC_P2P_MAX_RANKS; ++r) c->remote[r] = nullptr;
+  c->remote[rank] = c->local;
+  *p2p = c;
+  return 0;
+}
+
+extern "C" int sic_p2p_connect(void* p2p, const uint8_t* all_handles) {
+  if (!p2p || !all_handles) return sic_fail("sic_p2p_connect: null");
+  sic::P2P* c = (sic::P2P*)p2p;
+  for (int r = 0; r < c->n_ranks; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    if (int rc = sic_check_cuda(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+      return rc;
+    c->remote[r] = (double*)ptr;
+  }
+  return 0;
+}
+
+extern "C" int sic_p2p_error(void* p2p) {   // synchronous: 1 if a wait on a peer's flag timed out
+  if (!p2p) return 0;
+  int e = 0;
+  cudaMemcpy(&e, ((sic::P2P*)p2p)->error, sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
+}
+
+extern "C" int sic_p2p_destroy(void* p2p) {
+  if (!p2p) return 0;
+  sic::P2P* c = (sic::P2P*)p2p;
+  for (int r = 0; r < c->n_ranks; ++r)
+    if (r != c->rank && c->remote[r]) cudaIpcCloseMemHandle(c->remote[r]);
+  cudaFree(c->local);
+  cudaFree(c->counters);
+  delete c;
+  return 0;
+}
+
+extern "C" int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double* scal, int n_scal, void* stream) {
+  if (!h || h->n_ranks <= 1) return 0;
+  static int dbg_skip = -1;   // SIC_DBG_NOXCHG=1: timing experiment only (results are wrong)
+  if (dbg_skip < 0) { const char* e = getenv("SIC_DBG_NOXCHG"); dbg_skip = (e && e[0] == '1') ? 1 : 0; }
+  if (dbg_skip) return 0;
+  if (n_scal < 0 || n_scal > SIC_P2P_NSCAL) return sic_fail("sic_exchange: n_scal must be 0..8");
+  if (!h->p2p) {   // NCCL path
+    if (ncomp > 0) { if (int rc = sic_halo_sum(h, vec, ncomp, stream)) return rc; }
+    if (n_scal > 0) return sic_allreduce_sum(h->comm, scal, n_scal, stream);
+    return 0;
+  }
+  sic::P2P* c = (sic::P2P*)h->p2p;
+  cudaStream_t st = (cudaStream_t)stream;
+  int cap_needed = 0;
+  for (int p = 0; p < h->n_peers; ++p) {
+    int cnt = h->peer_off[p + 1] - h->peer_off[p];
+    if (cnt > cap_needed) cap_needed = cnt;
+  }
+  if (cap_needed > c->cap) return sic_fail("sic_exchange: mailbox too small for this halo plan");
+  if (h->n_peers != h->n_ranks - 1 && n_scal > 0) {
+    // scalars travel with the halo messages: every rank must be a neighbour of every other one.  Otherwise
+    // fall back to NCCL for the scalars (never the case for <= 8 Morton chunks of one mesh in practice).
+    if (ncomp > 0) { if (int rc = sic_exchange(h, vec, ncomp, nullptr, 0, stream)) return rc; }
+    return sic_allreduce_sum(h->comm, scal, n_scal, stream);
+  }
+  if (h->n_peers == 0) return 0;
+  const unsigned long long epoch = c->epoch++;
+  sic::k_p2p_exchange<<<h->n_peers * SIC_P2P_BPP, SIC_P2P_THREADS, 0, st>>>(*h, *c, vec, ncomp, scal, n_scal, epoch);
+  if (int rc = sic_check_launch("k_p2p_exchange")) return rc;
+  if (n_scal > 0) {
+    sic::k_p2p_scalars<<<1, 32, 0, st>>>(*c, scal, n_scal, epoch);
+    return sic_check_launch("k_p2p_scalars");
+  }
+  return 0;
 }

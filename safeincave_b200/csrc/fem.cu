@@ -169,7 +169,7 @@ extern "C" int sic_residual0(const sic_problem_t* p, const double* b_ext, const 
   if (int rc = sic_check_cuda(cudaMemsetAsync(r, 0, sizeof(double) * nd, st), "memset r")) return rc;
   if (p->n_cells > 0) SIC_EBE_LAUNCH(1, p, x0, r, st);
   if (int rc = sic_check_launch("k_ebe<1>")) return rc;
-  if (int rc = sic_halo_sum(halo, r, 3, stream)) return rc;
+  if (int rc = sic_exchange(halo, r, 3, nullptr, 0, stream)) return rc;
   if (nd > 0) k_add_mask<<<blocks_for(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, r, b_ext, fixed);
   return sic_check_launch("sic_residual0");
 }
@@ -181,7 +181,7 @@ extern "C" int sic_block_jacobi(const sic_problem_t* p, double* dinv, const uint
   if (int rc = sic_check_cuda(cudaMemsetAsync(dinv, 0, sizeof(double) * 9 * p->n_nodes, st), "memset dinv")) return rc;
   if (p->n_cells > 0) k_diag_blocks<<<blocks_for(p->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*p, dinv);
   if (int rc = sic_check_launch("k_diag_blocks")) return rc;
-  if (int rc = sic_halo_sum(halo, dinv, 9, stream)) return rc;
+  if (int rc = sic_exchange(halo, dinv, 9, nullptr, 0, stream)) return rc;
   if (p->n_nodes > 0)
     k_invert_blocks<<<blocks_for(p->n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(p->n_nodes, dinv, fixed);
   return sic_check_launch("sic_block_jacobi");

@@ -33,7 +33,8 @@ static_assert(sizeof(Scal) <= 64 * sizeof(double), "Scal must fit the reserved w
 #define SIC_WS_HEADER 64   /* doubles reserved for Scal */
 #define SIC_WS_COUNTERS 8  /* doubles reserved for ticket counters */
 
-enum { OP_REF = 0, OP_CG_INIT, OP_CG_ALPHA, OP_CG_BETA, OP_BI_INIT, OP_BI_ALPHA, OP_BI_OMEGA, OP_BI_BETA };
+enum { OP_NONE = -1, OP_REF = 0, OP_CG_INIT, OP_CG_ALPHA, OP_CG_BETA, OP_BI_INIT, OP_BI_ALPHA, OP_BI_OMEGA, OP_BI_BETA,
+       OP_CGCG_INIT, OP_CGCG_STEP };
 
 __device__ __forceinline__ void check_convergence(Scal* S, double rr) {
   S->rr = rr;
@@ -72,6 +73,21 @@ __device__ __forceinline__ void scal_step(Scal* S, int op, double rtol, double a
       S->rho = S->sum[0];
       check_convergence(S, S->sum[1]);
       break;
+    // Chronopoulos-Gear: sum[0] = gamma = r.u, sum[1] = r.r, sum[2] = delta = u.Ku
+    case OP_CGCG_INIT:
+      S->rz = S->sum[0];
+      init_tolerance(S, S->sum[1], rtol, atol, guess);
+      S->alpha = S->sum[0] / S->sum[2];
+      S->beta = 0.0;
+      break;
+    case OP_CGCG_STEP: {
+      const double gamma_new = S->sum[0];
+      S->beta = gamma_new / S->rz;
+      S->alpha = gamma_new / (S->sum[2] - S->beta * gamma_new / S->alpha);
+      S->rz = gamma_new;
+      check_convergence(S, S->sum[1]);
+      break;
+    }
   }
 }
 
@@ -80,13 +96,13 @@ __global__ void k_scal(Scal* S, int op, double rtol, double atol, int guess, int
   scal_step(S, op, rtol, atol, guess);
 }
 
-struct Fin {  // what the last block does with the grid totals
-  Scal* S; int op; double rtol, atol; int guess; int multi;
+struct Fin {  // what the last block does with the grid totals: store them at S->sum[slot..], then (one GPU) step
+  Scal* S; int op; double rtol, atol; int guess; int multi; int slot;
   template <int NV>
   __device__ __forceinline__ void run(const double* tot) const {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) S->sum[k] = tot[k];
-    if (!multi) scal_step(S, op, rtol, atol, guess);
+    for (int k = 0; k < NV; ++k) S->sum[slot + k] = tot[k];
+    if (!multi && op != OP_NONE) scal_step(S, op, rtol, atol, guess);
   }
 };
 
@@ -248,6 +264,74 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_cg_p(int nd, double* __rest
   q[d] = 0.0;
 }
 
+// ---- Chronopoulos-Gear CG -----------------------------------------------------------------------------
+// u = M^-1 r ; p = s = w = 0 ; sums gamma = r.u, rr = r.r
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_cgcg_init(int n_nodes, const double* __restrict__ r,
+                                                              double* __restrict__ u, double* __restrict__ p,
+                                                              double* __restrict__ s, double* __restrict__ w,
+                                                              const double* __restrict__ dinv,
+                                                              const double* __restrict__ ow, Fin fin,
+                                                              double* __restrict__ partials, unsigned* counter) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[2] = {0.0, 0.0};
+  if (n < n_nodes) {
+    double rn[3], un[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) rn[j] = r[3 * (size_t)n + j];
+    precond3(dinv, n, rn, un);
+    const double wn = ow ? ow[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      u[d] = un[j]; p[d] = 0.0; s[d] = 0.0; w[d] = 0.0;
+      v[0] += wn * rn[j] * un[j];
+      v[1] += wn * rn[j] * rn[j];
+    }
+  }
+  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
+}
+
+// p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; w = 0 ; sums gamma, rr
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_cgcg_vec(int n_nodes, double* __restrict__ x, double* __restrict__ r,
+                                                             double* __restrict__ u, double* __restrict__ p,
+                                                             double* __restrict__ s, double* __restrict__ w,
+                                                             const double* __restrict__ dinv,
+                                                             const uint8_t* __restrict__ fixed,
+                                                             const double* __restrict__ ow, Fin fin,
+                                                             double* __restrict__ partials, unsigned* counter) {
+  if (fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const double alpha = fin.S->alpha, beta = fin.S->beta;
+  double v[2] = {0.0, 0.0};
+  if (n < n_nodes) {
+    double rn[3], un[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      if (fixed[d]) {
+        rn[j] = 0.0; p[d] = 0.0; s[d] = 0.0;
+      } else {
+        const double pn = u[d] + beta * p[d];
+        const double sn = w[d] + beta * s[d];
+        p[d] = pn; s[d] = sn;
+        x[d] += alpha * pn;
+        rn[j] = r[d] - alpha * sn;
+      }
+      r[d] = rn[j];
+      w[d] = 0.0;
+    }
+    precond3(dinv, n, rn, un);
+    const double wn = ow ? ow[n] : 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      u[3 * (size_t)n + j] = un[j];
+      v[0] += wn * rn[j] * un[j];
+      v[1] += wn * rn[j] * rn[j];
+    }
+  }
+  grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run<2>(tot); });
+}
+
 // ---- BiCGStab (right-preconditioned) -------------------------------------------------------------
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_bi_init(int n_nodes, const double* __restrict__ r,
                                                             double* __restrict__ rh, double* __restrict__ p,
@@ -403,7 +487,7 @@ static int64_t partial_slots(int n_nodes) {
 extern "C" int64_t sic_ksp_workspace_doubles(int n_nodes, int method) {
   // header + counters + partials (sized for up to 8 cells per node) + vectors
   const int64_t nd = 3 * (int64_t)n_nodes;
-  const int64_t nvec = (method == SIC_KSP_BICGSTAB) ? 8 : 4;
+  const int64_t nvec = (method == SIC_KSP_BICGSTAB) ? 8 : (method == SIC_KSP_CGCG ? 5 : 4);
   return SIC_WS_HEADER + SIC_WS_COUNTERS + partial_slots(n_nodes) + nvec * nd;
 }
 
@@ -434,7 +518,8 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
                              const uint8_t* fixed, const double* dinv, double* work, const sic_halo_t* halo,
                              void* stream) {
   if (!p || !ksp || !b_ext || !x || !fixed || !dinv || !work) return sic_fail("sic_ksp_solve: null argument");
-  if (ksp->method != SIC_KSP_CG && ksp->method != SIC_KSP_BICGSTAB) return sic_fail("sic_ksp_solve: unknown method");
+  if (ksp->method != SIC_KSP_CG && ksp->method != SIC_KSP_BICGSTAB && ksp->method != SIC_KSP_CGCG)
+    return sic_fail("sic_ksp_solve: unknown method");
   cudaStream_t st = (cudaStream_t)stream;
   const int nn = p->n_nodes, nd = 3 * nn, nc = p->n_cells;
   const int64_t part = partial_slots(nn);
@@ -442,9 +527,10 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
     if (int rc = sic_check_cuda(cudaMallocHost((void**)&g_host_scal, sizeof(Scal)), "cudaMallocHost")) return rc;
   }
   const int multi = (halo && halo->n_ranks > 1) ? 1 : 0;
-  if (multi && (!halo->comm || !halo->owner_w)) return sic_fail("sic_ksp_solve: halo without communicator / owner weights");
+  if (multi && ((!halo->comm && !halo->p2p) || !halo->owner_w))
+    return sic_fail("sic_ksp_solve: halo without communicator / owner weights");
   const double* w = multi ? halo->owner_w : nullptr;
-  void* comm = multi ? halo->comm : nullptr;
+  const double* ow_ptr = w;
   Scal* S = (Scal*)work;
   unsigned* counter = (unsigned*)(work + SIC_WS_HEADER);
   double* partials = work + SIC_WS_HEADER + SIC_WS_COUNTERS;
@@ -472,11 +558,11 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
   const int check = ksp->check_every > 0 ? ksp->check_every : 25;
   const int guess = ksp->guess_nonzero ? 1 : 0;
   const double rtol = ksp->rtol, atol = ksp->atol;
-  auto fin = [&](int op) { return Fin{S, op, rtol, atol, guess, multi}; };
+  auto fin = [&](int op, int slot = 0) { return Fin{S, op, rtol, atol, guess, multi, slot}; };
   // several GPUs: all-reduce S->sum and run the scalar recurrence in a one-thread kernel
   auto reduce = [&](int op, int count, int skip_if_done) -> int {
     if (!multi) return 0;
-    if (int rc = sic_allreduce_sum(comm, S->sum, count, stream)) return rc;
+    if (int rc = sic_exchange(halo, nullptr, 0, S->sum, count, stream)) return rc;
     k_scal<<<1, 1, 0, st>>>(S, op, rtol, atol, guess, skip_if_done);
     return sic_check_launch("k_scal");
   };
@@ -492,7 +578,36 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
   }
   if (int rc = sic_residual0(p, b_ext, x, r, fixed, halo, stream)) return rc;
 
-  if (ksp->method == SIC_KSP_CG) {
+  if (ksp->method == SIC_KSP_CGCG) {
+    double *u = v1, *pp = v2, *sv = v3, *w = vec + 4 * (size_t)nd;
+    // one operator application + ONE reduction / exchange per iteration
+    auto apply_and_reduce = [&](int op, int k) -> int {
+      timer.begin(k);
+      k_ebe_dot<<<cb, ebt, esm, st>>>(*p, u, w, fin(OP_NONE, 2), partials, counter);
+      timer.end(k);
+      k_sum_partials<<<1, 1024, 0, st>>>(partials, cb, fin(multi ? OP_NONE : op, 2));
+      if (multi) {
+        if (int rc = sic_exchange(halo, w, 3, S->sum, 3, stream)) return rc;
+        k_scal<<<1, 1, 0, st>>>(S, op, rtol, atol, guess, op == OP_CGCG_STEP ? 1 : 0);
+      }
+      return sic_check_launch("cgcg apply");
+    };
+    k_cgcg_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, u, pp, sv, w, dinv, ow_ptr, fin(OP_NONE, 0), partials, counter + 1);
+    if (int rc = apply_and_reduce(OP_CGCG_INIT, 1)) return rc;
+    while (true) {
+      cudaMemcpyAsync(g_host_scal, S, sizeof(Scal), cudaMemcpyDeviceToHost, st);
+      if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "ksp sync")) return rc;
+      timer.collect();
+      if (g_host_scal->done || launched >= ksp->max_it) break;
+      const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
+      for (int k = 0; k < batch; ++k) {
+        k_cgcg_vec<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, u, pp, sv, w, dinv, fixed, ow_ptr, fin(OP_NONE, 0), partials,
+                                                   counter + 1);
+        if (int rc = apply_and_reduce(OP_CGCG_STEP, k)) return rc;
+      }
+      launched += batch;
+    }
+  } else if (ksp->method == SIC_KSP_CG) {
     double *z = v1, *pp = v2, *q = v3;
     k_cg_init<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, pp, q, dinv, w, fin(OP_CG_INIT), partials, counter);
     if (int rc = reduce(OP_CG_INIT, 2, 0)) return rc;
@@ -509,9 +624,9 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
 #if SIC_EBE_IMPL == 3
         k_sum_partials<<<1, 1024, 0, st>>>(partials, cb, fin(OP_CG_ALPHA));
 #endif
-        if (multi) {
-          if (int rc = sic_halo_sum(halo, q, 3, stream)) return rc;
-          if (int rc = reduce(OP_CG_ALPHA, 1, 1)) return rc;
+        if (multi) {   // halo sum of q and the sum over ranks of p.Kp travel in ONE exchange
+          if (int rc = sic_exchange(halo, q, 3, S->sum, 1, stream)) return rc;
+          k_scal<<<1, 1, 0, st>>>(S, OP_CG_ALPHA, rtol, atol, guess, 1);
         }
         k_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, z, pp, q, dinv, fixed, w, fin(OP_CG_BETA), partials,
                                                     counter + 1);
@@ -536,12 +651,12 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
         timer.begin(k);
         k_ebe_plain<<<cb, ebt, esm, st>>>(*p, y, v, S);
         timer.end(k);
-        if (int rc = sic_halo_sum(halo, v, 3, stream)) return rc;
+        if (int rc = sic_exchange(halo, v, 3, nullptr, 0, stream)) return rc;
         k_bi_dot1<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, rh, v, fixed, w, fin(OP_BI_ALPHA), partials, counter);
         if (int rc = reduce(OP_BI_ALPHA, 1, 1)) return rc;
         k_bi_s<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, v, s, z, t, dinv, fixed, S);
         k_ebe_plain<<<cb, ebt, esm, st>>>(*p, z, t, S);
-        if (int rc = sic_halo_sum(halo, t, 3, stream)) return rc;
+        if (int rc = sic_exchange(halo, t, 3, nullptr, 0, stream)) return rc;
         k_bi_dot2<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, t, s, fixed, w, fin(OP_BI_OMEGA), partials, counter + 1);
         if (int rc = reduce(OP_BI_OMEGA, 2, 1)) return rc;
         k_bi_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, s, t, y, z, rh, fixed, w, fin(OP_BI_BETA), partials,
@@ -553,6 +668,7 @@ extern "C" int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const doubl
       if (int rc = sic_check_launch("bicgstab batch")) return rc;
     }
   }
+  if (multi && halo->p2p && sic_p2p_error(halo->p2p)) return sic_fail("P2P exchange timed out waiting for a peer");
   ksp->iterations = g_host_scal->iters;
   ksp->rnorm = sqrt(g_host_scal->rr);
   ksp->rnorm0 = sqrt(g_host_scal->rr0);

@@ -19,6 +19,30 @@ from .partition import Partition, build_partition
 class DistContext:
     def __init__(self, rank, world, device, comm=None):
         self.rank, self.world, self.device, self.comm = rank, world, device, comm
+        self.p2p = None
+        self.use_p2p = os.environ.get("SIC_P2P", "1") != "0"    # 0: NCCL send/recv + allreduce instead
+
+    def make_p2p(self, part):
+        """Mailbox for the peer-to-peer exchange kernel: allocate, all-gather the IPC handles, map the peers."""
+        if self.world == 1 or self.device.type != "cuda" or not self.use_p2p:
+            return None
+        lib = L.load()
+        cap = max([int(s.numel()) for s in part.shared] + [1])
+        t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        handle = (ctypes.c_uint8 * 64)()
+        ctx = ctypes.c_void_p(0)
+        L.check(lib.sic_p2p_create(self.rank, self.world, int(t.item()), ctypes.byref(ctx),
+                                   ctypes.cast(handle, ctypes.c_void_p)), "sic_p2p_create")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        raw = bytes(torch.cat(allh).cpu().tolist())
+        buf = (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)
+        L.check(lib.sic_p2p_connect(ctx, ctypes.cast(buf, ctypes.c_void_p)), "sic_p2p_connect")
+        dist.barrier()
+        self.p2p = ctx
+        return ctx
 
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -84,4 +108,4 @@ def attach(eq, part: Partition, ctx: DistContext):
     """Give a LinearMomentum built on the local grid its halo plan and communicator."""
     eq.dist = ctx
     if ctx.world > 1:
-        eq.engine.set_partition(part, ctx.comm)
+        eq.engine.set_partition(part, ctx.comm, ctx.make_p2p(part))

@@ -250,7 +250,7 @@ class Engine:
         self.launches += 2
 
     # ------------------------------------------------------------------ several GPUs
-    def set_partition(self, part, comm):
+    def set_partition(self, part, comm, p2p=None):
         """Attach the halo plan of safeincave_b200.partition.Partition and an NCCL communicator handle."""
         if part.n_ranks <= 1:
             self.halo = None
@@ -273,6 +273,7 @@ class Engine:
         h.peer_off[len(part.peers)] = off
         h.idx, h.owner_w, h.send_buf, h.recv_buf = _ptr(idx), _ptr(owner_w), _ptr(send), _ptr(recv)
         h.comm = comm
+        h.p2p = p2p
         self.halo = h
         self._halo_keep = (idx, owner_w, send, recv)
         self.owner_w = owner_w
@@ -280,7 +281,7 @@ class Engine:
     def halo_sum(self, vec, ncomp):
         if self.halo is None:
             return
-        L.check(self.lib.sic_halo_sum(self._ph(), _ptr(vec), int(ncomp), self._stream()), "sic_halo_sum")
+        L.check(self.lib.sic_exchange(self._ph(), _ptr(vec), int(ncomp), None, 0, self._stream()), "sic_exchange")
         self.launches += 2
 
     def neumann(self, tri, area_n, bc_of_tri, bc_par, b):
@@ -306,11 +307,11 @@ class Engine:
         ksp.guess_nonzero = 1 if guess_nonzero else 0
         L.check(self.lib.sic_ksp_solve(self._pp(), ctypes.byref(ksp), _ptr(b_ext), _ptr(x), _ptr(fixed), _ptr(dinv),
                                        _ptr(w), self._ph(), self._stream()), "sic_ksp_solve")
-        per_it = 4 if method == L.KSP_CG else 7
+        per_it = {L.KSP_CG: 4, L.KSP_CGCG: 3}.get(method, 7)
         self.launches += 3 + per_it * int(ksp.iterations)
         self.op_ms += float(ksp.op_ms)
         self.op_samples += int(ksp.op_samples)
-        self.op_launches += (1 if method == L.KSP_CG else 2) * int(ksp.iterations)
+        self.op_launches += (2 if method == L.KSP_BICGSTAB else 1) * int(ksp.iterations)
         return ksp
 
     def fp64_peak(self):

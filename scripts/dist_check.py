@@ -22,10 +22,12 @@ gg = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
 case = cases.cavern_case(gg, n_steps=2, ksp_type=ksp, rtol=1e-12)
 grid, part = distributed.partition_grid(ctx, tm)
 eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
+eq.solver.single_reduction = os.environ.get("SIC_CGCG", "0") == "1"
 sim.verbose = False
 hist = sim.run()
 # single-domain run of the same case on this rank's GPU
 eq1, sim1 = cases.build(case, gg, device=dev)
+eq1.solver.single_reduction = eq.solver.single_reduction
 sim1.verbose = False
 hist1 = sim1.run()
 ln = part.local_nodes.to(dev)

@@ -125,13 +125,14 @@ def test_neumann_and_body_force(sf):
         assert (eq.fixed.cpu().numpy() == mask).all()
 
 
-@pytest.mark.parametrize("method,sym", [("cg", True), ("bicg", False)])
+@pytest.mark.parametrize("method,sym", [("cg", True), ("cgcg", True), ("bicg", False)])
 def test_krylov_solve_matches_direct(sf, method, sym):
     from safeincave_b200 import cases
     grid = load_grid(sf, "cavern_regular")
     tm = grid.tetmesh
-    case = cases.cavern_case(grid, ksp_type=method, rtol=1e-13)
+    case = cases.cavern_case(grid, ksp_type="cg" if method == "cgcg" else method, rtol=1e-13)
     eq, sim = cases.build(case, grid)
+    eq.solver.single_reduction = method == "cgcg"     # Chronopoulos-Gear CG
     osim = oracle_simulator(case, tm)
     eng = eq.engine
     N = eng.N
@@ -147,12 +148,14 @@ def test_krylov_solve_matches_direct(sf, method, sym):
     assert relerr(eq.X.reshape(-1).cpu().numpy(), u_ref) < 1e-9
 
 
-def run_both(sf, grid_name, case_fn, n_steps, levels=0, **kw):
+def run_both(sf, grid_name, case_fn, n_steps, levels=0, solver_opts=None, **kw):
     from safeincave_b200 import cases
     grid = load_grid(sf, grid_name, levels)
     tm = grid.tetmesh
     case = case_fn(grid, n_steps=n_steps, **kw)
     eq, sim = cases.build(case, grid)
+    for k, v in (solver_opts or {}).items():
+        setattr(eq.solver, k, v)
     if case.get("desai_initial_hardening"):
         def hook(eq_, stress):
             for e in eq_.mat.elems_ne:
@@ -196,5 +199,15 @@ def test_time_steps_cavern_regular(sf):
     """BASELINE config 2: cavern_regular (14 346 cells), fully implicit, cyclic gas pressure."""
     from safeincave_b200 import cases
     eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, 2, ksp_type="bicg")
+    assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+    check_fields(eq, osim, ohist)
+
+
+def test_time_steps_cavern_regular_warm_started_cg(sf):
+    """The bench configuration of the solver (CG warm-started from the previous Newton iterate, rtol relative to
+    the zero-guess residual) gives the same fields as the oracle's direct solves."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, 2, ksp_type="cg",
+                                          solver_opts=dict(initial_guess_nonzero=True))
     assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
     check_fields(eq, osim, ohist)
