@@ -217,6 +217,8 @@ def run_b200(args):
     clocks = ClockSampler(local)
     clocks.start()
     eng.time_operator = True
+    eng.profile = True
+    eng.profile_summary()
     eng.op_ms, eng.op_samples, eng.op_launches = 0.0, 0, 0
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -235,6 +237,27 @@ def run_b200(args):
     op_ms = eng.op_ms / max(eng.op_samples, 1)
     op_launches = eng.op_launches
     eng.time_operator = False
+    prof = eng.profile_summary()
+    eng.profile = False
+    # cell-updates/s of the constitutive update alone = N * Newton iterations / time in the
+    # tangent + post-solve + commit kernels
+    S = len(eng.elems)
+    t_const = sum(prof.get(k, (0, 0.0))[1] for k in ("tangent", "post", "commit"))
+    tan_n, tan_ms = prof.get("tangent", (0, 0.0))
+    post_n, post_ms = prof.get("post", (0, 0.0))
+    tan_bytes = N_loc * 8 * (6 + 2 + 42 + 24 * S) + 4 * N_loc          # sig_k, T/T0, C_T + eps_rhs, per element 18 r + 6 w
+    post_bytes = N_loc * (16 + 8 * (12 + 36 + 6 + 6 + 12 + 6 * S)) + 24 * M_loc
+    constitutive = {
+        "cell_updates_per_s": N * iters / (t_const * 1e-3) if t_const > 0 else None,
+        "ms_per_newton_iteration": t_const / max(iters, 1),
+        "share_of_step_time": t_const / ms if ms > 0 else None,
+        "k_tangent": {"avg_ms": tan_ms / max(tan_n, 1), "hbm_gbs": tan_bytes / (tan_ms / max(tan_n, 1) * 1e-3) / 1e9 if tan_ms > 0 else None,
+                      "algorithmic_bytes": tan_bytes},
+        "k_post": {"avg_ms": post_ms / max(post_n, 1), "hbm_gbs": post_bytes / (post_ms / max(post_n, 1) * 1e-3) / 1e9 if post_ms > 0 else None,
+                   "algorithmic_bytes": post_bytes},
+        "block_jacobi_ms": prof.get("block_jacobi", (0, 0.0))[1] / max(prof.get("block_jacobi", (1, 0))[0], 1),
+    }
+    fp64_peak = eng.fp64_peak()
 
     # ---- end-to-end through the public API with host buffers
     e2e = None
@@ -287,7 +310,8 @@ def run_b200(args):
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
                    "preconditioner": "nodal 3x3 block Jacobi", "warm_start": bool(args.warm_start),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
-        "clocks": clk, "gpu_launches": launches, "roofline": roofline,
+        "clocks": clk, "gpu_launches": launches, "roofline": roofline, "constitutive": constitutive,
+        "fp64_peak_tflops_measured": fp64_peak / 1e12,
     }
     if e2e:
         line["e2e"] = e2e

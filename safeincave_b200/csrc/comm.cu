@@ -153,31 +153,70 @@ struct P2P {
   double* remote[SIC_P2P_MAX_RANKS];      // peers' mailboxes mapped into this process (remote[rank] == local)
   unsigned* counters;                     // [n_ranks] blocks-done counters (device)
   int* error;                             // device flag: a wait timed out
-  unsigned long long epoch;               // exchanges issued so far (identical on every rank)
+  unsigned long long epoch;               // nodal (halo) exchanges issued so far (identical on every rank)
+  unsigned long long epoch_s;             // scalar exchanges issued so far; own counter so that two consecutive
+                                          // scalar exchanges always alternate the mailbox parity
 };
 
 __device__ __forceinline__ double* p2p_slot(double* mailbox, size_t slot_doubles, int src, int parity) {
   return mailbox + ((size_t)src * 2 + parity) * slot_doubles;
 }
 
-// grid = n_peers * BPP blocks.  Block (p, c) handles chunk c of the data exchanged with peer p.
+// grid = n_peers * BPP halo blocks (+ 1 scalar block when n_scal > 0).
+//   halo block (p, c): chunk c of the nodal data exchanged with neighbour p (only ranks that share nodes);
+//   scalar block     : thread r sends this rank's n_scal partial sums to rank r (EVERY rank, neighbour or not),
+//                      waits for rank r's, then the sums are formed in rank order (identical on all ranks).
+// Slot layout per (source rank, parity): [9*cap nodal values | NSCAL scalars | halo flag | scalar flag].
 __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, P2P ctx, double* __restrict__ vec, int ncomp,
                                                                  double* __restrict__ scal, int n_scal,
-                                                                 unsigned long long epoch) {
+                                                                 unsigned long long epoch, unsigned long long epoch_s) {
+  const int parity = (int)(epoch & 1ull);
+  const size_t scal_off = 9 * (size_t)ctx.cap;
+  const int n_halo_blocks = (ncomp > 0) ? H.n_peers * SIC_P2P_BPP : 0;
+  __shared__ int ok;
+  __shared__ double mine[SIC_P2P_NSCAL];
+  if ((int)blockIdx.x >= n_halo_blocks) {
+    // ---------------- scalar block -----------------------------------------------------------------
+    const int r = threadIdx.x;
+    const int parity = (int)(epoch_s & 1ull);          // shadows the halo parity
+    const unsigned long long epoch = epoch_s;          // and the halo epoch
+    if (r < n_scal) mine[r] = scal[r];
+    __syncthreads();
+    if (r < ctx.n_ranks && r != ctx.rank) {
+      double* out = p2p_slot(ctx.remote[r], ctx.slot_doubles, ctx.rank, parity) + scal_off;
+      for (int j = 0; j < n_scal; ++j) out[j] = mine[j];
+      __threadfence_system();
+      *(volatile unsigned long long*)(out + SIC_P2P_NSCAL + 1) = epoch + 1;
+      volatile unsigned long long* flag =
+          (volatile unsigned long long*)(p2p_slot(ctx.local, ctx.slot_doubles, r, parity) + scal_off + SIC_P2P_NSCAL + 1);
+      const long long t0 = clock64();
+      while (*flag != epoch + 1) {
+        if (clock64() - t0 > 20000000000ll) { atomicExch(ctx.error, 1); break; }   // ~10 s
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (r < n_scal) {
+      double acc = 0.0;
+      for (int q = 0; q < ctx.n_ranks; ++q)
+        acc += (q == ctx.rank) ? mine[r] : __ldcv(p2p_slot(ctx.local, ctx.slot_doubles, q, parity) + scal_off + r);
+      scal[r] = acc;
+    }
+    return;
+  }
+  // ---------------- halo block ---------------------------------------------------------------------
   const int p = blockIdx.x / SIC_P2P_BPP, chunk = blockIdx.x % SIC_P2P_BPP;
   const int peer = H.peer[p];
-  const int parity = (int)(epoch & 1ull);
   const int off = H.peer_off[p], cnt = H.peer_off[p + 1] - off;
-  const int n = cnt * ncomp;            // ncomp == 0: scalars only, no nodal data
+  const int n = cnt * ncomp;
   const int per = (n + SIC_P2P_BPP - 1) / SIC_P2P_BPP;
   const int lo = chunk * per, hi = min(n, lo + per);
-  // ---- send: my partial sums for the nodes shared with `peer` go straight into ITS mailbox -------------
+  // send: my partial sums for the nodes shared with `peer` go straight into ITS mailbox
   double* out = p2p_slot(ctx.remote[peer], ctx.slot_doubles, ctx.rank, parity);
   for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
     const int k = t / ncomp, c = t - k * ncomp;
     out[t] = vec[(size_t)H.idx[off + k] * ncomp + c];
   }
-  if (chunk == 0 && threadIdx.x < n_scal) out[9 * (size_t)ctx.cap + threadIdx.x] = scal[threadIdx.x];
   __syncthreads();                           // CTA-scope ordering of everybody's stores before thread 0's fence
   if (threadIdx.x == 0) {
     __threadfence_system();                  // cumulative: covers the whole CTA's remote stores
@@ -185,15 +224,13 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     if (done == SIC_P2P_BPP - 1) {           // last chunk for this peer: publish
       ctx.counters[p] = 0;
       __threadfence_system();
-      volatile unsigned long long* flag = (volatile unsigned long long*)(out + 9 * (size_t)ctx.cap + SIC_P2P_NSCAL);
-      *flag = epoch + 1;
+      *(volatile unsigned long long*)(out + scal_off + SIC_P2P_NSCAL) = epoch + 1;
     }
   }
-  // ---- receive: wait for the peer's flag in MY mailbox, then add its partial sums ----------------------
+  // receive: wait for the peer's flag in MY mailbox, then add its partial sums
   double* in = p2p_slot(ctx.local, ctx.slot_doubles, peer, parity);
-  __shared__ int ok;
   if (threadIdx.x == 0) {
-    volatile unsigned long long* flag = (volatile unsigned long long*)(in + 9 * (size_t)ctx.cap + SIC_P2P_NSCAL);
+    volatile unsigned long long* flag = (volatile unsigned long long*)(in + scal_off + SIC_P2P_NSCAL);
     const long long t0 = clock64();
     int good = 1;
     while (*flag != epoch + 1) {
@@ -209,27 +246,14 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, __ldcv(in + t));
   }
 }
-
-// after k_p2p_exchange: scal[j] = sum over ranks (own value + every peer's, in rank order: identical on all ranks)
-__global__ void k_p2p_scalars(P2P ctx, double* __restrict__ scal, int n_scal, unsigned long long epoch) {
-  const int j = threadIdx.x;
-  if (j >= n_scal) return;
-  const int parity = (int)(epoch & 1ull);
-  double acc = 0.0;
-  for (int r = 0; r < ctx.n_ranks; ++r) {
-    if (r == ctx.rank) acc += scal[j];
-    else acc += __ldcv(p2p_slot(ctx.local, ctx.slot_doubles, r, parity) + 9 * (size_t)ctx.cap + j);
-  }
-  scal[j] = acc;
-}
 }  // namespace sic
 
 extern "C" int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, uint8_t* handle64) {
   if (!p2p || !handle64) return sic_fail("sic_p2p_create: null");
   if (n_ranks < 2 || n_ranks > SIC_P2P_MAX_RANKS) return sic_fail("sic_p2p_create: 2..16 ranks");
   sic::P2P* c = new sic::P2P();
-  c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1; c->epoch = 0;
-  c->slot_doubles = 9 * (size_t)c->cap + SIC_P2P_NSCAL + 1;
+  c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1; c->epoch = 0; c->epoch_s = 0;
+  c->slot_doubles = 9 * (size_t)c->cap + SIC_P2P_NSCAL + 2;   // + halo flag + scalar flag
   const size_t bytes = sizeof(double) * c->slot_doubles * 2 * n_ranks;
   if (int rc = sic_check_cuda(cudaMalloc((void**)&c->local, bytes), "cudaMalloc mailbox")) return rc;
   if (int rc = sic_check_cuda(cudaMemset(c->local, 0, bytes), "memset mailbox")) return rc;
@@ -298,20 +322,15 @@ extern "C" int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double*
     int cnt = h->peer_off[p + 1] - h->peer_off[p];
     if (cnt > cap_needed) cap_needed = cnt;
   }
-  if (cap_needed > c->cap) return sic_fail("sic_exchange: mailbox too small for this halo plan");
-  if (h->n_peers != h->n_ranks - 1 && n_scal > 0) {
-    // scalars travel with the halo messages: every rank must be a neighbour of every other one.  Otherwise
-    // fall back to NCCL for the scalars (never the case for <= 8 Morton chunks of one mesh in practice).
-    if (ncomp > 0) { if (int rc = sic_exchange(h, vec, ncomp, nullptr, 0, stream)) return rc; }
-    return sic_allreduce_sum(h->comm, scal, n_scal, stream);
-  }
-  if (h->n_peers == 0) return 0;
-  const unsigned long long epoch = c->epoch++;
-  sic::k_p2p_exchange<<<h->n_peers * SIC_P2P_BPP, SIC_P2P_THREADS, 0, st>>>(*h, *c, vec, ncomp, scal, n_scal, epoch);
-  if (int rc = sic_check_launch("k_p2p_exchange")) return rc;
-  if (n_scal > 0) {
-    sic::k_p2p_scalars<<<1, 32, 0, st>>>(*c, scal, n_scal, epoch);
-    return sic_check_launch("k_p2p_scalars");
-  }
-  return 0;
+  if (ncomp > 0 && cap_needed > c->cap) return sic_fail("sic_exchange: mailbox too small for this halo plan");
+  if (h->n_ranks > SIC_P2P_THREADS) return sic_fail("sic_exchange: too many ranks");
+  const int blocks = (ncomp > 0 ? h->n_peers * SIC_P2P_BPP : 0) + (n_scal > 0 ? 1 : 0);
+  // every rank takes this path for every call (nodal data to the neighbours, scalars to everybody), so the
+  // epoch counters of all ranks advance in lock step
+  const unsigned long long epoch = c->epoch, epoch_s = c->epoch_s;
+  if (ncomp > 0) c->epoch++;
+  if (n_scal > 0) c->epoch_s++;
+  if (blocks == 0) return 0;
+  sic::k_p2p_exchange<<<blocks, SIC_P2P_THREADS, 0, st>>>(*h, *c, vec, ncomp, scal, n_scal, epoch, epoch_s);
+  return sic_check_launch("k_p2p_exchange");
 }

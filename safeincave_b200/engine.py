@@ -118,6 +118,8 @@ class Engine:
         self._prob = None
         self.launches = 0   # kernels launched through this engine (bench.py's gpu_launches)
         self.time_operator = False          # bracket one operator launch per Krylov batch with CUDA events
+        self.profile = False                # bracket the constitutive kernels with CUDA events (bench.py)
+        self._prof_events = {}
         self.halo = None                    # L.SicHalo when the mesh is partitioned over several GPUs
         self._halo_keep = None
         self.op_ms, self.op_samples, self.op_launches = 0.0, 0, 0
@@ -201,9 +203,33 @@ class Engine:
     def _pp(self):
         return ctypes.byref(self.problem())
 
+    # ------------------------------------------------------------------ measurement
+    def _tic(self, name):
+        if not self.profile:
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._prof_events.setdefault(name, []).append((e0, e1))
+        return e1
+
+    @staticmethod
+    def _toc(e1):
+        if e1 is not None:
+            e1.record()
+
+    def profile_summary(self, reset=True):
+        """{kernel: (launches, total ms)} from the recorded CUDA events (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self._prof_events.items()}
+        if reset:
+            self._prof_events = {}
+        return out
+
     # ------------------------------------------------------------------ part (1)
     def tangent(self, dt, theta):
+        t = self._tic("tangent")
         L.check(self.lib.sic_tangent(self._pp(), float(dt), float(theta), self._stream()), "sic_tangent")
+        self._toc(t)
         self.launches += 1
 
     def elastic_tangent(self):
@@ -212,12 +238,16 @@ class Engine:
 
     def post(self, u, dt, theta, kelvin_phi2, flags):
         up = _ptr(u) if u is not None else ctypes.c_void_p(0)
+        t = self._tic("post")
         L.check(self.lib.sic_post(self._pp(), up, float(dt), float(theta), float(kelvin_phi2), int(flags),
                                   _ptr(self.err_out), _ptr(self.err_scratch), self._stream()), "sic_post")
+        self._toc(t)
         self.launches += 2 if (flags & L.POST_ERROR) else 1
 
     def commit(self, dt, theta):
+        t = self._tic("commit")
         L.check(self.lib.sic_commit(self._pp(), float(dt), float(theta), self._stream()), "sic_commit")
+        self._toc(t)
         self.launches += 1
 
     def commit_rates(self):
@@ -245,8 +275,10 @@ class Engine:
         self.launches += 2
 
     def block_jacobi(self, dinv, fixed):
+        t = self._tic("block_jacobi")
         L.check(self.lib.sic_block_jacobi(self._pp(), _ptr(dinv), _ptr(fixed), self._ph(), self._stream()),
                 "sic_block_jacobi")
+        self._toc(t)
         self.launches += 2
 
     # ------------------------------------------------------------------ several GPUs

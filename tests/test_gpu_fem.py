@@ -211,3 +211,17 @@ def test_time_steps_cavern_regular_warm_started_cg(sf):
                                           solver_opts=dict(initial_guess_nonzero=True))
     assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
     check_fields(eq, osim, ohist)
+
+
+def test_time_step_cavern_regular_config3_desai_pressure_solution(sf):
+    """BASELINE config 3 physics on cavern_regular: Spring + Kelvin + DislocationCreep + PressureSolutionCreep +
+    ViscoplasticDesai with compute_initial_hardening after the elastic response (theta = 0.5)."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, 1, ksp_type="bicg", theta=0.5,
+                                          elements=("kelvin", "dislocation", "pressure_solution", "desai"))
+    assert hist[0]["iterations"] == ohist[1]["iters"]
+    check_fields(eq, osim, ohist, tol=1e-7)
+    eng = eq.engine
+    d_gpu, d_or = eng.elems[3].desai, osim.mat.elems[3]
+    assert relerr(eng.get1(d_gpu[0]), d_or.alpha) < 1e-9          # hardening variable
+    assert relerr(eng.get1(d_gpu[4]), d_or.Fvp) < 1e-6 or np.abs(d_or.Fvp).max() < 1e-6
