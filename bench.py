@@ -179,14 +179,21 @@ def run_b200(args):
     from safeincave_b200.mesh import TetMesh, morton_order, red_refine
 
     from safeincave_b200 import distributed
+    t_start = time.perf_counter()
+
+    def note(msg):
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
     ctx = distributed.init()
     world, rank, dev = ctx.world, ctx.rank, ctx.device
     local = dev.index or 0
+    note(f"process group up, world {world}")
 
     tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
     for _ in range(args.levels):
         tm = red_refine(tm, device=dev)
     tm = morton_order(tm, device=dev)
+    note(f"mesh refined and ordered: {tm.n_cells} cells")
     grid_global = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
     n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
     case = cases.cavern_case(grid_global, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
@@ -205,13 +212,16 @@ def run_b200(args):
     eng = eq.engine
     N, M = tm.n_cells, tm.n_nodes                        # global counts (the metric is whole-job)
     N_loc, M_loc = eng.N, eng.M
+    note(f"engine built: {N_loc} local cells")
     sim.initialize()                                     # elastic response + initial rates (setup, untimed)
     torch.cuda.synchronize()
+    note(f"elastic response solved in {eq.ksp_log[-1][0]} iterations")
 
     for _ in range(args.warmup):
         sim.step()
     torch.cuda.synchronize()
     ctx.barrier()
+    note("warm-up done")
 
     # ---- device-resident timing
     clocks = ClockSampler(local)
@@ -230,6 +240,7 @@ def run_b200(args):
     ctx.barrier()
     ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
     clk = clocks.stop()
+    note(f"timed steps done: {ms / args.steps:.1f} ms/step")
     launches = eng.launches - launches0
     iters = sum(r["iterations"] for r in recs)
     ksp_its = sum(r["ksp_iterations"] for r in recs)

@@ -152,6 +152,7 @@ struct P2P {
   double* local;                          // this rank's mailbox (cudaMalloc)
   double* remote[SIC_P2P_MAX_RANKS];      // peers' mailboxes mapped into this process (remote[rank] == local)
   unsigned* counters;                     // [n_ranks] blocks-done counters (device)
+  unsigned long long* gbar;               // device: halo blocks that have finished READING vec, over all exchanges
   int* error;                             // device flag: a wait timed out
   unsigned long long epoch;               // nodal (halo) exchanges issued so far (identical on every rank)
   unsigned long long epoch_s;             // scalar exchanges issued so far; own counter so that two consecutive
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
   __syncthreads();                           // CTA-scope ordering of everybody's stores before thread 0's fence
   if (threadIdx.x == 0) {
     __threadfence_system();                  // cumulative: covers the whole CTA's remote stores
+    atomicAdd(ctx.gbar, 1ull);               // this block no longer reads vec
     const unsigned done = atomicAdd(ctx.counters + p, 1u);
     if (done == SIC_P2P_BPP - 1) {           // last chunk for this peer: publish
       ctx.counters[p] = 0;
@@ -235,6 +237,12 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     int good = 1;
     while (*flag != epoch + 1) {
       if (clock64() - t0 > 20000000000ll) { good = 0; atomicExch(ctx.error, 1); break; }   // ~10 s
+    }
+    // A node shared by three ranks sits in two neighbours' lists: nobody may ADD to vec before every halo
+    // block of this launch has finished READING its part of vec (grid-wide barrier; all blocks are resident).
+    const unsigned long long target = (epoch + 1) * (unsigned long long)n_halo_blocks;
+    while (*(volatile unsigned long long*)ctx.gbar < target) {
+      if (clock64() - t0 > 20000000000ll) { good = 0; atomicExch(ctx.error, 1); break; }
     }
     __threadfence_system();
     ok = good;
@@ -257,10 +265,12 @@ extern "C" int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, 
   const size_t bytes = sizeof(double) * c->slot_doubles * 2 * n_ranks;
   if (int rc = sic_check_cuda(cudaMalloc((void**)&c->local, bytes), "cudaMalloc mailbox")) return rc;
   if (int rc = sic_check_cuda(cudaMemset(c->local, 0, bytes), "memset mailbox")) return rc;
-  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->counters, sizeof(unsigned) * SIC_P2P_MAX_RANKS + sizeof(int)), "cudaMalloc"))
+  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->counters, sizeof(unsigned) * SIC_P2P_MAX_RANKS + 2 * sizeof(unsigned long long)),
+                              "cudaMalloc"))
     return rc;
-  cudaMemset(c->counters, 0, sizeof(unsigned) * SIC_P2P_MAX_RANKS + sizeof(int));
-  c->error = (int*)(c->counters + SIC_P2P_MAX_RANKS);
+  cudaMemset(c->counters, 0, sizeof(unsigned) * SIC_P2P_MAX_RANKS + 2 * sizeof(unsigned long long));
+  c->gbar = (unsigned long long*)(c->counters + SIC_P2P_MAX_RANKS);
+  c->error = (int*)(c->gbar + 1);
   cudaIpcMemHandle_t h;
   if (int rc = sic_check_cuda(cudaIpcGetMemHandle(&h, c->local), "cudaIpcGetMemHandle")) return rc;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
