@@ -66,9 +66,11 @@ class LinearMomentumBase:
 
 
 class LinearMomentum(LinearMomentumBase):
+    engine_cls = Engine      # the device back end (the test-suite's host emulation substitutes its own subclass)
+
     def __init__(self, grid, theta: float, device="cuda"):
         self.grid, self.theta = grid, float(theta)
-        self.engine = Engine(grid.tetmesh.coords, grid.tetmesh.cells, device=device)
+        self.engine = self.engine_cls(grid.tetmesh.coords, grid.tetmesh.cells, device=device)
         eng = self.engine
         self.n_elems, self.n_nodes = eng.N, eng.M
         dev = eng.device

@@ -71,6 +71,41 @@ class SicError(RuntimeError):
     pass
 
 
+def declare(lib, single_gpu_only=False):
+    """Attach the prototypes of include/safeincave_cuda.h to a loaded library handle."""
+    lib.sic_last_error.restype = c_char_p
+    lib.sic_abi_version.restype = c_int
+    PP = POINTER(SicProblem)
+    lib.sic_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.sic_tangent.argtypes = [PP, c_double, c_double, c_void_p]
+    lib.sic_elastic_tangent.argtypes = [PP, c_void_p]
+    lib.sic_post.argtypes = [PP, c_void_p, c_double, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]
+    lib.sic_post_blocks.argtypes = [c_int]
+    lib.sic_commit.argtypes = [PP, c_double, c_double, c_void_p]
+    lib.sic_commit_rates.argtypes = [PP, c_void_p]
+    lib.sic_desai_initial_hardening.argtypes = [PP, c_int, c_double, c_void_p, c_void_p]
+    lib.sic_apply.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p]
+    PH = POINTER(SicHalo)
+    lib.sic_residual0.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_block_jacobi.argtypes = [PP, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_neumann.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
+    lib.sic_ksp_workspace_doubles.restype = c_int64
+    lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
+    if not single_gpu_only:
+        lib.sic_comm_unique_id.argtypes = [c_void_p]
+        lib.sic_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
+        lib.sic_comm_destroy.argtypes = [c_void_p]
+        lib.sic_halo_sum.argtypes = [PH, c_void_p, c_int, c_void_p]
+        lib.sic_allreduce_sum.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+        lib.sic_p2p_create.argtypes = [c_int, c_int, c_int, POINTER(c_void_p), c_void_p]
+        lib.sic_p2p_connect.argtypes = [c_void_p, c_void_p]
+        lib.sic_p2p_destroy.argtypes = [c_void_p]
+        lib.sic_p2p_error.argtypes = [c_void_p]
+        lib.sic_exchange.argtypes = [PH, c_void_p, c_int, c_void_p, c_int, c_void_p]
+
+
 _lib = None
 
 
@@ -87,38 +122,10 @@ def load():
     missing = [s for s in EXPORTS if not hasattr(lib, s)]
     if missing:
         raise SicError(f"libsafeincave_cuda.so lacks symbols {missing}")
-    lib.sic_last_error.restype = c_char_p
     lib.sic_abi_version.restype = c_int
     if lib.sic_abi_version() != SIC_ABI_VERSION:
         raise SicError("libsafeincave_cuda.so ABI version mismatch; rebuild")
-    PP = POINTER(SicProblem)
-    lib.sic_device_info.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_int)]
-    lib.sic_tangent.argtypes = [PP, c_double, c_double, c_void_p]
-    lib.sic_elastic_tangent.argtypes = [PP, c_void_p]
-    lib.sic_post.argtypes = [PP, c_void_p, c_double, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]
-    lib.sic_post_blocks.argtypes = [c_int]
-    lib.sic_commit.argtypes = [PP, c_double, c_double, c_void_p]
-    lib.sic_commit_rates.argtypes = [PP, c_void_p]
-    lib.sic_desai_initial_hardening.argtypes = [PP, c_int, c_double, c_void_p, c_void_p]
-    lib.sic_apply.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p]
-    PH = POINTER(SicHalo)
-    lib.sic_residual0.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
-    lib.sic_block_jacobi.argtypes = [PP, c_void_p, c_void_p, PH, c_void_p]
-    lib.sic_comm_unique_id.argtypes = [c_void_p]
-    lib.sic_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
-    lib.sic_comm_destroy.argtypes = [c_void_p]
-    lib.sic_halo_sum.argtypes = [PH, c_void_p, c_int, c_void_p]
-    lib.sic_allreduce_sum.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
-    lib.sic_p2p_create.argtypes = [c_int, c_int, c_int, POINTER(c_void_p), c_void_p]
-    lib.sic_p2p_connect.argtypes = [c_void_p, c_void_p]
-    lib.sic_p2p_destroy.argtypes = [c_void_p]
-    lib.sic_p2p_error.argtypes = [c_void_p]
-    lib.sic_exchange.argtypes = [PH, c_void_p, c_int, c_void_p, c_int, c_void_p]
-    lib.sic_neumann.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
-    lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
-    lib.sic_ksp_workspace_doubles.restype = c_int64
-    lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
-    lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
+    declare(lib)
     _lib = lib
     return lib
 

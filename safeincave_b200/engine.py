@@ -75,6 +75,10 @@ class Engine:
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SicError("safeincave_b200 needs a CUDA device (no CPU fallback)")
+        self._setup(coords, cells, device)
+
+    def _setup(self, coords, cells, device):
+        """Allocate and fill every buffer of sic_problem_t (torch index plumbing, once per mesh)."""
         self.device = torch.device(device)
         coords = torch.as_tensor(coords, dtype=torch.float64).to(self.device).contiguous()
         cells = torch.as_tensor(cells).to(self.device, dtype=torch.int64).contiguous()

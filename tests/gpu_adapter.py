@@ -68,6 +68,8 @@ class GpuMaterial:
     G = None
     B = None
 
+    engine_cls = Engine          # tests/hostemu swaps in EmuEngine to run the same kernels on the host
+
     def __init__(self, g, dtype=torch.float64):
         t = lambda a: torch.tensor(np.asarray(a), dtype=dtype)
         spec = [str(s) for s in g["spec"]]
@@ -88,7 +90,7 @@ class GpuMaterial:
             elif kind == "thermo":
                 mat.add_to_thermoelastic(sf.Thermoelastic(P(kind, "alpha")))
         coords, cells = disjoint_tets(N)
-        self.eng = Engine(coords, cells)
+        self.eng = self.engine_cls(coords, cells)
         mat.bind(self.eng)
         self.mat = mat
         self.elems = [GpuElemView(self.eng, i) for i in range(len(self.eng.elems))]

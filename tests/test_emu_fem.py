@@ -1,0 +1,26 @@
+"""The parity tests of tests/test_gpu_fem.py (operator, RHS, preconditioner blocks, Krylov solves, whole
+time steps against oracle/fem.py), executed on the HOST through tests/hostemu: the product's own kernels
+and drivers (fem.cu, solver.cu, constitutive.cu), compiled by g++ against a CUDA emulation layer.
+What this covers that `-m "not gpu"` otherwise could not: indexing, scatter plans, reductions, the
+device-resident Krylov recurrences and the Simulator_M loop.  What it cannot cover: nvcc code generation
+and real concurrency (atomics, memory ordering) -- that is what `-m gpu` is for."""
+import pytest
+
+from tests import test_gpu_fem as G
+
+
+@pytest.fixture(scope="module")
+def sf():
+    import safeincave_b200 as sf
+    from tests.hostemu import EmuEngine
+    old = sf.LinearMomentum.engine_cls
+    sf.LinearMomentum.engine_cls = EmuEngine
+    yield sf
+    sf.LinearMomentum.engine_cls = old
+
+
+test_operator_rhs_blocks_strain = G.test_operator_rhs_blocks_strain
+test_neumann_and_body_force = G.test_neumann_and_body_force
+test_time_steps_triaxial_cube = G.test_time_steps_triaxial_cube
+test_time_steps_triaxial_cube_with_desai = G.test_time_steps_triaxial_cube_with_desai
+test_krylov_solve_matches_direct = G.test_krylov_solve_matches_direct
