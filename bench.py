@@ -49,6 +49,11 @@ def parse():
                     help="1: Chronopoulos-Gear CG (one reduction per iteration); only sound for SYMMETRIC tangents -- it "
                          "diverges on the reference's non-symmetric finite-difference tangent (SURVEY T3), hence off")
     ap.add_argument("--max-it", type=int, default=0, help="debug: cap Krylov iterations per solve (timing experiments)")
+    ap.add_argument("--pc", default="auto", choices=["auto", "mg", "jacobi"],
+                    help="preconditioner of the Krylov solve: mg = geometric multigrid V-cycle on the refinement hierarchy "
+                         "(csrc/mg.cu, single GPU), jacobi = nodal 3x3 block Jacobi; auto = mg when a probe solve on a "
+                         "smaller mesh (run in a child process) reproduces the block-Jacobi solution, else jacobi")
+    ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -169,6 +174,60 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+# multigrid probe: does the V-cycle preconditioned CG reproduce the block-Jacobi CG solution on this box?
+# ----------------------------------------------------------------------------------------------
+def probe_mg(levels=2, device="cuda:0"):
+    """Elastic response of the cavern case on cavern_regular x8^levels with both preconditioners (both are this
+    repo's CUDA paths).  Prints MG_PROBE_OK / MG_PROBE_FAIL; run in a child process so that a device fault in the
+    newer code path cannot take the benchmark down with it."""
+    import torch
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    dev = torch.device(device)
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz")), levels, device=dev)
+    grid = sf.GridHandlerGMSH.from_hierarchy(h)
+    case = cases.cavern_case(grid, n_steps=1, ksp_type="cg", rtol=1e-10)
+    out = {}
+    for pc in ("jacobi", "mg"):
+        eq, sim = cases.build(case, grid, device=dev)
+        eq.solver.getPC().setType("mg" if pc == "mg" else "asm")
+        sim.verbose = False
+        sim.initialize()
+        rec = sim.step()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        out[pc] = (eq.X.clone(), [k[0] for k in eq.ksp_log], [k[1] for k in eq.ksp_log], rec)
+        del eq, sim
+    xj, xm = out["jacobi"][0], out["mg"][0]
+    err = float((xj - xm).abs().max() / xj.abs().max())
+    its_m, its_j = out["mg"][1], out["jacobi"][1]
+    ok = err < 1e-7 and all(r > 0 for r in out["mg"][2]) and max(its_m) <= 80 and out["mg"][3]["converged"] \
+        and out["mg"][3]["iterations"] == out["jacobi"][3]["iterations"]
+    print(f"{'MG_PROBE_OK' if ok else 'MG_PROBE_FAIL'} rel_diff={err:.2e} mg_its={its_m} jacobi_its={its_j}", flush=True)
+    return 0 if ok else 1
+
+
+def decide_pc(args, world, note):
+    if args.pc != "auto":
+        return args.pc, "forced by --pc"
+    if world > 1:
+        return "jacobi", "multigrid path is single-GPU in this version"
+    if args.levels < 1 or args.ksp != "cg":
+        return "jacobi", "no refinement hierarchy / KSP type is not cg"
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-mg"], capture_output=True, text=True,
+                           timeout=900)
+        tail = [ln for ln in r.stdout.splitlines() if ln.startswith("MG_PROBE")]
+        msg = tail[-1] if tail else f"probe exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] }"
+        note(f"multigrid probe: {msg}")
+        return ("mg" if r.returncode == 0 and tail and tail[-1].startswith("MG_PROBE_OK") else "jacobi"), msg
+    except Exception as e:      # timeout, spawn failure
+        return "jacobi", f"probe failed: {e!r}"
+
+
+# ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -189,12 +248,19 @@ def run_b200(args):
     local = dev.index or 0
     note(f"process group up, world {world}")
 
+    pc, pc_why = decide_pc(args, world, note)
     tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
-    for _ in range(args.levels):
-        tm = red_refine(tm, device=dev)
-    tm = morton_order(tm, device=dev)
-    note(f"mesh refined and ordered: {tm.n_cells} cells")
-    grid_global = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    if pc == "mg":
+        from safeincave_b200.multigrid import refine_hierarchy
+        hierarchy = refine_hierarchy(tm, args.levels, device=dev)      # every level kept, each in Morton order
+        tm = hierarchy.finest
+        grid_global = sf.GridHandlerGMSH.from_hierarchy(hierarchy)
+    else:
+        for _ in range(args.levels):
+            tm = red_refine(tm, device=dev)
+        tm = morton_order(tm, device=dev)
+        grid_global = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    note(f"mesh refined and ordered: {tm.n_cells} cells; preconditioner: {pc} ({pc_why})")
     n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
     case = cases.cavern_case(grid_global, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
     if world > 1:            # strong scaling: the SAME mesh, cells partitioned along the Morton curve
@@ -204,6 +270,8 @@ def run_b200(args):
         grid, part = grid_global, None
         eq, sim = cases.build(case, grid, device=dev)
     sim.verbose = False
+    if pc == "mg":
+        eq.solver.getPC().setType("mg")
     eq.solver.initial_guess_nonzero = bool(args.warm_start)
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
@@ -305,7 +373,7 @@ def run_b200(args):
     if os.path.isfile(tpath):        # ncu --set full capture at 918 144 cells; DRAM traffic scales with the cell count
         ref = json.load(open(tpath))
         traffic = int(ref["918144"] * N_loc / 918144)
-    roofline = {"bound": "hbm", "kernel": "k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain",
+    roofline = {"bound": "hbm", "kernel": "k_mg_ebe (finest level)" if pc == "mg" else ("k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": op_ms, "launches_sampled": eng.op_samples, "launches_in_timed_region": op_launches,
@@ -319,7 +387,9 @@ def run_b200(args):
                    "cells_per_gpu": N_loc, "partition": "Morton-curve chunks, interface nodes duplicated, NCCL halo sum "
                    "+ 2 scalar allreduces per CG iteration" if world > 1 else "single GPU",
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
-                   "preconditioner": "nodal 3x3 block Jacobi", "warm_start": bool(args.warm_start),
+                   "preconditioner": ("geometric multigrid V(2,2), Chebyshev/block-Jacobi smoother, Galerkin coarse tangents, "
+                                      f"{args.levels + 1} levels") if pc == "mg" else "nodal 3x3 block Jacobi",
+                   "pc_choice": pc_why, "warm_start": bool(args.warm_start),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
         "clocks": clk, "gpu_launches": launches, "roofline": roofline, "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,
@@ -338,6 +408,8 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.probe_mg:
+        sys.exit(probe_mg())
     if a.impl == "reference":
         run_reference(a)
     else:

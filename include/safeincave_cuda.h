@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 5
+#define SIC_ABI_VERSION 6
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -262,6 +262,54 @@ int64_t sic_ksp_workspace_doubles(int n_nodes, int method);
  * dinv: block-Jacobi blocks from sic_block_jacobi. */
 int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
                   const uint8_t* fixed, const double* dinv, double* work, const sic_halo_t* halo, void* stream);
+
+/* ---- part (3b): geometric multigrid preconditioner on a nested red-refinement hierarchy ------------- */
+/* The synthetic 10M-80M cell meshes of BASELINE config 5 are built by regular (Bey) refinement of a gmsh
+ * grid, so every level of the hierarchy is available.  P1 spaces on nested meshes are nested, children of a
+ * cell have equal volume and the parent's shape-function gradients, hence the GALERKIN coarse operator
+ * P^T K P is exactly the same matrix-free operator evaluated with the arithmetic mean of the eight children's
+ * C_T: coarse levels are sic_problem_t's of their own and reuse the operator kernel.  Smoother: Chebyshev
+ * polynomial in (block-Jacobi)^-1 K; cycle: V(nu,nu); coarsest level: a longer Chebyshev sweep.  Used as the
+ * preconditioner of CG in place of the reference's PETSc PC (MomentumEquation.py:1023-1025; `gamg` in
+ * examples/mechanics/nobian/run_interlayer.py:2114-2116).  Level 0 is the COARSEST mesh. */
+#define SIC_MG_MAX_LEVELS 8
+
+typedef struct {
+  sic_problem_t prob;      /* operator of the level: mesh, tiles, scatter plan, CT (coarse levels: CT is an output of
+                              sic_mg_setup; constitutive fields may be NULL) */
+  const uint8_t* fixed;    /* [3 n_nodes] Dirichlet mask of the level */
+  double* dinv;            /* [9 n_nodes] inverted nodal blocks (output of sic_mg_setup) */
+  double lambda_max;       /* largest eigenvalue estimate of dinv*K (output of sic_mg_setup) */
+  /* relation to the next COARSER level (NULL on level 0) */
+  const int32_t* parent_a; /* [n_nodes] coarse node(s) this node interpolates from: a == b for a node that */
+  const int32_t* parent_b; /*           exists on the coarse mesh, else the two ends of the bisected edge  */
+  const int32_t* rst_ptr;  /* [n_coarse_nodes + 1] CSR over coarse nodes ...                                 */
+  const int32_t* rst_idx;  /* [2 n_nodes] ... of the nodes of THIS level they restrict from, weight 1/2 each */
+  const int32_t* children; /* [8][n_coarse_cells] cells of this level that refine each coarse cell           */
+  /* work vectors, [3 n_nodes] each */
+  double *x, *b, *r, *d, *t;
+} sic_mg_level_t;
+
+typedef struct {
+  int32_t nu;              /* Chebyshev degree of the pre- and of the post-smoother (2) */
+  int32_t coarse_its;      /* Chebyshev steps on level 0 (20) */
+  double smooth_lo;        /* smoother targets eigenvalues in [smooth_lo, 1] * lambda_max (0.1) */
+  double coarse_lo;        /* same for the coarsest level (0.02) */
+  double safety;           /* lambda_max is the power-iteration estimate times this (1.15) */
+  int32_t power_its;       /* power iterations per level in sic_mg_setup (>= 2, default 16); 0: keep lambda_max as it is */
+} sic_mg_opts_t;
+
+/* Once per tangent: restrict C_T down the hierarchy (mean of the 8 children), build the block-Jacobi blocks of
+ * every level and estimate lambda_max.  levels[n_levels-1].prob is the fine problem (its CT is the input). */
+int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes);   /* of the FINEST level; one workspace serves all calls */
+int sic_mg_setup(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);
+
+/* CG preconditioned by one V-cycle, same contract as sic_ksp_solve (ksp->method is ignored; single GPU). */
+int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, sic_ksp_t* ksp,
+                 const double* b_ext, double* x, double* work, void* stream);
+
+/* z = V-cycle(r) alone (tests, and users who bring their own Krylov method): reads levels[top].b, writes .x */
+int sic_mg_vcycle(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-free DFMA chains; returns achieved FLOP/s in *flops (used to record the FP64 peak) */

@@ -108,6 +108,14 @@ class GridHandlerGMSH:
     def from_mesh(cls, tetmesh: TetMesh, reorder=True):
         return cls(tetmesh=tetmesh, reorder=reorder)
 
+    @classmethod
+    def from_hierarchy(cls, hierarchy):
+        """Grid on the finest level of a ``multigrid.Hierarchy``; the coarser levels stay attached
+        (``grid.hierarchy``) for the multigrid preconditioner (PC type ``mg``)."""
+        grid = cls(tetmesh=hierarchy.finest, reorder=False)
+        grid.hierarchy = hierarchy
+        return grid
+
     # --- tag queries (Grid.py:392-494)
     def get_boundary_names(self):
         return list(self.dolfin_tags[2].keys())
@@ -157,6 +165,8 @@ class GridHandlerGMSH:
         self._smoother = True
 
     def __getattr__(self, name):
+        if name == "hierarchy":
+            return None
         if name in ("A_csr", "B_csr", "smoother"):
             self.build_smoother()
             return self.__dict__[name]

@@ -91,6 +91,8 @@ class LinearMomentum(LinearMomentumBase):
         self.eps_tot = CellField(eng, eng.eps)
         self._nodes_vol = None
         self.dist = None                    # safeincave_b200.distributed.DistContext when partitioned
+        self.mg = None                      # multigrid.Multigrid, built on the first solve with PC type "mg"
+        self.mg_options = {}                # nu, coarse_its, smooth_lo, coarse_lo, safety, power_its
 
     # ------------------------------------------------------------------ configuration
     def set_material(self, material: Material):
@@ -165,10 +167,30 @@ class LinearMomentum(LinearMomentumBase):
             self.X.zero_()                                   # PETSc default: zero initial guess
         x = self.X.reshape(-1)
         to.where(self.fixed.bool(), self.u_prescribed, x, out=x)
-        eng.block_jacobi(self.dinv, self.fixed)
         rtol, atol, max_it = ksp.effective()
+        if ksp.uses_multigrid(self.grid):
+            return self._linear_solve_mg(x, rtol, atol, max_it)
+        eng.block_jacobi(self.dinv, self.fixed)
         res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
                             max_it=max_it, check_every=ksp.check_every, guess_nonzero=ksp.initial_guess_nonzero)
+        ksp.record(res)
+        self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+        return res
+
+    def _linear_solve_mg(self, x, rtol, atol, max_it):
+        """CG preconditioned by a geometric-multigrid V-cycle on the grid's refinement hierarchy (csrc/mg.cu)."""
+        eng, ksp = self.engine, self.solver
+        if self.dist is not None and self.dist.world > 1:
+            raise NotImplementedError("the multigrid preconditioner is single-GPU in this version")
+        if ksp.getType().lower() != "cg":
+            raise NotImplementedError("PC type 'mg' is implemented for KSP type 'cg'")
+        if self.mg is None:
+            from .multigrid import Multigrid
+            self.mg = Multigrid(eng, self.grid.hierarchy, **self.mg_options)
+        self.mg.setup(self.fixed, self.dinv)
+        res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
+                            check_every=ksp.mg_check_every, guess_nonzero=ksp.initial_guess_nonzero,
+                            time_operator=eng.time_operator)
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
         return res

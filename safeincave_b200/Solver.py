@@ -7,7 +7,9 @@ is ``sic_ksp_solve`` (block-Jacobi CG / BiCGStab on the matrix-free operator):
     cg                       -> SIC_KSP_CG
     bicg, bcgs, gmres, ...   -> SIC_KSP_BICGSTAB   (non-symmetric tangents)
     preonly (+ lu)           -> SIC_KSP_BICGSTAB with rtol 1e-13
-    any PC type              -> nodal 3x3 block Jacobi
+    PC mg (or gamg on a grid that carries its refinement hierarchy, Grid.from_hierarchy)
+                             -> CG preconditioned by a geometric-multigrid V-cycle (csrc/mg.cu)
+    any other PC type        -> nodal 3x3 block Jacobi
 
 T10: the examples' max_it = 100 silently truncates PETSc solves on large meshes; here the solve runs
 to the requested rtol (``min_max_it``) unless ``respect_max_it`` is set.
@@ -36,6 +38,7 @@ class KSP:
         self.check_every = 25
         self.initial_guess_nonzero = False
         self.single_reduction = False      # cg -> Chronopoulos-Gear CG; symmetric (elastic) tangents only, see header
+        self.mg_max_it, self.mg_check_every = 500, 4
         self._its, self._rnorm, self._reason = 0, 0.0, 0
         self.total_iterations = 0
 
@@ -89,6 +92,13 @@ class KSP:
         if t == "cg":
             return L.KSP_CGCG if self.single_reduction else L.KSP_CG
         return L.KSP_BICGSTAB
+
+    def uses_multigrid(self, grid):
+        pc = self._pc.getType().lower()
+        has = getattr(grid, "hierarchy", None) is not None and grid.hierarchy.n_levels > 1
+        if pc == "mg" and not has:
+            raise ValueError("PC type 'mg' needs a grid built with GridHandlerGMSH.from_hierarchy(refine_hierarchy(...))")
+        return has and pc in ("mg", "gamg")
 
     def effective(self):
         rtol = 1e-13 if self._type.lower() == "preonly" else self.rtol

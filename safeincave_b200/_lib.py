@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 5
+SIC_ABI_VERSION = 6
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -30,6 +30,7 @@ EXPORTS = (
     "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
     "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
+    "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle",
 )
 
 
@@ -58,6 +59,21 @@ class SicKsp(ctypes.Structure):
                 ("iterations", c_int32), ("reason", c_int32),
                 ("rnorm", c_double), ("rnorm0", c_double),
                 ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double)]
+
+
+class SicMgLevel(ctypes.Structure):
+    _fields_ = [("prob", SicProblem), ("fixed", c_void_p), ("dinv", c_void_p), ("lambda_max", c_double),
+                ("parent_a", c_void_p), ("parent_b", c_void_p), ("rst_ptr", c_void_p), ("rst_idx", c_void_p),
+                ("children", c_void_p),
+                ("x", c_void_p), ("b", c_void_p), ("r", c_void_p), ("d", c_void_p), ("t", c_void_p)]
+
+
+class SicMgOpts(ctypes.Structure):
+    _fields_ = [("nu", c_int32), ("coarse_its", c_int32), ("smooth_lo", c_double), ("coarse_lo", c_double),
+                ("safety", c_double), ("power_its", c_int32)]
+
+
+SIC_MG_MAX_LEVELS = 8
 
 
 class SicHalo(ctypes.Structure):
@@ -93,6 +109,12 @@ def declare(lib, single_gpu_only=False):
     lib.sic_ksp_workspace_doubles.restype = c_int64
     lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
     lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
+    PL, PO = POINTER(SicMgLevel), POINTER(SicMgOpts)
+    lib.sic_mg_workspace_doubles.argtypes = [c_int, c_int]
+    lib.sic_mg_workspace_doubles.restype = c_int64
+    lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
+    lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     if not single_gpu_only:
         lib.sic_comm_unique_id.argtypes = [c_void_p]
         lib.sic_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]

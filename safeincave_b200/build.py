@@ -19,6 +19,7 @@ UNITS = [
     ("constitutive.cu", ["-fmad=false"]),
     ("fem.cu", []),
     ("solver.cu", []),
+    ("mg.cu", []),
     ("comm.cu", []),
 ]
 

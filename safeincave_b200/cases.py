@@ -29,7 +29,7 @@ ELEMENT_LIBRARY = {
 }
 
 
-def triaxial_case(grid, elements=("kelvin", "dislocation"), n_steps=None):
+def triaxial_case(grid, elements=("kelvin", "dislocation"), n_steps=None, ksp_override=None):
     t_final = 24 * hour
     names = grid.get_boundary_names()
     up = {n.upper(): n for n in names}
@@ -48,7 +48,7 @@ def triaxial_case(grid, elements=("kelvin", "dislocation"), n_steps=None):
                  dict(boundary=up["TOP"], direction=2, density=0.0, ref_pos=0.0, gravity=0.0,
                       values=[4.1 * MPa, 16 * MPa, 16 * MPa, 6 * MPa, 6 * MPa],
                       time_values=[0 * hour, 2 * hour, 14 * hour, 16 * hour, 24 * hour])],
-        ksp=dict(type="bicg", rtol=1e-12), desai_initial_hardening=False,
+        ksp=dict(type=ksp_override or "bicg", rtol=1e-12), desai_initial_hardening=False,
     )
     if n_steps is not None:
         case["t_final_run"] = n_steps * case["dt"]

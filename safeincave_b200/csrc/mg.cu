@@ -1,0 +1,579 @@
+// mg.cu — hot-path part (3b): geometric multigrid preconditioned CG on the nested red-refinement hierarchy.
+//
+// Replaces the PETSc preconditioner of `self.solver.solve(b, X)` (MomentumEquation.py:1023-1025; the
+// reference's examples use `asm`, `gamg` once: nobian/run_interlayer.py:2114-2116).  Block-Jacobi CG
+// (solver.cu) needs 300 / 660 / 1400 / 2800 iterations on the 14k / 115k / 918k / 7.3M-cell levels of
+// cavern_regular; one V(2,2) cycle per CG iteration keeps the count at ~25 on every level for ~6 operator
+// applications per iteration (scripts/mg_prototype.py).
+//
+// B200 design: every level is a sic_problem_t of its own and runs the SAME operator kernel
+// (ebe_tile_scatter, fem.cuh).  Coarse operators are Galerkin by construction: on nested P1 tets with
+// equal-volume children, P^T K P is the operator evaluated with the mean of the eight children's C_T, so
+// "coarsening" is one streaming pass over C_T per tangent (k_ct_coarsen).  The smoother is a Chebyshev
+// polynomial in (block-Jacobi)^-1 K: no dot products, hence no grid-wide reduction and no host
+// synchronisation anywhere inside the cycle; its coefficients are kernel arguments computed on the host
+// from lambda_max (a few power iterations per level per tangent).  Transfers are gather-only
+// (deterministic, no atomics): restriction walks a CSR of the fine nodes each coarse node receives from,
+// prolongation reads the two parents of each fine node.  Dirichlet dofs are kept at zero on every level.
+// The outer CG keeps its scalars on the device (as solver.cu does) and the host looks at them every
+// `check_every` iterations; every kernel of the cycle is a no-op once the `done` flag is up.
+#include <math.h>
+#include <string.h>
+
+#include "fem.cuh"
+
+namespace sic {
+
+struct MgScal {
+  double rz, pq, rr, rr0, rr_ref, alpha, beta, tol2;
+  double pw;            // power iteration: ||Dinv K v||^2 with ||v|| = 1
+  int done, iters, nanflag, reason;
+};
+static_assert(sizeof(MgScal) <= 64 * sizeof(double), "MgScal must fit the reserved workspace header");
+
+#define SIC_MG_HEADER 64    /* doubles reserved for MgScal */
+#define SIC_MG_COUNTERS 8   /* doubles reserved for the ticket counters of grid_reduce */
+
+enum { MG_OP_REF = 0, MG_OP_INIT_RR, MG_OP_INIT_RZ, MG_OP_RR, MG_OP_RZ, MG_OP_PW };
+
+struct MgFin {   // what the last block of a reducing kernel does with the grid total
+  MgScal* S; int op; double rtol, atol; int guess;
+  __device__ __forceinline__ void run(double tot) const {
+    switch (op) {
+      case MG_OP_REF: S->rr_ref = tot; break;
+      case MG_OP_INIT_RR: {
+        S->rr = tot; S->rr0 = tot;
+        const double ref = guess ? S->rr_ref : tot;
+        const double t = rtol * rtol * ref, a2 = atol * atol;
+        S->tol2 = (t > a2) ? t : a2;
+        S->iters = 0; S->nanflag = 0; S->reason = 0; S->done = 0;
+        if (!(tot == tot) || isinf(tot)) { S->nanflag = 1; S->done = 1; S->reason = -9; }
+        else if (tot <= S->tol2 || tot == 0.0) { S->done = 1; S->reason = (tot <= a2) ? 3 : 2; }
+        break;
+      }
+      case MG_OP_INIT_RZ: S->rz = tot; S->beta = 0.0; break;
+      case MG_OP_RR:
+        S->rr = tot; S->iters += 1;
+        if (!(tot == tot) || isinf(tot)) { S->nanflag = 1; S->done = 1; S->reason = -9; }
+        else if (tot <= S->tol2) { S->done = 1; }
+        break;
+      case MG_OP_RZ: S->beta = tot / S->rz; S->rz = tot; break;
+      case MG_OP_PW: S->pw = tot; break;
+    }
+  }
+};
+
+// ---- operator (the kernel of fem.cuh) ---------------------------------------------------------------
+__global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, const double* __restrict__ x,
+                                                            double* __restrict__ y, const int* done) {
+  __shared__ TileScratch sc;
+  ebe_tile_scatter<0>(P, x, y, sc, done);
+}
+
+// q = K p with the per-cell energies p.Kp summed per block (finished by k_mg_sum_pq)
+__global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+                                                                double* __restrict__ y, double* __restrict__ partials,
+                                                                const int* done) {
+  __shared__ TileScratch sc;
+  double v[1] = {ebe_tile_scatter<0>(P, x, y, sc, done)};
+  block_partials<1, SIC_TILE_CELLS>(v, partials);
+}
+
+__global__ void __launch_bounds__(1024) k_mg_sum_pq(const double* __restrict__ partials, int n, MgScal* S) {
+  if (S->done) return;
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n; k += 1024) a += partials[k];
+  a = warp_sum(a);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 32; ++k) tot += sh[k];
+    S->pq = tot;
+    S->alpha = S->rz / tot;
+  }
+}
+
+__device__ __forceinline__ void mg_precond3(const double* __restrict__ dinv, size_t n, const double r[3], double z[3]) {
+  const double* d = dinv + 9 * n;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) z[j] = __ldg(d + 3 * j) * r[0] + __ldg(d + 3 * j + 1) * r[1] + __ldg(d + 3 * j + 2) * r[2];
+}
+
+// ---- outer CG ---------------------------------------------------------------------------------------
+// z = fixed ? x : 0
+__global__ void k_mg_zero_free(int nd, double* __restrict__ z, const double* __restrict__ x,
+                               const uint8_t* __restrict__ fixed) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < nd) z[d] = fixed[d] ? x[d] : 0.0;
+}
+
+// sum a.b over all dofs
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int n_nodes, const double* __restrict__ a,
+                                                           const double* __restrict__ b, MgFin fin, int skip_if_done,
+                                                           double* __restrict__ partials, unsigned* counter) {
+  if (skip_if_done && fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (n < n_nodes) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[0] += a[3 * (size_t)n + j] * b[3 * (size_t)n + j];
+  }
+  grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
+}
+
+// x += alpha p ; r -= alpha q (fixed dofs: r = 0) ; rr = r.r -> convergence test
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int n_nodes, double* __restrict__ x,
+                                                                 double* __restrict__ r, const double* __restrict__ p,
+                                                                 const double* __restrict__ q,
+                                                                 const uint8_t* __restrict__ fixed, MgFin fin,
+                                                                 double* __restrict__ partials, unsigned* counter) {
+  if (fin.S->done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const double alpha = fin.S->alpha;
+  double v[1] = {0.0};
+  if (n < n_nodes) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t d = 3 * (size_t)n + j;
+      double rn = 0.0;
+      if (!fixed[d]) {
+        x[d] += alpha * p[d];
+        rn = r[d] - alpha * q[d];
+      }
+      r[d] = rn;
+      v[0] += rn * rn;
+    }
+  }
+  grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
+}
+
+// p = z + beta p (first: p = z ; fixed dofs: 0) ; q = 0
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_p(int nd, double* __restrict__ p, const double* __restrict__ z,
+                                                            double* __restrict__ q, const uint8_t* __restrict__ fixed,
+                                                            const MgScal* S, int first) {
+  if (S->done) return;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nd) return;
+  const double v = first ? z[d] : z[d] + S->beta * p[d];
+  p[d] = fixed[d] ? 0.0 : v;
+  q[d] = 0.0;
+}
+
+// ---- Chebyshev smoother -------------------------------------------------------------------------------
+// First step.  zero_guess: r = b, x = d = Dinv r / theta.  Otherwise t holds K x: r = b - t, d = Dinv r / theta,
+// x += d.  Leaves t = 0 for the next operator application.
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_first(int n_nodes, const double* __restrict__ b,
+                                                                  double* __restrict__ r, double* __restrict__ d,
+                                                                  double* __restrict__ x, double* __restrict__ t,
+                                                                  const double* __restrict__ dinv,
+                                                                  const uint8_t* __restrict__ fixed, double inv_theta,
+                                                                  int zero_guess, const int* done) {
+  if (*done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  double rn[3], zn[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const size_t k = 3 * (size_t)n + j;
+    double v = zero_guess ? b[k] : b[k] - t[k];
+    if (fixed[k]) v = 0.0;
+    rn[j] = v;
+    r[k] = v;
+    t[k] = 0.0;
+  }
+  mg_precond3(dinv, n, rn, zn);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const size_t k = 3 * (size_t)n + j;
+    const double dn = fixed[k] ? 0.0 : zn[j] * inv_theta;
+    d[k] = dn;
+    x[k] = zero_guess ? dn : x[k] + dn;
+  }
+}
+
+// Step k >= 1.  t holds K d: r -= t ; d = a d + c Dinv r ; x += d ; t = 0.
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, double* __restrict__ r,
+                                                                 double* __restrict__ d, double* __restrict__ x,
+                                                                 double* __restrict__ t, const double* __restrict__ dinv,
+                                                                 const uint8_t* __restrict__ fixed, double a, double c,
+                                                                 const int* done) {
+  if (*done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  double rn[3], zn[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const size_t k = 3 * (size_t)n + j;
+    const double v = fixed[k] ? 0.0 : r[k] - t[k];
+    rn[j] = v;
+    r[k] = v;
+    t[k] = 0.0;
+  }
+  mg_precond3(dinv, n, rn, zn);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const size_t k = 3 * (size_t)n + j;
+    const double dn = fixed[k] ? 0.0 : a * d[k] + c * zn[j];
+    d[k] = dn;
+    x[k] += dn;
+  }
+}
+
+// r -= t (t = K d of the last smoothing step): the true residual of x ; t = 0
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_resid(int nd, double* __restrict__ r, double* __restrict__ t,
+                                                             const uint8_t* __restrict__ fixed, const int* done) {
+  if (*done) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nd) return;
+  r[k] = fixed[k] ? 0.0 : r[k] - t[k];
+  t[k] = 0.0;
+}
+
+// ---- transfers ----------------------------------------------------------------------------------------
+// b_c = P^T r_f: every coarse node sums the fine nodes that interpolate from it, weight 1/2 per entry (a fine
+// node that IS the coarse node appears twice)
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_restrict(int n_coarse, const int32_t* __restrict__ ptr,
+                                                                const int32_t* __restrict__ idx,
+                                                                const double* __restrict__ r_f, double* __restrict__ b_c,
+                                                                const uint8_t* __restrict__ fixed_c, const int* done) {
+  if (*done) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_coarse) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const int e1 = __ldg(ptr + c + 1);
+  for (int e = __ldg(ptr + c); e < e1; ++e) {
+    const size_t f = 3 * (size_t)__ldg(idx + e);
+    s0 += r_f[f]; s1 += r_f[f + 1]; s2 += r_f[f + 2];
+  }
+  const size_t k = 3 * (size_t)c;
+  b_c[k] = fixed_c[k] ? 0.0 : 0.5 * s0;
+  b_c[k + 1] = fixed_c[k + 1] ? 0.0 : 0.5 * s1;
+  b_c[k + 2] = fixed_c[k + 2] ? 0.0 : 0.5 * s2;
+}
+
+// x_f += P x_c
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_prolong_add(int n_fine, const int32_t* __restrict__ pa,
+                                                                   const int32_t* __restrict__ pb,
+                                                                   const double* __restrict__ x_c, double* __restrict__ x_f,
+                                                                   const uint8_t* __restrict__ fixed_f, const int* done) {
+  if (*done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_fine) return;
+  const size_t a = 3 * (size_t)__ldg(pa + n), b = 3 * (size_t)__ldg(pb + n), k = 3 * (size_t)n;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (!fixed_f[k + j]) x_f[k + j] += 0.5 * (x_c[a + j] + x_c[b + j]);
+  }
+}
+
+// CT_c = mean of the eight children's CT_f (Galerkin coarse operator; both in the tiled SIC_CT_INDEX layout)
+__global__ void __launch_bounds__(128) k_mg_ct_coarsen(int n_coarse, const int32_t* __restrict__ children,
+                                                      const double* __restrict__ CT_f, double* __restrict__ CT_c) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_coarse) return;
+  int ch[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ch[j] = __ldg(children + (size_t)j * n_coarse + c);
+  for (int rc = 0; rc < 36; ++rc) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __ldg(CT_f + SIC_CT_INDEX(rc, ch[j]));
+    CT_c[SIC_CT_INDEX(rc, c)] = 0.125 * s;
+  }
+}
+
+// ---- power iteration for lambda_max(Dinv K) --------------------------------------------------------------
+__global__ void k_mg_pw_init(int nd, double* __restrict__ v, double* __restrict__ t, const uint8_t* __restrict__ fixed,
+                             double scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nd) return;
+  unsigned h = (unsigned)k * 2654435761u;      // deterministic pseudo-random start vector, all frequencies
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const double u = (double)(h & 0xffffu) / 65536.0 - 0.5;
+  v[k] = fixed[k] ? 0.0 : u * scale;
+  t[k] = 0.0;
+}
+
+// w = Dinv t (t = K v), fixed dofs 0, stored over t's companion vector w ; sums w.w
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_pw_step(int n_nodes, const double* __restrict__ t,
+                                                               double* __restrict__ w, const double* __restrict__ dinv,
+                                                               const uint8_t* __restrict__ fixed, MgFin fin,
+                                                               double* __restrict__ partials, unsigned* counter) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (n < n_nodes) {
+    double tn[3], zn[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tn[j] = fixed[3 * (size_t)n + j] ? 0.0 : t[3 * (size_t)n + j];
+    mg_precond3(dinv, n, tn, zn);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t k = 3 * (size_t)n + j;
+      const double wn = fixed[k] ? 0.0 : zn[j];
+      w[k] = wn;
+      v[0] += wn * wn;
+    }
+  }
+  grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
+}
+
+// v = w / ||w|| ; t = 0
+__global__ void k_mg_pw_scale(int nd, double* __restrict__ v, const double* __restrict__ w, double* __restrict__ t,
+                              const MgScal* S) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nd) return;
+  const double nrm = sqrt(S->pw);
+  v[k] = (nrm > 0.0) ? w[k] / nrm : 0.0;
+  t[k] = 0.0;
+}
+
+}  // namespace sic
+
+using namespace sic;
+
+static inline int mg_blocks(int n, int t) { return (n + t - 1) / t; }
+
+static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o) {
+  if (!lv || !o) return sic_fail("multigrid: null argument");
+  if (n_levels < 1 || n_levels > SIC_MG_MAX_LEVELS) return sic_fail("multigrid: bad number of levels");
+  if (o->nu < 1 || o->coarse_its < 1) return sic_fail("multigrid: nu and coarse_its must be >= 1");
+  if (!(o->smooth_lo > 0.0 && o->smooth_lo < 1.0 && o->coarse_lo > 0.0 && o->coarse_lo < 1.0))
+    return sic_fail("multigrid: smooth_lo / coarse_lo must lie in (0,1)");
+  for (int l = 0; l < n_levels; ++l) {
+    const sic_mg_level_t& L = lv[l];
+    if (L.prob.abi_version != SIC_ABI_VERSION) return sic_fail("multigrid: sic_problem_t.abi_version mismatch");
+    if (!L.fixed || !L.dinv || !L.x || !L.b || !L.r || !L.d || !L.t || !L.prob.CT)
+      return sic_fail("multigrid: level with a null buffer");
+    if (l > 0) {
+      if (!L.parent_a || !L.parent_b || !L.rst_ptr || !L.rst_idx || !L.children)
+        return sic_fail("multigrid: level without transfer tables");
+      if (L.prob.n_cells != 8 * lv[l - 1].prob.n_cells) return sic_fail("multigrid: levels are not nested 1:8");
+    }
+  }
+  return 0;
+}
+
+// scratch shared by the reducing kernels of one call (header + counters + block partials)
+struct MgWork {
+  MgScal* S; unsigned* counter; double* partials;
+};
+static MgWork mg_work(double* work) {
+  return MgWork{(MgScal*)work, (unsigned*)(work + SIC_MG_HEADER), work + SIC_MG_HEADER + SIC_MG_COUNTERS};
+}
+static int64_t mg_partial_slots(int n_cells, int n_nodes) {
+  return (int64_t)n_cells / SIC_TILE_CELLS + (int64_t)n_nodes / SIC_VEC_THREADS + 8;
+}
+
+extern "C" int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes) {
+  return SIC_MG_HEADER + SIC_MG_COUNTERS + mg_partial_slots(n_cells, n_nodes) + 3 * 3 * (int64_t)n_nodes;
+}
+
+static MgScal* g_mg_host = nullptr;   // pinned mirror of the device scalars
+static cudaEvent_t g_mg_ev[2] = {nullptr, nullptr};
+
+static int mg_host_mirror() {
+  if (g_mg_host) return 0;
+  return sic_check_cuda(cudaMallocHost((void**)&g_mg_host, sizeof(MgScal)), "cudaMallocHost");
+}
+
+// One Chebyshev sweep of `its` steps on level L for eigenvalues in [lo, 1] * lambda_max; b: right-hand side.
+// zero_guess != 0: x starts from 0.  On return r is the residual BEFORE the last update d (see mg_true_residual).
+static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, double lo, int zero_guess, const int* done,
+                        cudaStream_t st) {
+  const int nn = L.prob.n_nodes, nc = L.prob.n_cells;
+  const int nb = mg_blocks(nn, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
+  const double lmax = L.lambda_max, lmin = lo * lmax;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  if (!zero_guess) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.x, L.t, done);   // t = K x (t is 0 on entry)
+  k_mg_cheb_first<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta, zero_guess,
+                                                  done);
+  for (int k = 1; k < its; ++k) {
+    k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    k_mg_cheb_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
+                                                   2.0 * rho_new / delta, done);
+    rho = rho_new;
+  }
+  return sic_check_launch("multigrid: Chebyshev sweep");
+}
+
+// V(nu,nu) cycle: reads `b_top` as the right-hand side of the finest level, leaves the result in levels[top].x.
+// `done` points at a device int: every kernel is a no-op once it is non-zero.
+static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, const double* b_top, const int* done,
+                     cudaStream_t st, cudaEvent_t* time_top_apply) {
+  const int top = n_levels - 1;
+  for (int l = top; l >= 1; --l) {
+    const sic_mg_level_t& L = lv[l];
+    const sic_mg_level_t& C = lv[l - 1];
+    const double* b = (l == top) ? b_top : L.b;
+    if (int rc = mg_chebyshev(L, b, o->nu, o->smooth_lo, 1, done, st)) return rc;
+    const int nn = L.prob.n_nodes, nd = 3 * nn, cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+    if (time_top_apply && l == top) cudaEventRecord(time_top_apply[0], st);
+    k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
+    k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
+    k_mg_restrict<<<mg_blocks(C.prob.n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(
+        C.prob.n_nodes, L.rst_ptr, L.rst_idx, L.r, C.b, C.fixed, done);
+  }
+  {
+    const sic_mg_level_t& L = lv[0];
+    const double* b = (top == 0) ? b_top : L.b;
+    if (int rc = mg_chebyshev(L, b, o->coarse_its, o->coarse_lo, 1, done, st)) return rc;
+  }
+  for (int l = 1; l <= top; ++l) {
+    const sic_mg_level_t& L = lv[l];
+    const sic_mg_level_t& C = lv[l - 1];
+    const double* b = (l == top) ? b_top : L.b;
+    const int nn = L.prob.n_nodes;
+    k_mg_prolong_add<<<mg_blocks(nn, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nn, L.parent_a, L.parent_b, C.x, L.x,
+                                                                                 L.fixed, done);
+    if (int rc = mg_chebyshev(L, b, o->nu, o->smooth_lo, 0, done, st)) return rc;
+  }
+  return sic_check_launch("multigrid: V-cycle");
+}
+
+extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, double* work, void* stream) {
+  if (int rc = mg_check_levels(lv, n_levels, o)) return rc;
+  if (!work) return sic_fail("sic_mg_setup: null workspace");
+  if (o->power_its == 1) return sic_fail("sic_mg_setup: power_its must be 0 or >= 2");
+  if (int rc = mg_host_mirror()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // 1. Galerkin coarse tangents, fine to coarse
+  for (int l = n_levels - 1; l >= 1; --l) {
+    const int ncoarse = lv[l - 1].prob.n_cells;
+    if (ncoarse > 0)
+      k_mg_ct_coarsen<<<mg_blocks(ncoarse, 128), 128, 0, st>>>(ncoarse, lv[l].children, lv[l].prob.CT, lv[l - 1].prob.CT);
+  }
+  if (int rc = sic_check_launch("k_mg_ct_coarsen")) return rc;
+  MgWork W = mg_work(work);
+  // 2. block-Jacobi blocks and 3. lambda_max(Dinv K) by power iteration, level by level (x: v, d: w, t: K v)
+  for (int l = 0; l < n_levels; ++l) {
+    sic_mg_level_t& L = lv[l];
+    if (int rc = sic_block_jacobi(&L.prob, L.dinv, L.fixed, nullptr, stream)) return rc;
+    if (o->power_its <= 0) {
+      if (!(L.lambda_max > 0.0)) return sic_fail("sic_mg_setup: power_its = 0 needs lambda_max from an earlier call");
+      continue;
+    }
+    const int nn = L.prob.n_nodes, nd = 3 * nn, nc = L.prob.n_cells;
+    if (int rc = sic_check_cuda(cudaMemsetAsync(work, 0, sizeof(double) * (SIC_MG_HEADER + SIC_MG_COUNTERS), st),
+                                "memset mg scalars"))
+      return rc;
+    const int db = mg_blocks(nd, SIC_VEC_THREADS), nb = mg_blocks(nn, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
+    const int* never = &W.S->done;    // stays 0
+    k_mg_pw_init<<<db, SIC_VEC_THREADS, 0, st>>>(nd, L.x, L.t, L.fixed, 1.0);
+    for (int it = 0; it < o->power_its; ++it) {
+      k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.x, L.t, never);
+      // w = Dinv K v ; pw = w.w (= lambda^2 once v has unit length, i.e. from the second pass on)
+      k_mg_pw_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.t, L.d, L.dinv, L.fixed, MgFin{W.S, MG_OP_PW, 0.0, 0.0, 0},
+                                                   W.partials, W.counter);
+      if (it + 1 < o->power_its) k_mg_pw_scale<<<db, SIC_VEC_THREADS, 0, st>>>(nd, L.x, L.d, L.t, W.S);
+    }
+    if (int rc = sic_check_launch("multigrid: power iteration")) return rc;
+    cudaMemcpyAsync(g_mg_host, W.S, sizeof(MgScal), cudaMemcpyDeviceToHost, st);
+    if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "sic_mg_setup sync")) return rc;
+    const double lam = sqrt(g_mg_host->pw);
+    if (!(lam > 0.0) || isinf(lam)) return sic_fail("sic_mg_setup: power iteration failed (lambda_max not positive/finite)");
+    L.lambda_max = o->safety * lam;
+    if (int rc = sic_check_cuda(cudaMemsetAsync(L.t, 0, sizeof(double) * nd, st), "memset t")) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sic_mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, double* work, void* stream) {
+  if (int rc = mg_check_levels(lv, n_levels, o)) return rc;
+  if (!work) return sic_fail("sic_mg_vcycle: null workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!(lv[l].lambda_max > 0.0)) return sic_fail("sic_mg_vcycle: call sic_mg_setup first (lambda_max not set)");
+    if (int rc = sic_check_cuda(cudaMemsetAsync(lv[l].t, 0, sizeof(double) * 3 * lv[l].prob.n_nodes, st), "memset t"))
+      return rc;
+  }
+  if (int rc = sic_check_cuda(cudaMemsetAsync(work, 0, sizeof(double) * (SIC_MG_HEADER + SIC_MG_COUNTERS), st),
+                              "memset mg header"))
+    return rc;
+  MgWork W = mg_work(work);
+  return mg_vcycle(lv, n_levels, o, lv[n_levels - 1].b, &W.S->done, st, nullptr);
+}
+
+extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, sic_ksp_t* ksp,
+                            const double* b_ext, double* x, double* work, void* stream) {
+  if (int rc = mg_check_levels(lv, n_levels, o)) return rc;
+  if (!ksp || !b_ext || !x || !work) return sic_fail("sic_mg_solve: null argument");
+  if (int rc = mg_host_mirror()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  sic_mg_level_t& T = lv[n_levels - 1];
+  const sic_problem_t* p = &T.prob;
+  const uint8_t* fixed = T.fixed;
+  const int nn = p->n_nodes, nd = 3 * nn, nc = p->n_cells;
+  for (int l = 0; l < n_levels; ++l)
+    if (!(lv[l].lambda_max > 0.0)) return sic_fail("sic_mg_solve: call sic_mg_setup first (lambda_max not set)");
+  MgWork W = mg_work(work);
+  MgScal* S = W.S;
+  double* vec = W.partials + mg_partial_slots(nc, nn);
+  double *r = vec, *pp = vec + nd, *q = vec + 2 * (size_t)nd;
+  double* z = T.x;
+  if (int rc = sic_check_cuda(cudaMemsetAsync(work, 0, sizeof(double) * (SIC_MG_HEADER + SIC_MG_COUNTERS), st),
+                              "memset mg header"))
+    return rc;
+  if (int rc = sic_check_cuda(cudaMemsetAsync(vec, 0, sizeof(double) * 3 * (size_t)nd, st), "memset mg-cg vectors"))
+    return rc;
+  for (int l = 0; l < n_levels; ++l)
+    if (int rc = sic_check_cuda(cudaMemsetAsync(lv[l].t, 0, sizeof(double) * 3 * lv[l].prob.n_nodes, st), "memset t"))
+      return rc;
+  const int nb = mg_blocks(nn, SIC_VEC_THREADS), db = mg_blocks(nd, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
+  const int check = ksp->check_every > 0 ? ksp->check_every : 4;
+  const int guess = ksp->guess_nonzero ? 1 : 0;
+  const double rtol = ksp->rtol, atol = ksp->atol;
+  auto fin = [&](int op) { return MgFin{S, op, rtol, atol, guess}; };
+  ksp->op_samples = 0;
+  ksp->op_ms = 0.0;
+  cudaEvent_t* ev = nullptr;
+  if (ksp->time_operator) {
+    if (!g_mg_ev[0]) { cudaEventCreate(&g_mg_ev[0]); cudaEventCreate(&g_mg_ev[1]); }
+    ev = g_mg_ev;
+  }
+
+  if (guess) {   // reference norm of rtol: the residual of the zero guess (prescribed values only), as PETSc's ||b||
+    k_mg_zero_free<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, x, fixed);
+    if (int rc = sic_residual0(p, b_ext, pp, r, fixed, nullptr, stream)) return rc;
+    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, fin(MG_OP_REF), 0, W.partials, W.counter);
+  }
+  if (int rc = sic_residual0(p, b_ext, x, r, fixed, nullptr, stream)) return rc;
+  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
+  if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, nullptr)) return rc;
+  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
+  k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);   // p = z ; q = 0
+
+  int launched = 0;
+  while (true) {
+    cudaMemcpyAsync(g_mg_host, S, sizeof(MgScal), cudaMemcpyDeviceToHost, st);
+    if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "mg sync")) return rc;
+    if (ev && launched > 0) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { ksp->op_ms += ms; ksp->op_samples += 1; }
+    }
+    if (g_mg_host->done || launched >= ksp->max_it) break;
+    const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
+    for (int k = 0; k < batch; ++k) {
+      k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
+      k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, S);
+      k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, fin(MG_OP_RR), W.partials, W.counter);
+      if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, (k == 0) ? ev : nullptr)) return rc;
+      k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, fin(MG_OP_RZ), 1, W.partials, W.counter);
+      k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
+    }
+    launched += batch;
+    if (int rc = sic_check_launch("mg-cg batch")) return rc;
+  }
+  ksp->iterations = g_mg_host->iters;
+  ksp->rnorm = sqrt(g_mg_host->rr);
+  ksp->rnorm0 = sqrt(g_mg_host->rr0);
+  if (g_mg_host->nanflag) ksp->reason = -9;
+  else if (g_mg_host->done) ksp->reason = g_mg_host->reason ? g_mg_host->reason : 2;
+  else ksp->reason = -3;
+  return 0;
+}

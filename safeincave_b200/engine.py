@@ -71,14 +71,15 @@ class ElemState:
 
 
 class Engine:
-    def __init__(self, coords, cells, device="cuda"):
+    def __init__(self, coords, cells, device="cuda", operator_only=False):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SicError("safeincave_b200 needs a CUDA device (no CPU fallback)")
-        self._setup(coords, cells, device)
+        self._setup(coords, cells, device, operator_only)
 
-    def _setup(self, coords, cells, device):
-        """Allocate and fill every buffer of sic_problem_t (torch index plumbing, once per mesh)."""
+    def _setup(self, coords, cells, device, operator_only=False):
+        """Allocate and fill every buffer of sic_problem_t (torch index plumbing, once per mesh).
+        operator_only: a coarse multigrid level -- mesh, scatter plan and C_T, no constitutive state."""
         self.device = torch.device(device)
         coords = torch.as_tensor(coords, dtype=torch.float64).to(self.device).contiguous()
         cells = torch.as_tensor(cells).to(self.device, dtype=torch.int64).contiguous()
@@ -103,12 +104,13 @@ class Engine:
         self.geom_tiles[:, 1536:1664] = self.vol.reshape(nt, 128)
         self.geom_tiles[:, 1664:].view(torch.int32).copy_(self.conn.reshape(4, nt, 128).permute(1, 0, 2).reshape(nt, 512))
         self._build_scatter_plan()
-        z = lambda rows: torch.zeros((rows, ns), dtype=torch.float64, device=dev)
+        self.operator_only = bool(operator_only)
+        z = lambda rows: None if operator_only else torch.zeros((rows, ns), dtype=torch.float64, device=dev)
         self.sig, self.sig_k, self.eps, self.eps_prev = z(6), z(6), z(6), z(6)
         self.eps_rhs = z(6)
         self.CT = torch.zeros((ns // 128, 36, 128), dtype=torch.float64, device=dev)    # tiled, SIC_CT_INDEX
-        self.T = torch.zeros(ns, dtype=torch.float64, device=dev)     # MomentumEquation.py:116-117
-        self.T0 = torch.zeros(ns, dtype=torch.float64, device=dev)
+        z1 = lambda: None if operator_only else torch.zeros(ns, dtype=torch.float64, device=dev)
+        self.T, self.T0 = z1(), z1()                                  # MomentumEquation.py:116-117
         self.n_singular = torch.zeros(1, dtype=torch.int32, device=dev)
         self.n_clamped = torch.zeros(1, dtype=torch.int32, device=dev)
         self.err_out = torch.zeros(2, dtype=torch.float64, device=dev)

@@ -204,8 +204,10 @@ def orient_boundary(mesh: TetMesh):
 # ----------------------------------------------------------------------------------------------
 # refinement and ordering (torch: runs on the GPU for the 10M+ cell meshes)
 # ----------------------------------------------------------------------------------------------
-def red_refine(mesh: TetMesh, device="cpu") -> TetMesh:
-    """One level of Bey's red refinement.  Conforming; children of a parent are contiguous."""
+def red_refine(mesh: TetMesh, device="cpu", return_edges=False):
+    """One level of Bey's red refinement.  Conforming; children of a parent are contiguous (8p..8p+7), the
+    coarse nodes keep their ids and the midpoint of the k-th edge (sorted by (lo, hi)) gets id M + k.
+    return_edges: also return the (E,2) end nodes of those edges (the multigrid transfer tables need them)."""
     dev = torch.device(device)
     cells = torch.as_tensor(mesh.cells, device=dev)
     tris = torch.as_tensor(mesh.tris, device=dev)
@@ -239,8 +241,11 @@ def red_refine(mesh: TetMesh, device="cpu") -> TetMesh:
         new_ttags = torch.as_tensor(mesh.tri_tags, device=dev).repeat_interleave(4)
     else:
         new_tris, new_ttags = tris, torch.as_tensor(mesh.tri_tags, device=dev)
-    return TetMesh(new_coords.cpu().numpy(), new_cells.cpu().numpy(), new_ctags.cpu().numpy(),
+    fine = TetMesh(new_coords.cpu().numpy(), new_cells.cpu().numpy(), new_ctags.cpu().numpy(),
                    new_tris.cpu().numpy(), new_ttags.cpu().numpy(), mesh.names)
+    if return_edges:
+        return fine, torch.stack([lo, hi], dim=1).cpu().numpy()
+    return fine
 
 
 def _spread3(v):

@@ -1,0 +1,199 @@
+"""Nested red-refinement hierarchy and the transfer tables of the geometric multigrid preconditioner
+(host side: torch/numpy index plumbing, once per mesh; the arithmetic is csrc/mg.cu).
+
+The synthetic 10M-80M cell cavern meshes of BASELINE config 5 are regular refinements of a gmsh grid
+(SURVEY 8d), so every coarser level exists by construction.  ``refine_hierarchy`` keeps them all, each in
+its own Morton order, together with, per level l >= 1 relative to level l-1:
+
+    parent_a, parent_b  (M_l,)      the coarse node(s) a node interpolates from (a == b: it IS that node)
+    rst_ptr, rst_idx    CSR         for every coarse node the level-l nodes it restricts from (weight 1/2 each)
+    children            (8, N_{l-1}) the cells of level l refining each coarse cell
+    inject              (M_{l-1},)  level-l id of every coarse node (Dirichlet masks are injected through it)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .mesh import TetMesh, morton_order, red_refine
+
+
+@dataclass
+class Transfer:
+    parent_a: np.ndarray
+    parent_b: np.ndarray
+    rst_ptr: np.ndarray
+    rst_idx: np.ndarray
+    children: np.ndarray
+    inject: np.ndarray
+
+
+@dataclass
+class Hierarchy:
+    meshes: list = field(default_factory=list)        # level 0 = coarsest ... last = finest (each Morton-ordered)
+    transfers: list = field(default_factory=list)     # transfers[l] relates level l to l-1 (None for l = 0)
+
+    @property
+    def n_levels(self):
+        return len(self.meshes)
+
+    @property
+    def finest(self) -> TetMesh:
+        return self.meshes[-1]
+
+
+def _transfer(coarse: TetMesh, fine_raw: TetMesh, edges: np.ndarray, fine: TetMesh) -> Transfer:
+    Mc, Mf, Nc = coarse.n_nodes, fine.n_nodes, coarse.n_cells
+    pa_raw = np.concatenate([np.arange(Mc, dtype=np.int64), edges[:, 0]])
+    pb_raw = np.concatenate([np.arange(Mc, dtype=np.int64), edges[:, 1]])
+    nperm, cperm = fine.node_perm, fine.cell_perm        # new id i was raw id perm[i]
+    pa, pb = pa_raw[nperm], pb_raw[nperm]
+    inv_c = np.empty(8 * Nc, dtype=np.int64)
+    inv_c[cperm] = np.arange(8 * Nc)
+    children = np.ascontiguousarray(inv_c.reshape(Nc, 8).T)
+    inv_n = np.empty(Mf, dtype=np.int64)
+    inv_n[nperm] = np.arange(Mf)
+    inject = inv_n[:Mc]
+    rows = np.concatenate([pa, pb])
+    idx = np.concatenate([np.arange(Mf), np.arange(Mf)])
+    order = np.argsort(rows, kind="stable")
+    ptr = np.zeros(Mc + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum(np.bincount(rows, minlength=Mc))
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return Transfer(i32(pa), i32(pb), i32(ptr), i32(idx[order]), i32(children), i32(inject))
+
+
+def refine_hierarchy(base: TetMesh, levels: int, device="cpu") -> Hierarchy:
+    """``levels`` regular refinements of ``base``; returns all levels (level 0 = ``base`` in Morton order)."""
+    m0 = base if hasattr(base, "cell_perm") else morton_order(base, device=device)
+    h = Hierarchy([m0], [None])
+    for _ in range(levels):
+        coarse = h.meshes[-1]
+        raw, edges = red_refine(coarse, device=device, return_edges=True)
+        fine = morton_order(raw, device=device)
+        h.transfers.append(_transfer(coarse, raw, edges, fine))
+        h.meshes.append(fine)
+    return h
+
+
+def prolongation_matrix(t: Transfer, n_coarse_nodes: int):
+    """P (M_fine x M_coarse, scipy CSR) of one transfer: used by the tests to check the tables."""
+    import scipy.sparse as sp
+    Mf = t.parent_a.shape[0]
+    rows = np.concatenate([np.arange(Mf), np.arange(Mf)])
+    cols = np.concatenate([t.parent_a, t.parent_b]).astype(np.int64)
+    return sp.csr_matrix((np.full(2 * Mf, 0.5), (rows, cols)), shape=(Mf, n_coarse_nodes))
+
+
+# ----------------------------------------------------------------------------------------------
+# device side: one operator-only Engine per coarse level + the sic_mg_level_t array
+# ----------------------------------------------------------------------------------------------
+class Multigrid:
+    """V-cycle preconditioned CG on a ``Hierarchy`` (csrc/mg.cu through the C ABI).
+
+    The finest level IS the momentum equation's engine (its C_T is the tangent of the Newton iteration);
+    the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
+
+    def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=20, smooth_lo=0.1, coarse_lo=0.02,
+                 safety=1.15, power_its=16):
+        import ctypes
+
+        import torch
+
+        from . import _lib as L
+        from .engine import _ptr
+        self._L, self._ptr, self._ct, self._to = L, _ptr, ctypes, torch
+        if hierarchy.n_levels > L.SIC_MG_MAX_LEVELS:
+            raise L.SicError(f"at most {L.SIC_MG_MAX_LEVELS} multigrid levels")
+        fine = hierarchy.finest
+        if fine.n_cells != fine_engine.N or fine.n_nodes != fine_engine.M:
+            raise L.SicError("the hierarchy's finest level is not the mesh of the momentum equation")
+        self.h, self.fine = hierarchy, fine_engine
+        self.lib, dev = fine_engine.lib, fine_engine.device
+        self.engines = [type(fine_engine)(m.coords, m.cells, device=dev, operator_only=True)
+                        for m in hierarchy.meshes[:-1]] + [fine_engine]
+        self.opts = L.SicMgOpts(int(nu), int(coarse_its), float(smooth_lo), float(coarse_lo), float(safety), int(power_its))
+        n = hierarchy.n_levels
+        self.levels = (L.SicMgLevel * n)()
+        self._keep = []
+        zeros = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype, device=dev)
+        dt = lambda a: torch.as_tensor(a).to(dev).contiguous()
+        self.fixed, self.dinv, self.vec = [], [], []
+        for l, eng in enumerate(self.engines):
+            self.fixed.append(zeros(3 * eng.M, dtype=torch.uint8))
+            self.dinv.append(zeros(eng.M, 9))
+            self.vec.append({k: zeros(3 * eng.M) for k in "xbrdt"})
+            lv = self.levels[l]
+            lv.lambda_max = 0.0
+            if l > 0:
+                t = hierarchy.transfers[l]
+                tabs = {k: dt(getattr(t, k)) for k in ("parent_a", "parent_b", "rst_ptr", "rst_idx", "children", "inject")}
+                self._keep.append(tabs)
+                lv.parent_a, lv.parent_b = _ptr(tabs["parent_a"]), _ptr(tabs["parent_b"])
+                lv.rst_ptr, lv.rst_idx, lv.children = _ptr(tabs["rst_ptr"]), _ptr(tabs["rst_idx"]), _ptr(tabs["children"])
+            else:
+                self._keep.append(None)
+            for k in "xbrdt":
+                setattr(lv, k, _ptr(self.vec[l][k]))
+        need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
+        self.work = zeros(need)
+        self.launches_per_cycle = sum(2 * (2 * nu + 1) + 3 for _ in range(n - 1)) + 2 * coarse_its
+        self.setups = 0
+
+    def _refresh(self, fixed_fine=None, dinv_fine=None):
+        """Re-point the level structs at the engines' CURRENT buffers (the fine engine swaps sig/eps)."""
+        _ptr = self._ptr
+        n = len(self.engines)
+        if fixed_fine is not None:
+            self.fixed[-1] = fixed_fine
+        if dinv_fine is not None:
+            self.dinv[-1] = dinv_fine
+        for l, eng in enumerate(self.engines):
+            lv = self.levels[l]
+            lv.prob = eng.problem()
+            lv.fixed, lv.dinv = _ptr(self.fixed[l]), _ptr(self.dinv[l])
+
+    def setup(self, fixed_fine, dinv_fine):
+        """Once per tangent: inject the Dirichlet mask down the hierarchy, then sic_mg_setup (Galerkin C_T,
+        block-Jacobi blocks of every level, lambda_max)."""
+        L, torch = self._L, self._to
+        self._refresh(fixed_fine, dinv_fine)
+        for l in range(len(self.engines) - 1, 0, -1):
+            inj = self._keep[l]["inject"].long()
+            self.fixed[l - 1].view(-1, 3).copy_(self.fixed[l].view(-1, 3)[inj])
+        st = self.fine._stream()
+        L.check(self.lib.sic_mg_setup(self.levels, len(self.engines), self._ct.byref(self.opts), self._ptr(self.work), st),
+                "sic_mg_setup")
+        self.setups += 1
+        self.fine.launches += sum(1 + 2 + 3 * max(self.opts.power_its, 0) for _ in self.engines)
+
+    def lambda_max(self):
+        return [float(lv.lambda_max) for lv in self.levels]
+
+    def vcycle(self, r):
+        """z = M^-1 r (one V-cycle); r, z: (3 M_fine,) device tensors."""
+        L = self._L
+        self._refresh()
+        self.vec[-1]["b"].copy_(r)
+        L.check(self.lib.sic_mg_vcycle(self.levels, len(self.engines), self._ct.byref(self.opts), self._ptr(self.work),
+                                       self.fine._stream()), "sic_mg_vcycle")
+        return self.vec[-1]["x"]
+
+    def solve(self, b_ext, x, rtol=1e-10, atol=0.0, max_it=500, check_every=4, guess_nonzero=False, time_operator=False):
+        L, ct = self._L, self._ct
+        self._refresh()
+        ksp = L.SicKsp()
+        ksp.method, ksp.max_it, ksp.rtol, ksp.atol = 0, int(max_it), float(rtol), float(atol)
+        ksp.check_every, ksp.use_graph = int(check_every), 0
+        ksp.guess_nonzero = 1 if guess_nonzero else 0
+        ksp.time_operator = 1 if time_operator else 0
+        L.check(self.lib.sic_mg_solve(self.levels, len(self.engines), ct.byref(self.opts), ct.byref(ksp), self._ptr(b_ext),
+                                      self._ptr(x), self._ptr(self.work), self.fine._stream()), "sic_mg_solve")
+        eng = self.fine
+        eng.launches += 6 + (self.launches_per_cycle + 5) * (int(ksp.iterations) + 1)
+        eng.op_ms += float(ksp.op_ms)
+        eng.op_samples += int(ksp.op_samples)
+        nu, n = self.opts.nu, len(self.engines)
+        eng.op_launches += (1 + (2 * nu if n > 1 else self.opts.coarse_its)) * int(ksp.iterations)   # fine-level applies
+        return ksp

@@ -1,0 +1,115 @@
+"""Parity checks of the multigrid path, shared by the host-emulation tests (tests/test_emu_mg.py, run
+everywhere) and the B200 tests (tests/test_gpu_mg.py): the `sf` argument is the package with
+``LinearMomentum.engine_cls`` pointing at the back end under test."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import constitutive as oc
+from oracle import fem
+from oracle.mg import OracleMG
+from tests.case_oracle import oracle_simulator
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def make(sf, name, levels, case_fn, **kw):
+    from safeincave_b200 import cases
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(GOLD, f"mesh_{name}.npz")), levels)
+    grid = sf.GridHandlerGMSH.from_hierarchy(h)
+    case = case_fn(grid, **kw)
+    eq, sim = cases.build(case, grid)
+    eq.solver.setType("cg")
+    eq.solver.getPC().setType("mg")
+    return h, grid, case, eq, sim
+
+
+def random_tangent(n, seed, nonsym=0.0):
+    rng = np.random.default_rng(seed)
+    CT = oc.iso_matrix(102e9 * (1 + 0.5 * rng.random(n)), 0.3 * np.ones(n))
+    if nonsym:
+        CT = CT * (1.0 + nonsym * rng.standard_normal((n, 6, 6)))
+    return CT
+
+
+def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0):
+    """sic_mg_setup (Galerkin C_T, masks, blocks, lambda_max), one V-cycle and the full solve against the
+    assembled-matrix oracle and the sparse direct solve."""
+    from safeincave_b200 import cases
+    from safeincave_b200.multigrid import Multigrid
+    h, grid, case, eq, sim = make(sf, name, levels, cases.triaxial_case if name == "cube_coarse" else cases.cavern_case)
+    eng = eq.engine
+    N, M = eng.N, eng.M
+    CT = random_tangent(N, 7, nonsym)
+    eng.put_CT(CT)
+    eps_rhs = 1e-5 * np.random.default_rng(3).standard_normal((N, 6))
+    eng.put6(eng.eps_rhs, eps_rhs)
+    eq.bc.update_dirichlet(0.0)
+    eq.bc.update_neumann(0.0)
+    mg = Multigrid(eng, h)
+    mg.setup(eq.fixed, eq.dinv)
+    fixed = eq.fixed.cpu().numpy().astype(bool)
+    om = OracleMG(h.meshes, h.transfers, CT, fixed)
+    # coarse tangents = mean of the children, masks injected, blocks inverted
+    for l in range(h.n_levels):
+        assert relerr(mg.engines[l].get_CT(), om.CT[l]) < 1e-14
+        assert (mg.fixed[l].cpu().numpy().astype(bool) == om.fixed[l]).all()
+        blocks = mg.dinv[l].cpu().numpy().reshape(-1, 3, 3)
+        ref = np.stack([om.Dinv[l][3 * n:3 * n + 3, 3 * n:3 * n + 3].toarray() for n in range(0, h.meshes[l].n_nodes, 7)])
+        assert relerr(blocks[::7], ref) < 1e-10
+    # lambda_max: the power iteration approaches the largest eigenvalue (D^-1 K is not normal: not strictly from below); times `safety` it bounds it
+    lam_dev = mg.lambda_max()
+    for l in range(h.n_levels):
+        lam_ref = om.power_lambda(l, its=300)
+        assert 0.88 * lam_ref < lam_dev[l] / mg.opts.safety <= 1.03 * lam_ref, (l, lam_dev[l], lam_ref)
+        assert lam_dev[l] >= lam_ref, (l, lam_dev[l], lam_ref)
+    # one V-cycle, vector for vector (same lambda_max on both sides)
+    om.lam = lam_dev
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(3 * M) * (~fixed)
+    z = mg.vcycle(torch.as_tensor(r).to(eng.device)).cpu().numpy()
+    z_ref = om.vcycle(h.n_levels - 1, r)
+    assert relerr(z, z_ref) < 1e-10
+    # a second cycle on the same data gives the same answer (no state leaks between cycles)
+    z2 = mg.vcycle(torch.as_tensor(r).to(eng.device)).cpu().numpy()
+    assert relerr(z2, z) < 1e-14
+    # full solve against the sparse direct solve; iteration count as the oracle's PCG
+    eq.solver.setTolerances(rtol=1e-12)
+    res = eq._linear_solve()
+    assert res.reason > 0, f"not converged: {res.reason} after {res.iterations}"
+    osim = oracle_simulator(case, h.finest)
+    u_ref = osim._solve(CT, eps_rhs, 0.0)
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), u_ref) < 1e-9
+    dofs, vals, b_ext = osim._bc(0.0)
+    b = (b_ext + fem.rhs_eps(h.finest.coords, h.finest.cells, CT, eps_rhs))
+    u0 = np.zeros(3 * M)
+    u0[dofs] = vals
+    Kfull = fem.assemble_K(h.finest.coords, h.finest.cells, CT)
+    rhs = (b - Kfull @ u0) * (~fixed)
+    _, it_ref = om.pcg(rhs, rtol=1e-12)
+    assert abs(res.iterations - it_ref) <= 2, (res.iterations, it_ref)
+    return res.iterations
+
+
+def check_time_steps(sf, name, levels, case_fn, n_steps, tol=1e-8, **kw):
+    """Whole time steps with PC mg against the oracle's direct solves."""
+    h, grid, case, eq, sim = make(sf, name, levels, case_fn, n_steps=n_steps, **kw)
+    hist = sim.run()
+    osim = oracle_simulator(case, h.finest)
+    ohist = osim.run(0.0, [case["dt"]] * n_steps)
+    assert [x["iterations"] for x in hist] == [x["iters"] for x in ohist[1:]]
+    eng = eq.engine
+    last = ohist[-1]
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), last["u"]) < tol
+    assert relerr(eng.get6(eng.sig), last["sig"]) < tol
+    for e_gpu, e_or in zip(eng.elems, osim.mat.elems):
+        assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol
+    return hist

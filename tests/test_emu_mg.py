@@ -1,0 +1,34 @@
+"""Multigrid preconditioned CG (csrc/mg.cu) on the HOST through tests/hostemu, against oracle/mg.py
+(assembled matrices) and the sparse direct solve.  Same checks as tests/test_gpu_mg.py."""
+import pytest
+
+from tests import mg_checks as C
+
+
+@pytest.fixture(scope="module")
+def sf():
+    import safeincave_b200 as sf
+    from tests.hostemu import EmuEngine
+    old = sf.LinearMomentum.engine_cls
+    sf.LinearMomentum.engine_cls = EmuEngine
+    yield sf
+    sf.LinearMomentum.engine_cls = old
+
+
+def test_setup_vcycle_solve_cube(sf):
+    its = C.check_setup_vcycle_solve(sf, "cube_coarse", levels=2)
+    assert its <= 30
+
+
+def test_setup_vcycle_solve_cube_nonsymmetric_tangent(sf):
+    C.check_setup_vcycle_solve(sf, "cube_coarse", levels=2, nonsym=0.01)
+
+
+def test_time_steps_triaxial_cube_mg(sf):
+    from safeincave_b200 import cases
+    C.check_time_steps(sf, "cube_coarse", 2, cases.triaxial_case, 3, ksp_override="cg")
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SIC_SLOW"), reason="~80 s under emulation; set SIC_SLOW=1")
+def test_setup_vcycle_solve_cavern_regular(sf):
+    assert C.check_setup_vcycle_solve(sf, "cavern_regular", levels=1, nonsym=0.01) <= 40
