@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 6
+#define SIC_ABI_VERSION 7
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -288,6 +288,7 @@ typedef struct {
   const int32_t* children; /* [8][n_coarse_cells] cells of this level that refine each coarse cell           */
   /* work vectors, [3 n_nodes] each */
   double *x, *b, *r, *d, *t;
+  double* pv;              /* [3 n_nodes] or NULL: power-iteration vector kept BETWEEN calls of sic_mg_setup (warm start) */
 } sic_mg_level_t;
 
 typedef struct {
@@ -297,6 +298,7 @@ typedef struct {
   double coarse_lo;        /* same for the coarsest level (0.02) */
   double safety;           /* lambda_max is the power-iteration estimate times this (1.15) */
   int32_t power_its;       /* power iterations per level in sic_mg_setup (>= 2, default 16); 0: keep lambda_max as it is */
+  int32_t power_its_warm;  /* passes when restarting from pv of the previous setup (4); 0: always start cold */
 } sic_mg_opts_t;
 
 /* Once per tangent: restrict C_T down the hierarchy (mean of the 8 children), build the block-Jacobi blocks of

@@ -440,6 +440,7 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (int rc = mg_check_levels(lv, n_levels, o)) return rc;
   if (!work) return sic_fail("sic_mg_setup: null workspace");
   if (o->power_its == 1) return sic_fail("sic_mg_setup: power_its must be 0 or >= 2");
+  if (o->power_its_warm < 0) return sic_fail("sic_mg_setup: power_its_warm must be >= 0");
   if (int rc = mg_host_mirror()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // 1. Galerkin coarse tangents, fine to coarse
@@ -464,13 +465,19 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
       return rc;
     const int db = mg_blocks(nd, SIC_VEC_THREADS), nb = mg_blocks(nn, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
     const int* never = &W.S->done;    // stays 0
-    k_mg_pw_init<<<db, SIC_VEC_THREADS, 0, st>>>(nd, L.x, L.t, L.fixed, 1.0);
-    for (int it = 0; it < o->power_its; ++it) {
-      k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.x, L.t, never);
-      // w = Dinv K v ; pw = w.w (= lambda^2 once v has unit length, i.e. from the second pass on)
+    // The iterate lives in L.pv when the caller provides that persistent vector: the next setup then restarts
+    // from it (the tangent changes little between Newton iterations) and needs only power_its_warm passes.
+    double* v = L.pv ? L.pv : L.x;
+    const bool warm = L.pv && L.lambda_max > 0.0 && o->power_its_warm >= 1;
+    const int its = warm ? o->power_its_warm : o->power_its;
+    if (!warm) k_mg_pw_init<<<db, SIC_VEC_THREADS, 0, st>>>(nd, v, L.t, L.fixed, 1.0);
+    else if (int rc = sic_check_cuda(cudaMemsetAsync(L.t, 0, sizeof(double) * nd, st), "memset t")) return rc;
+    for (int it = 0; it < its; ++it) {
+      k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, v, L.t, never);
+      // w = Dinv K v ; pw = w.w (= lambda^2 once v has unit length: from the second pass on, or at once when warm)
       k_mg_pw_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.t, L.d, L.dinv, L.fixed, MgFin{W.S, MG_OP_PW, 0.0, 0.0, 0},
                                                    W.partials, W.counter);
-      if (it + 1 < o->power_its) k_mg_pw_scale<<<db, SIC_VEC_THREADS, 0, st>>>(nd, L.x, L.d, L.t, W.S);
+      if (it + 1 < its || L.pv) k_mg_pw_scale<<<db, SIC_VEC_THREADS, 0, st>>>(nd, v, L.d, L.t, W.S);
     }
     if (int rc = sic_check_launch("multigrid: power iteration")) return rc;
     cudaMemcpyAsync(g_mg_host, W.S, sizeof(MgScal), cudaMemcpyDeviceToHost, st);

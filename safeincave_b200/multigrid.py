@@ -96,7 +96,7 @@ class Multigrid:
     the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=20, smooth_lo=0.1, coarse_lo=0.02,
-                 safety=1.15, power_its=16):
+                 safety=1.15, power_its=16, power_its_warm=4):
         import ctypes
 
         import torch
@@ -113,7 +113,8 @@ class Multigrid:
         self.lib, dev = fine_engine.lib, fine_engine.device
         self.engines = [type(fine_engine)(m.coords, m.cells, device=dev, operator_only=True)
                         for m in hierarchy.meshes[:-1]] + [fine_engine]
-        self.opts = L.SicMgOpts(int(nu), int(coarse_its), float(smooth_lo), float(coarse_lo), float(safety), int(power_its))
+        self.opts = L.SicMgOpts(int(nu), int(coarse_its), float(smooth_lo), float(coarse_lo), float(safety), int(power_its),
+                                int(power_its_warm))
         n = hierarchy.n_levels
         self.levels = (L.SicMgLevel * n)()
         self._keep = []
@@ -123,7 +124,7 @@ class Multigrid:
         for l, eng in enumerate(self.engines):
             self.fixed.append(zeros(3 * eng.M, dtype=torch.uint8))
             self.dinv.append(zeros(eng.M, 9))
-            self.vec.append({k: zeros(3 * eng.M) for k in "xbrdt"})
+            self.vec.append({k: zeros(3 * eng.M) for k in ("x", "b", "r", "d", "t", "pv")})
             lv = self.levels[l]
             lv.lambda_max = 0.0
             if l > 0:
@@ -134,7 +135,7 @@ class Multigrid:
                 lv.rst_ptr, lv.rst_idx, lv.children = _ptr(tabs["rst_ptr"]), _ptr(tabs["rst_idx"]), _ptr(tabs["children"])
             else:
                 self._keep.append(None)
-            for k in "xbrdt":
+            for k in ("x", "b", "r", "d", "t", "pv"):
                 setattr(lv, k, _ptr(self.vec[l][k]))
         need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
         self.work = zeros(need)
@@ -166,7 +167,8 @@ class Multigrid:
         L.check(self.lib.sic_mg_setup(self.levels, len(self.engines), self._ct.byref(self.opts), self._ptr(self.work), st),
                 "sic_mg_setup")
         self.setups += 1
-        self.fine.launches += sum(1 + 2 + 3 * max(self.opts.power_its, 0) for _ in self.engines)
+        its = self.opts.power_its_warm if (self.setups > 1 and self.opts.power_its_warm > 0) else self.opts.power_its
+        self.fine.launches += sum(1 + 2 + 3 * max(its, 0) for _ in self.engines)
 
     def lambda_max(self):
         return [float(lv.lambda_max) for lv in self.levels]

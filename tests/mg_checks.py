@@ -40,7 +40,7 @@ def random_tangent(n, seed, nonsym=0.0):
     return CT
 
 
-def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0):
+def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True):
     """sic_mg_setup (Galerkin C_T, masks, blocks, lambda_max), one V-cycle and the full solve against the
     assembled-matrix oracle and the sparse direct solve."""
     from safeincave_b200 import cases
@@ -67,10 +67,21 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0):
         assert relerr(blocks[::7], ref) < 1e-10
     # lambda_max: the power iteration approaches the largest eigenvalue (D^-1 K is not normal: not strictly from below); times `safety` it bounds it
     lam_dev = mg.lambda_max()
-    for l in range(h.n_levels):
+    for l in range(h.n_levels if full else 1):
         lam_ref = om.power_lambda(l, its=300)
         assert 0.88 * lam_ref < lam_dev[l] / mg.opts.safety <= 1.03 * lam_ref, (l, lam_dev[l], lam_ref)
         assert lam_dev[l] >= lam_ref, (l, lam_dev[l], lam_ref)
+    if full:   # a second setup after the tangent changed restarts the power iteration from the kept vector (4 passes)
+        CT2 = random_tangent(N, 11, nonsym) * (1.0 + 2.0 * (np.arange(N) % 3 == 0))[:, None, None]
+        eng.put_CT(CT2)
+        mg.setup(eq.fixed, eq.dinv)
+        om2 = OracleMG(h.meshes, h.transfers, CT2, fixed)
+        for l in range(h.n_levels):
+            lam_ref = om2.power_lambda(l, its=300)
+            assert lam_ref <= mg.lambda_max()[l] <= 1.2 * lam_ref, (l, mg.lambda_max()[l], lam_ref)
+        eng.put_CT(CT)
+        mg.setup(eq.fixed, eq.dinv)
+        lam_dev = mg.lambda_max()
     # one V-cycle, vector for vector (same lambda_max on both sides)
     om.lam = lam_dev
     rng = np.random.default_rng(5)
@@ -88,6 +99,8 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0):
     osim = oracle_simulator(case, h.finest)
     u_ref = osim._solve(CT, eps_rhs, 0.0)
     assert relerr(eq.X.reshape(-1).cpu().numpy(), u_ref) < 1e-9
+    if not full:          # large mesh: skip the oracle's own PCG (minutes of scipy on the host)
+        return res.iterations
     dofs, vals, b_ext = osim._bc(0.0)
     b = (b_ext + fem.rhs_eps(h.finest.coords, h.finest.cells, CT, eps_rhs))
     u0 = np.zeros(3 * M)
@@ -113,3 +126,21 @@ def check_time_steps(sf, name, levels, case_fn, n_steps, tol=1e-8, **kw):
     for e_gpu, e_or in zip(eng.elems, osim.mat.elems):
         assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol
     return hist
+
+
+def check_mg_equals_block_jacobi(sf, name, levels, case_fn, n_steps=1, tol=1e-8, warm_start=True, **kw):
+    """Time steps with PC mg and with the block-Jacobi CG of solver.cu (itself checked against the oracle's direct
+    solves in test_gpu_fem.py): same Newton iteration counts, same fields."""
+    out = {}
+    for pc in ("asm", "mg"):
+        h, grid, case, eq, sim = make(sf, name, levels, case_fn, n_steps=n_steps, **kw)
+        eq.solver.getPC().setType(pc)
+        eq.solver.setInitialGuessNonzero(warm_start)
+        hist = sim.run()
+        out[pc] = (eq, hist)
+    (ej, hj), (em, hm) = out["asm"], out["mg"]
+    assert [x["iterations"] for x in hm] == [x["iterations"] for x in hj]
+    assert all(k[1] > 0 for k in em.ksp_log)
+    assert relerr(em.X.reshape(-1).cpu().numpy(), ej.X.reshape(-1).cpu().numpy()) < tol
+    assert relerr(em.engine.get6(em.engine.sig), ej.engine.get6(ej.engine.sig)) < tol
+    return max(k[0] for k in em.ksp_log), max(k[0] for k in ej.ksp_log)

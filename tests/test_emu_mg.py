@@ -31,4 +31,9 @@ def test_time_steps_triaxial_cube_mg(sf):
 
 @pytest.mark.skipif(not __import__("os").environ.get("SIC_SLOW"), reason="~80 s under emulation; set SIC_SLOW=1")
 def test_setup_vcycle_solve_cavern_regular(sf):
-    assert C.check_setup_vcycle_solve(sf, "cavern_regular", levels=1, nonsym=0.01) <= 40
+    assert C.check_setup_vcycle_solve(sf, "cavern_regular", levels=1, nonsym=0.01, full=False) <= 40
+
+
+def test_time_steps_cube_mg_equals_block_jacobi(sf):
+    from safeincave_b200 import cases
+    C.check_mg_equals_block_jacobi(sf, "cube_coarse", 2, cases.triaxial_case, n_steps=2, ksp_override="cg")
