@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 7
+#define SIC_ABI_VERSION 8
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -52,7 +52,11 @@ enum {
   SIC_ELEM_KELVIN = 1,       /* Viscoelastic          :795-885   params: eta, c11, c12, c44 (C1) */
   SIC_ELEM_DISLOCATION = 2,  /* DislocationCreep      :890-961   params: A, Q, n */
   SIC_ELEM_PRESSURE_SOL = 3, /* PressureSolutionCreep :964-1034  params: A, d, Q */
-  SIC_ELEM_DESAI = 4         /* ViscoplasticDesai     :1037-1562 params: mu_1,N_1,a_1,eta,n,beta_1,beta,m,gamma,sigma_t */
+  SIC_ELEM_DESAI = 4,        /* ViscoplasticDesai     :1037-1562 params: mu_1,N_1,a_1,eta,n,beta_1,beta,m,gamma,sigma_t */
+  /* SURVEY 8f row 1 (a material that uses none of these runs the very same kernel code as before they existed) */
+  SIC_ELEM_MUNSON_DAWSON = 5,  /* MunsonDawsonCreep         :1971-2346 params: A,Q,n,K0,c,m,alpha_w,beta_w,delta,mu */
+  SIC_ELEM_MOHR_COULOMB = 6,   /* MohrCoulombViscoplastic   :1565-1746 params: mu_1,N_1,alpha_F,k_F,alpha_Q,sigma_t (derived :1640-1648) */
+  SIC_ELEM_MATSUOKA_NAKAI = 7  /* MatsuokaNakaiViscoplastic :1749-1968 params: mu_1,N_1,k_nfc,cohesive_shift,alpha_Q,sigma_t (:1816-1829) */
 };
 
 /* rows of the per-cell Desai state block [SIC_DESAI_ROWS][cell_stride] */
@@ -61,6 +65,14 @@ enum {
   SIC_DS_R = 5, SIC_DS_H = 6, SIC_DS_HSMALL = 7, SIC_DS_P = 8 /* ..13 */,
   SIC_DS_ALPHA_K = 14, SIC_DS_Q = 15 /* ..20 */, SIC_DESAI_ROWS = 21
 };
+
+/* rows of the per-cell Munson-Dawson state block [SIC_MD_ROWS][cell_stride] (sic_elem_t.desai points at it) */
+enum {
+  SIC_MD_ZETA = 0, SIC_MD_ZETA_OLD = 1, SIC_MD_F = 2, SIC_MD_ETS = 3, SIC_MD_R = 4, SIC_MD_H = 5, SIC_MD_HSMALL = 6,
+  SIC_MD_P = 7 /* ..12 */, SIC_MD_ZETA_K = 13, SIC_MD_Q = 14 /* ..19 */, SIC_MD_ROWS = 20
+};
+/* Mohr-Coulomb / Matsuoka-Nakai keep one row: the yield function value Fvp (diagnostic the user hooks read) */
+enum { SIC_VP_FVP = 0, SIC_VP_ROWS = 1 };
 
 /* flags of sic_post() */
 enum {
@@ -78,7 +90,8 @@ typedef struct {
   double* rate_old;    /* [6][cell_stride]  eps_ne_rate_old  */
   double* rate;        /* [6][cell_stride]  eps_ne_rate      */
   double* eps_k;       /* [6][cell_stride]  eps_ne_k         */
-  double* desai;       /* [SIC_DESAI_ROWS][cell_stride] or NULL */
+  double* desai;       /* internal-state block of the element or NULL: Desai [SIC_DESAI_ROWS][cell_stride],
+                          Munson-Dawson [SIC_MD_ROWS][cell_stride], Mohr-Coulomb / Matsuoka-Nakai [SIC_VP_ROWS][cell_stride] */
 } sic_elem_t;
 
 /* Everything a constitutive / assembly kernel needs.  Filled by the host, passed by pointer. */

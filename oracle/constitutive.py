@@ -80,6 +80,16 @@ def f_pow(x, y):
     return out
 
 
+def f_log10(x):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    if USE_LIBM:
+        with np.errstate(all="ignore"):
+            return np.log10(x)
+    out = np.empty_like(x)
+    _lib().sic_log10_array(x.ctypes.data_as(_P), out.ctypes.data_as(_P), ctypes.c_long(x.size))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Voigt helpers
 # --------------------------------------------------------------------------------------
@@ -509,6 +519,280 @@ class Desai(_Element):
         for k in ("alpha", "qsi", "qsi_old", "Fvp"):
             snap[k] = getattr(self, k).copy()
         return snap
+
+
+
+# --------------------------------------------------------------------------------------
+# MunsonDawsonCreep, MaterialProps.py:1971-2346
+# --------------------------------------------------------------------------------------
+class MunsonDawsonParams:
+    names = ("A", "Q", "n", "K0", "c", "m", "alpha_w", "beta_w", "delta", "mu")
+
+    def __init__(self, **kw):
+        for k in self.names:
+            setattr(self, k, np.asarray(kw[k], dtype=np.float64))
+
+
+def _clamp(x, lo, hi):
+    """torch.clamp(x, min=lo, max=hi): NaN propagates."""
+    with np.errstate(invalid="ignore"):
+        return np.where(x < lo, lo, np.where(x > hi, hi, x))
+
+
+def md_fields(sig, T, zeta, p):
+    """_compute_md_fields, MaterialProps.py:2104-2167.  Returns (s_dev (N,6), sigma_safe, epsdot_ss, eps_t_star, F)."""
+    sxx, syy, szz, sxy, sxz, syz = (sig[:, k] for k in range(6))
+    dev = _deviator(sig)
+    sigma = np.sqrt(0.5 * ((sxx - syy) ** 2 + (sxx - szz) ** 2 + (syy - szz) ** 2
+                           + 6.0 * (sxy ** 2 + sxz ** 2 + syz ** 2)))
+    sigma_safe = _clamp_min(sigma, 1.0)
+    mu_safe = _clamp_min(p.mu, 1.0)
+    with np.errstate(all="ignore"):
+        epsdot_ss = p.A * f_exp(-p.Q / (R_GAS * T)) * f_pow(sigma_safe, p.n)
+        ratio = _clamp_min(sigma_safe / mu_safe, 1e-30)
+        ets = p.K0 * f_exp(p.c * T) * f_pow(ratio, p.m)
+        ets = _clamp_min(ets, 1e-50)
+        Delta = p.alpha_w + p.beta_w * f_log10(ratio)
+        r_arg = 1.0 - (zeta / ets)
+        r2 = r_arg * r_arg
+        hard = zeta <= ets
+        arg = np.where(hard, _clamp(Delta * r2, -50.0, 50.0), _clamp(-p.delta * r2, -50.0, 50.0))
+        F = f_exp(arg)
+    return dev, sigma_safe, epsdot_ss, ets, F
+
+
+def rate_munson_dawson(sig, T, zeta, p):
+    """compute_eps_ne_rate, MaterialProps.py:2187-2229.  Returns (rate, F, eps_t_star)."""
+    dev, sigma_safe, epsdot_ss, ets, F = md_fields(sig, T, zeta, p)
+    scalar_rate = F * epsdot_ss
+    flow = (1.5 / sigma_safe)[:, None] * dev
+    return flow * scalar_rate[:, None], F, ets
+
+
+def md_residue(sig, T, zeta, zeta_old, dt, p):
+    """compute_residue, MaterialProps.py:2169-2181."""
+    _, _, epsdot_ss, _, F = md_fields(sig, T, zeta, p)
+    return zeta - zeta_old - (F - 1.0) * epsdot_ss * dt
+
+
+class MunsonDawson(_Element):
+    kind = "munson_dawson"
+    SQRT_EPS = 1.4901161193847656e-8          # MaterialProps.py:2013
+
+    def __init__(self, **params):
+        self.p = MunsonDawsonParams(**params)
+        super().__init__(len(self.p.A))
+        n = self.n
+        self.zeta, self.zeta_old = np.zeros(n), np.zeros(n)
+        self.F, self.eps_t_star = np.ones(n), np.ones(n)
+        self.r, self.h, self.P = np.zeros(n), np.ones(n), np.zeros((n, 6))
+        self.h_small = np.zeros(n, dtype=bool)
+
+    def tangent(self, sig, dt, theta, T):
+        """compute_G_B (707-728) = compute_B_and_H_over_h (2235-2313), compute_E (640-675), _compute_H (2315-2346)."""
+        p = self.p
+        _, _, _, ets_now, _ = md_fields(sig, T, self.zeta, p)
+        zeta_scale = _clamp_min(np.abs(self.zeta) + ets_now, 1e-30)
+        eps_zeta = self.SQRT_EPS * zeta_scale
+        self.r = md_residue(sig, T, self.zeta, self.zeta_old, dt, p)
+        zeta_eps = self.zeta + eps_zeta
+        r_zeta = md_residue(sig, T, zeta_eps, self.zeta_old, dt, p)
+        with np.errstate(all="ignore"):
+            self.h = (r_zeta - self.r) / eps_zeta
+            rate_ref = rate_munson_dawson(sig, T, self.zeta, p)[0]
+            rate_zeta = rate_munson_dawson(sig, T, zeta_eps, p)[0]
+            Q = (rate_zeta - rate_ref) / eps_zeta[:, None]
+            self.h_small = np.abs(self.h) < 1e-12
+            self.h = np.where(self.h_small, 1.0, self.h)
+            B = (self.r / self.h)[:, None] * Q
+        EPS_S = 1e-1
+        self.P = np.zeros((self.n, 6))
+        s = sig.copy()
+        for k in range(6):
+            s[:, k] += EPS_S
+            r_sig = md_residue(s, T, self.zeta, self.zeta_old, dt, p)
+            self.P[:, k] = (r_sig - self.r) / EPS_S
+            s[:, k] -= EPS_S
+        H = np.zeros((self.n, 6, 6))
+        for i in range(6):
+            for j in range(6):
+                H[:, i, j] = Q[:, i] * self.P[:, j] if j < 3 else 2 * Q[:, i] * self.P[:, j]
+        with np.errstate(all="ignore"):
+            H_over_h = H / self.h[:, None, None]
+        B[self.h_small] = 0.0
+        H_over_h[self.h_small] = 0.0
+        self.P[self.h_small] = 0.0
+        self.B = B
+        E = fd_tangent(lambda x: rate_munson_dawson(x, T, self.zeta, p)[0], sig)
+        self.G = E - H_over_h
+
+    def eval_rate(self, sig, phi1, T):
+        self.rate, self.F, self.eps_t_star = rate_munson_dawson(sig, T, self.zeta, self.p)
+
+    def increment_isv(self, sig, sig_k, dt):
+        """increment_internal_variables, MaterialProps.py:2081-2102."""
+        with np.errstate(all="ignore"):
+            d = -(self.r + ddot_sym(self.P, sig - sig_k)) / self.h
+        d = np.where(self.h_small, 0.0, d)
+        self.zeta = _clamp_min(self.zeta + d, 0.0)
+
+    def commit_isv(self):
+        """update_internal_variables, MaterialProps.py:2077-2079."""
+        self.zeta_old = self.zeta.copy()
+
+    def snapshot(self):
+        snap = super().snapshot()
+        for k in ("zeta", "zeta_old"):
+            snap[k] = getattr(self, k).copy()
+        return snap
+
+
+# --------------------------------------------------------------------------------------
+# MohrCoulombViscoplastic (1565-1746) and MatsuokaNakaiViscoplastic (1749-1968)
+# --------------------------------------------------------------------------------------
+def _dp_flow(s, I1, alpha_Q, is_tension):
+    """DP-based flow direction shared by both models (1705-1731 / 1927-1953): dQ/dsigma in the
+    compression-positive MPa convention, tension cells replaced by -1/3 on the diagonal."""
+    sxx, syy, szz, sxy, sxz, syz = (s[:, k] for k in range(6))
+    I2 = sxx * syy + syy * szz + sxx * szz - sxy ** 2 - syz ** 2 - sxz ** 2
+    J2 = _clamp_min((1.0 / 3.0) * I1 ** 2 - I2, 1e-20)
+    sqrt_J2 = np.sqrt(J2)
+    inv = 1.0 / (2.0 * sqrt_J2)
+    dJ2 = ((2.0 / 3.0) * I1 - (syy + szz), (2.0 / 3.0) * I1 - (sxx + szz), (2.0 / 3.0) * I1 - (sxx + syy),
+           2.0 * sxy, 2.0 * sxz, 2.0 * syz)
+    dQ = np.zeros_like(s)
+    for k in range(6):
+        dQ[:, k] = inv * dJ2[k] - alpha_Q if k < 3 else inv * dJ2[k]
+    dQ[is_tension, :] = 0.0
+    dQ[is_tension, :3] = -1.0 / 3.0
+    return dQ, sqrt_J2
+
+
+def _perzyna(Fvp, mu_1, N_1):
+    lam = np.zeros_like(Fvp)
+    with np.errstate(invalid="ignore"):
+        ramp = Fvp > 0
+    if ramp.any():
+        with np.errstate(all="ignore"):
+            lam[ramp] = mu_1[ramp] * f_pow(Fvp[ramp] / 1.0, N_1[ramp])
+    return lam
+
+
+def rate_mohr_coulomb(sig, mu_1, N_1, alpha_F, k_F, alpha_Q, sigma_t):
+    """MohrCoulombViscoplastic.compute_eps_ne_rate, MaterialProps.py:1652-1746.  Returns (rate, Fvp)."""
+    s = (-sig) / MPA
+    I1 = s[:, XX] + s[:, YY] + s[:, ZZ]
+    F_tension = -I1 / 3.0 - sigma_t
+    # the flow direction needs sqrt(J2) as well; the yield function uses the same value
+    dQ_shear_only, sqrt_J2 = _dp_flow(s, I1, alpha_Q, np.zeros(len(I1), dtype=bool))
+    F_shear = sqrt_J2 - alpha_F * I1 - k_F
+    Fvp = np.maximum(F_shear, F_tension)
+    is_tension = F_tension > F_shear
+    dQ = dQ_shear_only
+    dQ[is_tension, :] = 0.0
+    dQ[is_tension, :3] = -1.0 / 3.0
+    lam = _perzyna(Fvp, mu_1, N_1)
+    return -dQ * lam[:, None], Fvp
+
+
+EIGEN = "lapack"     # "jacobi": the fixed six-sweep cyclic Jacobi iteration the CUDA kernels run (bit-identical)
+
+
+def _jacobi_rotate(app, aqq, apq, arp, arq):
+    nz = apq != 0.0
+    with np.errstate(all="ignore"):
+        theta = np.where(nz, (aqq - app) / np.where(nz, 2.0 * apq, 1.0), 0.0)
+        t = 1.0 / (np.abs(theta) + np.sqrt(theta * theta + 1.0))
+    t = np.where(theta < 0.0, -t, t)
+    t = np.where(nz, t, 0.0)
+    c = 1.0 / np.sqrt(t * t + 1.0)
+    sn = t * c
+    return app - t * apq, aqq + t * apq, np.zeros_like(apq), c * arp - sn * arq, sn * arp + c * arq
+
+
+def eigvals_sym3_jacobi(s):
+    """Ascending eigenvalues of symmetric 3x3 tensors given as Voigt-6: restatement, operation for
+    operation, of eigvals_sym3 in safeincave_b200/csrc/constitutive.cuh."""
+    a00, a11, a22, a01, a02, a12 = (s[:, k].copy() for k in range(6))
+    for _ in range(6):
+        a00, a11, a01, a02, a12 = _jacobi_rotate(a00, a11, a01, a02, a12)
+        a00, a22, a02, a01, a12 = _jacobi_rotate(a00, a22, a02, a01, a12)
+        a11, a22, a12, a01, a02 = _jacobi_rotate(a11, a22, a12, a01, a02)
+    x, y, z = a00, a11, a22
+    x, y = np.where(y < x, y, x), np.where(y < x, x, y)
+    y, z = np.where(z < y, z, y), np.where(z < y, y, z)
+    x, y = np.where(y < x, y, x), np.where(y < x, x, y)
+    return np.stack([x, y, z], axis=1)
+
+
+def rate_matsuoka_nakai(sig, mu_1, N_1, k_nfc, shift, alpha_Q, sigma_t):
+    """MatsuokaNakaiViscoplastic.compute_eps_ne_rate, MaterialProps.py:1835-1968.  Returns (rate, Fvp)."""
+    s = (-sig) / MPA
+    if EIGEN == "jacobi":
+        eig = eigvals_sym3_jacobi(s)
+    else:
+        eig = np.linalg.eigvalsh(to_tensor(s))             # ascending (torch.linalg.eigvalsh, :1882)
+    sig3, sig2, sig1 = eig[:, 0], eig[:, 1], eig[:, 2]
+    s1, s2, s3 = sig1 + shift, sig2 + shift, sig3 + shift
+    d12, d23, d31 = _clamp_min(s1 + s2, 1e-20), _clamp_min(s2 + s3, 1e-20), _clamp_min(s3 + s1, 1e-20)
+    sin2_12, sin2_23, sin2_31 = ((s1 - s2) / d12) ** 2, ((s2 - s3) / d23) ** 2, ((s3 - s1) / d31) ** 2
+    f_nfc = np.sqrt(sin2_12 + sin2_23 + sin2_31 + 1e-30) - k_nfc
+    p_mean = _clamp_min((s1 + s2 + s3) / 3.0, 1e-20)
+    F_shear = f_nfc * p_mean
+    I1 = s[:, XX] + s[:, YY] + s[:, ZZ]
+    F_tension = -I1 / 3.0 - sigma_t
+    Fvp = np.maximum(F_shear, F_tension)
+    is_tension = F_tension > F_shear
+    dQ, _ = _dp_flow(s, I1, alpha_Q, is_tension)
+    lam = _perzyna(Fvp, mu_1, N_1)
+    return -dQ * lam[:, None], Fvp
+
+
+class _StressOnly(_Element):
+    """Viscoplastic elements whose rate depends on the stress only (no ISV)."""
+
+    def tangent(self, sig, dt, theta, T):
+        self.B = np.zeros((self.n, 6))
+        self.G = fd_tangent(lambda s: self._rate(s)[0], sig)
+
+    def eval_rate(self, sig, phi1, T):
+        self.rate, self.Fvp = self._rate(sig)
+
+
+class MohrCoulomb(_StressOnly):
+    kind = "mohr_coulomb"
+
+    def __init__(self, mu_1, N_1, cohesion, friction_angle, dilation_angle, sigma_t):
+        a = lambda x: np.asarray(x, dtype=np.float64)
+        super().__init__(len(mu_1))
+        self.mu_1, self.N_1, self.sigma_t = a(mu_1), a(N_1), a(sigma_t)
+        sin_phi, cos_phi, sin_psi = np.sin(a(friction_angle)), np.cos(a(friction_angle)), np.sin(a(dilation_angle))
+        self.alpha_F = 2.0 * sin_phi / (np.sqrt(3.0) * (3.0 - sin_phi))            # :1644
+        self.k_F = 6.0 * a(cohesion) * cos_phi / (np.sqrt(3.0) * (3.0 - sin_phi))  # :1645
+        self.alpha_Q = 2.0 * sin_psi / (np.sqrt(3.0) * (3.0 - sin_psi))            # :1648
+        self.Fvp = np.zeros(self.n)
+
+    def _rate(self, sig):
+        return rate_mohr_coulomb(sig, self.mu_1, self.N_1, self.alpha_F, self.k_F, self.alpha_Q, self.sigma_t)
+
+
+class MatsuokaNakai(_StressOnly):
+    kind = "matsuoka_nakai"
+
+    def __init__(self, mu_1, N_1, cohesion, friction_angle, dilation_angle, sigma_t):
+        a = lambda x: np.asarray(x, dtype=np.float64)
+        super().__init__(len(mu_1))
+        self.mu_1, self.N_1, self.sigma_t = a(mu_1), a(N_1), a(sigma_t)
+        sin_phi, cos_phi, sin_psi = np.sin(a(friction_angle)), np.cos(a(friction_angle)), np.sin(a(dilation_angle))
+        self.k_nfc = np.sqrt(2.0) * sin_phi                                        # :1816
+        small = np.abs(sin_phi) < 1e-10
+        safe = np.where(small, 1.0, sin_phi)
+        self.shift = np.where(small, 0.0, a(cohesion) * cos_phi / safe)            # :1820-1826
+        self.alpha_Q = 2.0 * sin_psi / (np.sqrt(3.0) * (3.0 - sin_psi))            # :1829
+        self.Fvp = np.zeros(self.n)
+
+    def _rate(self, sig):
+        return rate_matsuoka_nakai(sig, self.mu_1, self.N_1, self.k_nfc, self.shift, self.alpha_Q, self.sigma_t)
 
 
 class OracleMaterial:

@@ -55,6 +55,36 @@ def make_inputs(N, seed):
     return sig, T, noise
 
 
+MUNSON_DAWSON = dict(A=18.31 * (1e-6) ** 4.99 / (365 * 24 * 3600.0), Q=6356.0 * 8.32, n=4.99, K0=7.0e-7, c=9.02e-3,
+                     m=3.0, alpha_w=-13.2, beta_w=-7.738, delta=0.58,
+                     mu=20.425e9 / (2.0 * 1.25))      # nobian/Simulation/Run.py:1240-1276
+INTERLAYER = dict(mu_1=1e-9, N_1=1.0, cohesion=4.0, friction_angle=float(np.radians(35.0)),
+                  dilation_angle=float(np.radians(5.0)), sigma_t=1.0)   # run_interlayer.py:110-111, 1617-1623 (anhydrite)
+
+
+def make_inputs_interlayer(N, seed):
+    """Stress states around the Mohr-Coulomb / Matsuoka-Nakai surfaces of an anhydrite interlayer: low
+    confinement -(0.5..6) MPa with one strongly compressed axis -(10..45) MPa (shear yield on roughly half
+    of the cells), small shear, and a few cells in tension beyond sigma_t (tension cut-off)."""
+    g = np.random.default_rng(seed)
+    sig = np.zeros((N, 3, 3))
+    diag = -(0.5e6 + 5.5e6 * g.random((N, 3)))
+    axis = g.integers(0, 3, N)
+    diag[np.arange(N), axis] = -(10e6 + 35e6 * g.random(N))
+    n_t = max(2, N // 12)
+    diag[:n_t] = 0.5e6 + 3e6 * g.random((n_t, 3))
+    shear = 2e6 * (g.random((N, 3)) - 0.5)
+    for i in range(3):
+        sig[:, i, i] = diag[:, i]
+    for k, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+        sig[:, i, j] = shear[:, k]
+        sig[:, j, i] = shear[:, k]
+    T = 293 + 27 * g.random(N)
+    noise = 0.02 * (g.random((N, 3, 3)) - 0.5)
+    noise = 0.5 * (noise + noise.transpose(0, 2, 1))
+    return sig, T, noise
+
+
 def build(mp, N, spec, dtype=to.float64, het=None):
     """spec: list of element kinds. het: optional (N,) multiplier making parameters
     heterogeneous."""
@@ -85,6 +115,17 @@ def build(mp, N, spec, dtype=to.float64, het=None):
         elif kind == "thermo":
             p = dict(alpha=44e-6 * to.ones(N, dtype=dtype))
             mat.add_to_thermoelastic(mp.Thermoelastic(p["alpha"], "thermo"))
+        elif kind == "munson_dawson":
+            p = {k: v * to.ones(N, dtype=dtype) for k, v in MUNSON_DAWSON.items()}
+            p["A"] = p["A"] * one / one.mean() if het is not None else p["A"]
+            mat.add_to_non_elastic(mp.MunsonDawsonCreep(**p, name="munson_dawson"))
+        elif kind in ("mohr_coulomb", "matsuoka_nakai"):
+            p = {k: v * to.ones(N, dtype=dtype) for k, v in INTERLAYER.items()}
+            p["N_1"][::3] = 2.5                       # a fractional-free but non-unit rate exponent on a third of the cells
+            p["mu_1"][1::7] = 0.0                     # "salt" cells that never yield (run_interlayer.py:1632-1638)
+            cls = mp.MohrCoulombViscoplastic if kind == "mohr_coulomb" else mp.MatsuokaNakaiViscoplastic
+            mat.add_to_non_elastic(cls(p["mu_1"], p["N_1"], p["cohesion"], p["friction_angle"], p["dilation_angle"],
+                                       p["sigma_t"], kind))
         else:
             raise ValueError(kind)
         params[kind] = {k: v.double().numpy() for k, v in p.items()}
@@ -96,14 +137,14 @@ def record_elems(mat, rec, tag):
         pre = f"{tag}/e{i}"
         for name in ("eps_ne_rate", "eps_ne_rate_old", "eps_ne_old", "eps_ne_k", "G", "B"):
             rec[f"{pre}/{name}"] = getattr(e, name).double().numpy().copy()
-        for name in ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old", "r", "h", "P"):
+        for name in ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old", "r", "h", "P", "zeta", "zeta_old", "F"):
             if hasattr(e, name):
                 rec[f"{pre}/{name}"] = getattr(e, name).double().numpy().copy()
 
 
 def run_sequence(mp, name, N, seed, spec, dt, theta, n_steps=2, n_iters=3,
-                 desai_init=False, load_step=0.03, dtype=to.float64, het=False, dT=0.0):
-    sig0, T_np, noise = make_inputs(N, seed)
+                 desai_init=False, load_step=0.03, dtype=to.float64, het=False, dT=0.0, inputs=None):
+    sig0, T_np, noise = (inputs or make_inputs)(N, seed)
     het_arr = None
     if het:
         het_arr = 1 + 0.2 * (np.random.default_rng(seed + 1).random(N) - 0.5)
@@ -216,9 +257,23 @@ def kat_from_reference_tests(mp):
     print("wrote", path)
 
 
+def main_extended(mp):
+    """MunsonDawsonCreep, MohrCoulombViscoplastic, MatsuokaNakaiViscoplastic."""
+    H = 3600.0
+    run_sequence(mp, "md_alone", 32, 21, ["munson_dawson"], 2 * H, 0.5, n_steps=2, n_iters=3, load_step=0.05)
+    run_sequence(mp, "md_implicit_het", 32, 22, ["munson_dawson", "thermo"], 6 * H, 0.0, n_steps=2, n_iters=3,
+                 load_step=0.08, het=True, dT=5.0)
+    run_sequence(mp, "interlayer_mc", 48, 23, ["dislocation", "mohr_coulomb"], 1 * H, 0.5, load_step=0.04,
+                 inputs=make_inputs_interlayer)
+    run_sequence(mp, "interlayer_mn", 48, 24, ["dislocation", "matsuoka_nakai"], 1 * H, 0.0, load_step=0.04,
+                 inputs=make_inputs_interlayer)
+
+
 def main():
     mp = load_reference_material_props()
     to.manual_seed(0)
+    if "--extended-only" in sys.argv:
+        return main_extended(mp)
     kat_from_reference_tests(mp)
     H = 3600.0
     # config 1 (triaxial cube): Spring + Kelvin + DislocationCreep, theta 0.5, dt 0.5 h
@@ -235,6 +290,7 @@ def main():
                  12 * H, 0.5, het=True, dT=7.5)
     # float32 user parameters as in the examples -- documents the deviation
     run_sequence(mp, "cfg1_float32_params", 16, 6, ["kelvin", "dislocation"], 0.5 * H, 0.5, dtype=to.float32)
+    main_extended(mp)
 
 
 if __name__ == "__main__":

@@ -17,3 +17,6 @@ void sic_exp_array(const double* x, double* out, long n) {
 void sic_log_array(const double* x, double* out, long n) {
   for (long i = 0; i < n; ++i) out[i] = sic_log(x[i]);
 }
+void sic_log10_array(const double* x, double* out, long n) {
+  for (long i = 0; i < n; ++i) out[i] = sic_log10(x[i]);
+}

@@ -62,6 +62,19 @@ class _ParamOwner:
     def _columns(self):
         return [getattr(self, "_p_" + n) for n in self.param_names]
 
+    def __setattr__(self, name, value):
+        """Re-assigning a parameter AFTER the material was attached (e.g. ``mc.mu_1 = mc._real_mu_1`` to switch an
+        interlayer model on once the stress field has equilibrated, nobian/Simulation/run_interlayer.py:1664-1669)
+        rebuilds the device-side parameter table, keeping the state."""
+        object.__setattr__(self, name, value)
+        if name in self.param_names and "_p_" + name in self.__dict__:
+            v = to.as_tensor(value)
+            if v.ndim == 1 and v.shape[0] == self.__dict__["_p_" + name].shape[0]:
+                object.__setattr__(self, "_p_" + name, v.detach().cpu())
+                mat = self.__dict__.get("_material")
+                if mat is not None and mat._engine is not None:
+                    mat.rebind()
+
     def _set_params(self, **kw):
         n = None
         for k, v in kw.items():
@@ -71,8 +84,8 @@ class _ParamOwner:
             n = v.shape[0] if n is None else n
             if v.shape[0] != n:
                 raise ValueError(f"{type(self).__name__}: parameter {k} has {v.shape[0]} entries, expected {n}")
-            setattr(self, "_p_" + k, v.detach().cpu())
-            setattr(self, k, v)
+            object.__setattr__(self, "_p_" + k, v.detach().cpu())
+            object.__setattr__(self, k, v)
         return n
 
 
@@ -247,6 +260,101 @@ class ViscoplasticDesai(NonElasticElement):
         self.n_disabled = n_clamped
 
 
+class _IsvRows:
+    """Row accessors of the element's internal-state block on the device."""
+
+    def _row(self, r):
+        return self._state().desai[r, :self._engine.N].cpu()
+
+    def _set_row(self, r, v):
+        self._state().desai[r, :self._engine.N] = to.as_tensor(v, dtype=to.float64).to(self._engine.device)
+
+    def _rows6(self, r0):
+        st, n = self._state(), self._engine.N
+        return voigt_to_tensor(st.desai[r0:r0 + 6, :n].t()).cpu()
+
+
+class MunsonDawsonCreep(NonElasticElement, _IsvRows):
+    """Munson-Dawson transient + steady-state creep with the internal variable zeta
+    (MaterialProps.py:1971-2346), R = 8.32.  Parameters are promoted to float64 as the reference does (:2035-2049)."""
+    kind = L.ELEM_MUNSON_DAWSON
+    param_names = ("A", "Q", "n", "K0", "c", "m", "alpha_w", "beta_w", "delta", "mu")
+    n_row_params = 10
+
+    def __init__(self, A, Q, n, K0, c, m, alpha_w, beta_w, delta, mu, name="creep_munson_dawson"):
+        super().__init__(self._set_params(A=A, Q=Q, n=n, K0=K0, c=c, m=m, alpha_w=alpha_w, beta_w=beta_w,
+                                          delta=delta, mu=mu))
+        self.R = 8.32
+        self.name = name
+
+    zeta = property(lambda s: s._row(L.MD_ZETA), lambda s, v: s._set_row(L.MD_ZETA, v))
+    zeta_old = property(lambda s: s._row(L.MD_ZETA_OLD), lambda s, v: s._set_row(L.MD_ZETA_OLD, v))
+    F = property(lambda s: s._row(L.MD_F))
+    _eps_t_star = property(lambda s: s._row(L.MD_ETS))
+    r = property(lambda s: s._row(L.MD_R))
+    h = property(lambda s: s._row(L.MD_H))
+    P = property(lambda s: s._rows6(L.MD_P))
+
+
+def _dp_alpha(angle):
+    """2 sin(a) / (sqrt(3) (3 - sin(a))) with the reference's expression and dtype (MaterialProps.py:1644, 1648)."""
+    sn = to.sin(angle)
+    return 2.0 * sn / (np.sqrt(3.0) * (3.0 - sn))
+
+
+class MohrCoulombViscoplastic(NonElasticElement, _IsvRows):
+    """Mohr-Coulomb (Drucker-Prager fit in triaxial compression) with tension cut-off and Perzyna overstress
+    (MaterialProps.py:1565-1746).  alpha_F, k_F, alpha_Q are derived on the host with the reference's torch
+    expressions (:1640-1648), the kernels receive them per material row."""
+    kind = L.ELEM_MOHR_COULOMB
+    param_names = ("mu_1", "N_1", "cohesion", "friction_angle", "dilation_angle", "sigma_t")
+    n_row_params = 6
+
+    def __init__(self, mu_1, N_1, cohesion, friction_angle, dilation_angle, sigma_t, name="mohr_coulomb"):
+        super().__init__(self._set_params(mu_1=mu_1, N_1=N_1, cohesion=cohesion, friction_angle=friction_angle,
+                                          dilation_angle=dilation_angle, sigma_t=sigma_t))
+        self.name = name
+        self.F_0 = 1.0
+
+    def derived(self, rows):
+        phi = rows["friction_angle"]
+        sin_phi, cos_phi = to.sin(phi), to.cos(phi)
+        alpha_F = 2.0 * sin_phi / (np.sqrt(3.0) * (3.0 - sin_phi))
+        k_F = 6.0 * rows["cohesion"] * cos_phi / (np.sqrt(3.0) * (3.0 - sin_phi))
+        return [rows["mu_1"].double(), rows["N_1"].double(), alpha_F.double(), k_F.double(),
+                _dp_alpha(rows["dilation_angle"]).double(), rows["sigma_t"].double()]
+
+    Fvp = property(lambda s: s._row(L.VP_FVP))
+
+
+class MatsuokaNakaiViscoplastic(NonElasticElement, _IsvRows):
+    """Matsuoka-Nakai criterion in the NFC (n = 1) form of Panteghini & Lagioia on the principal stresses, with
+    Houlsby cohesive shift, tension cut-off, Drucker-Prager flow and Perzyna overstress (MaterialProps.py:1749-1968).
+    The principal stresses come from a fixed six-sweep cyclic Jacobi iteration on the device (the reference calls
+    torch.linalg.eigvalsh, :1882): agreement 1e-15 relative."""
+    kind = L.ELEM_MATSUOKA_NAKAI
+    param_names = ("mu_1", "N_1", "cohesion", "friction_angle", "dilation_angle", "sigma_t")
+    n_row_params = 6
+
+    def __init__(self, mu_1, N_1, cohesion, friction_angle, dilation_angle, sigma_t, name="matsuoka_nakai"):
+        super().__init__(self._set_params(mu_1=mu_1, N_1=N_1, cohesion=cohesion, friction_angle=friction_angle,
+                                          dilation_angle=dilation_angle, sigma_t=sigma_t))
+        self.name = name
+        self.F_0 = 1.0
+
+    def derived(self, rows):
+        phi = rows["friction_angle"]
+        sin_phi, cos_phi = to.sin(phi), to.cos(phi)
+        k_nfc = np.sqrt(2.0) * sin_phi                                              # :1816
+        small = sin_phi.abs() < 1e-10
+        safe = to.where(small, to.ones_like(sin_phi), sin_phi)
+        shift = to.where(small, to.zeros_like(sin_phi), rows["cohesion"] * cos_phi / safe)   # :1820-1826
+        return [rows["mu_1"].double(), rows["N_1"].double(), k_nfc.double(), shift.double(),
+                _dp_alpha(rows["dilation_angle"]).double(), rows["sigma_t"].double()]
+
+    Fvp = property(lambda s: s._row(L.VP_FVP))
+
+
 class Material:
     """Aggregate of elastic, thermoelastic and non-elastic elements (MaterialProps.py:22-331)."""
 
@@ -282,10 +390,20 @@ class Material:
         if not isinstance(elem, NonElasticElement) or elem.kind == 0:
             raise TypeError(
                 f"{type(elem).__name__} has no CUDA implementation in safeincave_b200 (supported: Viscoelastic, "
-                "DislocationCreep, PressureSolutionCreep, ViscoplasticDesai); there is no CPU fallback")
+                "DislocationCreep, PressureSolutionCreep, ViscoplasticDesai, MunsonDawsonCreep, MohrCoulombViscoplastic, "
+                "MatsuokaNakaiViscoplastic); there is no CPU fallback")
         if len(self.elems_ne) >= L.SIC_MAX_ELEMS:
             raise ValueError(f"at most {L.SIC_MAX_ELEMS} non-elastic elements")
         self.elems_ne.append(elem)
+        elem._material = self
+
+    def rebind(self):
+        """Rebuild the parameter table on the device after a parameter tensor was re-assigned; state is kept."""
+        engine = self._engine
+        table, ids, layout = self.build_table(device=engine.device)
+        engine.set_material(table.numpy(), ids, layout["spring_off"], layout["thermo_off"], layout["n_thermo"],
+                            layout["specs"], keep_state=True)
+        self._layout, self._table, self._ids = layout, table, ids.cpu()
 
     def add_to_thermoelastic(self, elem: Thermoelastic):
         if len(self.elems_th) >= L.SIC_MAX_THERMO:

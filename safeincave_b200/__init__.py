@@ -6,7 +6,8 @@ this package implements.
 __version__ = "0.1.0"
 
 from .MaterialProps import (Material, NonElasticElement, Spring, Thermoelastic, Viscoelastic,  # noqa: F401
-                            DislocationCreep, PressureSolutionCreep, ViscoplasticDesai)
+                            DislocationCreep, PressureSolutionCreep, ViscoplasticDesai, MunsonDawsonCreep,
+                            MohrCoulombViscoplastic, MatsuokaNakaiViscoplastic)
 from .Grid import GridHandlerGMSH  # noqa: F401
 from .MomentumEquation import LinearMomentumBase, LinearMomentum, CellField  # noqa: F401
 from .Simulators import Simulator_M  # noqa: F401

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 7
+SIC_ABI_VERSION = 8
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -20,6 +20,10 @@ ELEM_KELVIN, ELEM_DISLOCATION, ELEM_PRESSURE_SOL, ELEM_DESAI = 1, 2, 3, 4
 DS_ALPHA, DS_ALPHA0, DS_QSI, DS_QSI_OLD, DS_FVP, DS_R, DS_H, DS_HSMALL, DS_P, DS_ALPHA_K, DS_Q = (
     0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15)
 DESAI_ROWS = 21
+ELEM_MUNSON_DAWSON, ELEM_MOHR_COULOMB, ELEM_MATSUOKA_NAKAI = 5, 6, 7
+MD_ZETA, MD_ZETA_OLD, MD_F, MD_ETS, MD_R, MD_H, MD_HSMALL, MD_P, MD_ZETA_K, MD_Q, MD_ROWS = 0, 1, 2, 3, 4, 5, 6, 7, 13, 14, 20
+VP_FVP, VP_ROWS = 0, 1
+ISV_ROWS = {ELEM_DESAI: DESAI_ROWS, ELEM_MUNSON_DAWSON: MD_ROWS, ELEM_MOHR_COULOMB: VP_ROWS, ELEM_MATSUOKA_NAKAI: VP_ROWS}
 POST_STRAIN, POST_STRESS, POST_INCREMENT, POST_RATES, POST_ERROR = 1, 2, 4, 8, 16
 KSP_CG, KSP_BICGSTAB, KSP_CGCG = 1, 2, 3
 

@@ -26,6 +26,14 @@ ELEMENT_LIBRARY = {
     "dislocation": dict(kind="dislocation", A=1.9e-20, Q=51600.0, n=3.0),              # :72-75
     "pressure_solution": dict(kind="pressure_solution", A=1.29e-19, d=0.01, Q=13184.0),  # thermomechanics/2_cavern/main.py:82-87
     "desai": dict(kind="desai", **DESAI_TRIAXIAL),
+    # nobian/Simulation/Run.py:1262-1276 (scenario A, Munson-Dawson model; mu = E0 / (2 (1 + nu0)))
+    "munson_dawson": dict(kind="munson_dawson", A=18.31 * (1e-6) ** 4.99 / (365 * 24 * 3600.0), Q=6356.0 * 8.32, n=4.99,
+                          K0=7.0e-7, c=9.02e-3, m=3.0, alpha_w=-13.2, beta_w=-7.738, delta=0.58, mu=20.425e9 / 2.5),
+    # nobian/Simulation/run_interlayer.py:110-111, 1617-1623 (anhydrite interlayer)
+    "mohr_coulomb": dict(kind="mohr_coulomb", mu_1=1e-9, N_1=1.0, cohesion=4.0, friction_angle=float(np.radians(35.0)),
+                         dilation_angle=0.0, sigma_t=1.0),
+    "matsuoka_nakai": dict(kind="matsuoka_nakai", mu_1=1e-9, N_1=1.0, cohesion=4.0, friction_angle=float(np.radians(35.0)),
+                           dilation_angle=0.0, sigma_t=1.0),
 }
 
 
@@ -37,7 +45,7 @@ def triaxial_case(grid, elements=("kelvin", "dislocation"), n_steps=None, ksp_ov
         name="triaxial", theta=0.5, dt=0.5 * hour, t_final=t_final, time_unit="hour",
         density=2000.0, g=[0.0, 0.0, 0.0], T=293.0,
         spring=dict(E=102 * GPa, nu=0.3),
-        elements=[dict(ELEMENT_LIBRARY[e]) for e in elements],
+        elements=[dict(ELEMENT_LIBRARY[e]) if isinstance(e, str) else dict(e) for e in elements],
         dirichlet=[dict(boundary=up["WEST"], component=0, values=[0.0, 0.0], time_values=[0.0, t_final]),
                    dict(boundary=up["BOTTOM"], component=2, values=[0.0, 0.0], time_values=[0.0, t_final]),
                    dict(boundary=up["SOUTH"], component=1, values=[0.0, 0.0], time_values=[0.0, t_final])],
@@ -70,7 +78,7 @@ def cavern_case(grid, elements=("dislocation",), theta=0.0, dt_hours=2.0, p_ref=
         density=salt_density, g=[0.0, 0.0, g],
         T=dict(surface=293.0, gradient=27.0 / 1000.0, z_surface=z_top),           # 4_cavern/main.py:90-97
         spring=dict(E=102 * GPa, nu=0.3),
-        elements=[dict(ELEMENT_LIBRARY[e]) for e in elements],
+        elements=[dict(ELEMENT_LIBRARY[e]) if isinstance(e, str) else dict(e) for e in elements],
         dirichlet=[dict(boundary="West", component=0, values=[0.0, 0.0], time_values=[0.0, t_final]),
                    dict(boundary="Bottom", component=2, values=[0.0, 0.0], time_values=[0.0, t_final]),
                    dict(boundary="South", component=1, values=[0.0, 0.0], time_values=[0.0, t_final])],
@@ -128,6 +136,11 @@ def build(case, grid, verbose=False, outputs=None, device="cuda", part=None, ctx
             el = sf.PressureSolutionCreep(e["A"] * one, e["d"] * one, e["Q"] * one, "pressure_solution")
         elif k == "desai":
             el = sf.ViscoplasticDesai(*[e[p] * one for p in sf.ViscoplasticDesai.param_names], e["alpha_0"] * one, "desai")
+        elif k == "munson_dawson":
+            el = sf.MunsonDawsonCreep(*[e[p] * one for p in sf.MunsonDawsonCreep.param_names], "munson_dawson")
+        elif k in ("mohr_coulomb", "matsuoka_nakai"):
+            cls = sf.MohrCoulombViscoplastic if k == "mohr_coulomb" else sf.MatsuokaNakaiViscoplastic
+            el = cls(*[e[p] * one for p in cls.param_names], k)
         else:
             raise ValueError(k)
         mat.add_to_non_elastic(el)

@@ -34,6 +34,19 @@ __device__ __forceinline__ DesaiP load_desai(const Row& row, int off) {
   return q;
 }
 
+__device__ __forceinline__ MunsonDawsonP load_md(const Row& row, int off) {
+  MunsonDawsonP q;
+  q.A = row[off + 0]; q.Q = row[off + 1]; q.n = row[off + 2]; q.K0 = row[off + 3]; q.c = row[off + 4];
+  q.m = row[off + 5]; q.alpha_w = row[off + 6]; q.beta_w = row[off + 7]; q.delta = row[off + 8]; q.mu = row[off + 9];
+  return q;
+}
+__device__ __forceinline__ MohrCoulombP load_mc(const Row& row, int off) {
+  return MohrCoulombP{row[off], row[off + 1], row[off + 2], row[off + 3], row[off + 4], row[off + 5]};
+}
+__device__ __forceinline__ MatsuokaNakaiP load_mn(const Row& row, int off) {
+  return MatsuokaNakaiP{row[off], row[off + 1], row[off + 2], row[off + 3], row[off + 4], row[off + 5]};
+}
+
 // accumulate column k of a 6x6 held in registers without dynamic indexing
 __device__ __forceinline__ void add_col(double G[36], int k, const double col[6]) {
 #pragma unroll
@@ -95,9 +108,52 @@ __device__ __forceinline__ double desai_Hh(const DesaiLin& L, int i, int k) {
   return H / L.h;
 }
 
+// Munson-Dawson: compute_B_and_H_over_h (MaterialProps.py:2235-2313).  Leaves r, h, h_small, P, Q in the same
+// record the Desai element uses (H/h has the same rank-one structure, desai_Hh).
+__device__ __forceinline__ void md_linearise(const double sig_k[6], double T, double zeta, double zeta_old, double dt,
+                                             const MunsonDawsonP& mp, DesaiLin& L) {
+  double rate_ref[6], rate_z[6], Fd, ets_now;
+  rate_munson_dawson(sig_k, T, zeta, mp, rate_ref, Fd, ets_now);
+  const double zeta_scale = clamp_min(fabs(zeta) + ets_now, 1.0e-30);
+  const double eps_zeta = SIC_MD_SQRT_EPS * zeta_scale;
+  L.r = md_residue(sig_k, T, zeta, zeta_old, dt, mp);
+  const double zeta_eps = zeta + eps_zeta;
+  const double r_zeta = md_residue(sig_k, T, zeta_eps, zeta_old, dt, mp);
+  double h = (r_zeta - L.r) / eps_zeta;
+  double ets_z;
+  rate_munson_dawson(sig_k, T, zeta_eps, mp, rate_z, Fd, ets_z);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) L.Q[c] = (rate_z[c] - rate_ref[c]) / eps_zeta;
+  L.h_small = fabs(h) < SIC_MD_H_MIN;
+  if (L.h_small) h = 1.0;
+  L.h = h;
+  double s[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) s[c] = sig_k[c];
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = (c == k) ? s[c] + SIC_MD_EPS_STRESS : s[c];
+    const double r_sig = md_residue(s, T, zeta, zeta_old, dt, mp);
+    const double Pk = (r_sig - L.r) / SIC_MD_EPS_STRESS;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.P[c] = (c == k) ? Pk : L.P[c];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = (c == k) ? s[c] - SIC_MD_EPS_STRESS : s[c];
+  }
+  L.qsi = 0.0;
+  if (L.h_small) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.P[c] = 0.0;
+  }
+}
+
 // =============================================================================================
 // tangent phase: LinearMomentum.compute_CT + compute_eps_rhs (MomentumEquation.py:799-820, 868-890)
+// EXT = false: the elements of BASELINE configs 1-4; EXT = true adds the SURVEY 8f elements (the host
+// picks the instantiation from the material, so the configs that do not use them run unchanged code).
 // =============================================================================================
+template <bool EXT>
 __global__ void __launch_bounds__(SIC_CELL_THREADS) k_tangent(sic_problem_t P, double dt, double theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
@@ -177,6 +233,45 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_tangent(sic_problem_t P, d
                    add_col(G, k, gc);
                  });
     }
+    if constexpr (EXT) {
+      if (el.kind == SIC_ELEM_MUNSON_DAWSON) {
+        MunsonDawsonP mp = load_md(row, off);
+        double* ms = el.desai;
+        const double zeta = ms[(size_t)SIC_MD_ZETA * ns + i];
+        const double zeta_old = ms[(size_t)SIC_MD_ZETA_OLD * ns + i];
+        DesaiLin L;
+        md_linearise(sk, T, zeta, zeta_old, dt, mp, L);
+        ms[(size_t)SIC_MD_R * ns + i] = L.r;
+        ms[(size_t)SIC_MD_H * ns + i] = L.h;
+        ms[(size_t)SIC_MD_HSMALL * ns + i] = L.h_small ? 1.0 : 0.0;
+        ms[(size_t)SIC_MD_ZETA_K * ns + i] = zeta;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          ms[(size_t)(SIC_MD_P + c) * ns + i] = L.P[c];
+          ms[(size_t)(SIC_MD_Q + c) * ns + i] = L.Q[c];
+        }
+        if (!L.h_small) {
+          double rh = L.r / L.h;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) B[c] = B[c] + rh * L.Q[c];
+        }
+        fd_columns([&](const double* s, double* r) { double f, e; rate_munson_dawson(s, T, zeta, mp, r, f, e); }, sk,
+                   [&](int k, const double* col) {
+                     double gc[6];
+#pragma unroll
+                     for (int r = 0; r < 6; ++r) gc[r] = col[r] - desai_Hh(L, r, k);
+                     add_col(G, k, gc);
+                   });
+      } else if (el.kind == SIC_ELEM_MOHR_COULOMB) {
+        MohrCoulombP cp = load_mc(row, off);
+        fd_columns([&](const double* s, double* r) { double f; rate_mohr_coulomb(s, cp, r, f); }, sk,
+                   [&](int k, const double* col) { add_col(G, k, col); });
+      } else if (el.kind == SIC_ELEM_MATSUOKA_NAKAI) {
+        MatsuokaNakaiP np_ = load_mn(row, off);
+        fd_columns([&](const double* s, double* r) { double f; rate_matsuoka_nakai(s, np_, r, f); }, sk,
+                   [&](int k, const double* col) { add_col(G, k, col); });
+      }
+    }
   }
 
   // eps_th = sum alpha_th (T - T0) I   (MaterialProps.py:365-382, MomentumEquation.py:343-357)
@@ -253,6 +348,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_elastic_tangent(sic_proble
 // =============================================================================================
 // post-solve phase of one Newton iteration (Simulators.py:416-436)
 // =============================================================================================
+template <bool EXT>
 __global__ void __launch_bounds__(SIC_CELL_THREADS) k_post(sic_problem_t P, const double* __restrict__ u, double dt,
                                                           double theta, double kelvin_phi2, int flags,
                                                           double* __restrict__ err_scratch) {
@@ -347,6 +443,38 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_post(sic_problem_t P, cons
           double fv;
           rate_desai(sig, alpha, alpha_0, dp, rate, fv);
           ds[(size_t)SIC_DS_FVP * ns + i] = fv;
+        } else if (EXT && el.kind == SIC_ELEM_MUNSON_DAWSON) {
+          MunsonDawsonP mp = load_md(row, off);
+          double* ms = el.desai;
+          double zeta = ms[(size_t)SIC_MD_ZETA * ns + i];
+          if (flags & SIC_POST_INCREMENT) {
+            // increment_internal_variables (MaterialProps.py:2081-2102)
+            double sk[6], Pv[6], dsig[6];
+            load6(P.sig_k, ns, i, sk);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              Pv[c] = ms[(size_t)(SIC_MD_P + c) * ns + i];
+              dsig[c] = sig[c] - sk[c];
+            }
+            const double r = ms[(size_t)SIC_MD_R * ns + i];
+            const double h = ms[(size_t)SIC_MD_H * ns + i];
+            const bool h_small = ms[(size_t)SIC_MD_HSMALL * ns + i] != 0.0;
+            double d_zeta = (-(r + ddot_sym(Pv, dsig))) / h;
+            if (h_small) d_zeta = 0.0;
+            zeta = clamp_min(zeta + d_zeta, 0.0);
+            ms[(size_t)SIC_MD_ZETA * ns + i] = zeta;
+          }
+          if (!(flags & SIC_POST_RATES)) continue;
+          double Fd, ets;
+          rate_munson_dawson(sig, T, zeta, mp, rate, Fd, ets);
+          ms[(size_t)SIC_MD_F * ns + i] = Fd;
+          ms[(size_t)SIC_MD_ETS * ns + i] = ets;
+        } else if (EXT && (el.kind == SIC_ELEM_MOHR_COULOMB || el.kind == SIC_ELEM_MATSUOKA_NAKAI)) {
+          if (!(flags & SIC_POST_RATES)) continue;
+          double fv;
+          if (el.kind == SIC_ELEM_MOHR_COULOMB) rate_mohr_coulomb(sig, load_mc(row, off), rate, fv);
+          else rate_matsuoka_nakai(sig, load_mn(row, off), rate, fv);
+          el.desai[(size_t)SIC_VP_FVP * ns + i] = fv;
         } else {
           if (!(flags & SIC_POST_RATES)) continue;
           if (el.kind == SIC_ELEM_KELVIN) {
@@ -405,6 +533,7 @@ __global__ void k_post_err_final(const double* __restrict__ scratch, int n_block
 // =============================================================================================
 // commit of a converged step (Simulators.py:509-517)
 // =============================================================================================
+template <bool EXT>
 __global__ void __launch_bounds__(SIC_CELL_THREADS) k_commit(sic_problem_t P, double dt, double theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
@@ -469,6 +598,42 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_commit(sic_problem_t P, do
                  });
       // update_internal_variables (MaterialProps.py:1119-1127)
       ds[(size_t)SIC_DS_QSI_OLD * ns + i] = ds[(size_t)SIC_DS_QSI * ns + i];
+    }
+    if constexpr (EXT) {
+      if (el.kind == SIC_ELEM_MUNSON_DAWSON) {
+        MunsonDawsonP mp = load_md(row, off);
+        double* ms = el.desai;
+        DesaiLin L;
+        L.r = ms[(size_t)SIC_MD_R * ns + i];
+        L.h = ms[(size_t)SIC_MD_H * ns + i];
+        L.h_small = ms[(size_t)SIC_MD_HSMALL * ns + i] != 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          L.P[c] = ms[(size_t)(SIC_MD_P + c) * ns + i];
+          L.Q[c] = ms[(size_t)(SIC_MD_Q + c) * ns + i];
+        }
+        const double zeta_k = ms[(size_t)SIC_MD_ZETA_K * ns + i];
+        if (!L.h_small) {
+          double rh = L.r / L.h;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) Bv[c] = rh * L.Q[c];
+        }
+        fd_columns([&](const double* s, double* r) { double f, e; rate_munson_dawson(s, T, zeta_k, mp, r, f, e); }, sk,
+                   [&](int k, const double* col) {
+                     double gc[6];
+#pragma unroll
+                     for (int r = 0; r < 6; ++r) gc[r] = col[r] - desai_Hh(L, r, k);
+                     acc(k, gc);
+                   });
+        // update_internal_variables (MaterialProps.py:2077-2079)
+        ms[(size_t)SIC_MD_ZETA_OLD * ns + i] = ms[(size_t)SIC_MD_ZETA * ns + i];
+      } else if (el.kind == SIC_ELEM_MOHR_COULOMB) {
+        MohrCoulombP cp = load_mc(row, off);
+        fd_columns([&](const double* s, double* r) { double f; rate_mohr_coulomb(s, cp, r, f); }, sk, acc);
+      } else if (el.kind == SIC_ELEM_MATSUOKA_NAKAI) {
+        MatsuokaNakaiP np_ = load_mn(row, off);
+        fd_columns([&](const double* s, double* r) { double f; rate_matsuoka_nakai(s, np_, r, f); }, sk, acc);
+      }
     }
     // update_eps_ne_rate_old (:630-638)
     double rate[6];
@@ -545,18 +710,26 @@ static int check_problem(const sic_problem_t* p) {
   if (p->n_thermo < 0 || p->n_thermo > SIC_MAX_THERMO) return sic_fail("too many thermoelastic elements");
   for (int e = 0; e < p->n_elems; ++e) {
     int k = p->elems[e].kind;
-    if (k < SIC_ELEM_KELVIN || k > SIC_ELEM_DESAI) return sic_fail("unknown element kind");
-    if (k == SIC_ELEM_DESAI && !p->elems[e].desai) return sic_fail("Desai element without state block");
+    if (k < SIC_ELEM_KELVIN || k > SIC_ELEM_MATSUOKA_NAKAI) return sic_fail("unknown element kind");
+    if (k >= SIC_ELEM_DESAI && !p->elems[e].desai) return sic_fail("element with internal state but without its state block");
   }
   return 0;
 }
 
 static inline int cell_blocks(int n) { return (n + SIC_CELL_THREADS - 1) / SIC_CELL_THREADS; }
 
+// does the material use one of the SURVEY 8f elements (-> the EXT instantiations of the kernels)?
+static inline bool has_ext(const sic_problem_t* p) {
+  for (int e = 0; e < p->n_elems; ++e)
+    if (p->elems[e].kind > SIC_ELEM_DESAI) return true;
+  return false;
+}
+
 extern "C" int sic_tangent(const sic_problem_t* p, double dt, double theta, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (p->n_cells == 0) return 0;
-  k_tangent<<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  if (has_ext(p)) k_tangent<true><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  else k_tangent<false><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
   return sic_check_launch("k_tangent");
 }
 
@@ -577,7 +750,8 @@ extern "C" int sic_post(const sic_problem_t* p, const double* u, double dt, doub
     return sic_fail("sic_post: SIC_POST_ERROR needs SIC_POST_STRAIN, err_out and err_scratch");
   if (p->n_cells == 0) return 0;
   const int nb = cell_blocks(p->n_cells);
-  k_post<<<nb, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, u, dt, theta, kelvin_phi2, flags, err_scratch);
+  if (has_ext(p)) k_post<true><<<nb, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, u, dt, theta, kelvin_phi2, flags, err_scratch);
+  else k_post<false><<<nb, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, u, dt, theta, kelvin_phi2, flags, err_scratch);
   if (int rc = sic_check_launch("k_post")) return rc;
   if (flags & SIC_POST_ERROR) {
     k_post_err_final<<<1, 1024, 0, (cudaStream_t)stream>>>(err_scratch, nb, err_out);
@@ -589,7 +763,8 @@ extern "C" int sic_post(const sic_problem_t* p, const double* u, double dt, doub
 extern "C" int sic_commit(const sic_problem_t* p, double dt, double theta, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (p->n_cells == 0 || p->n_elems == 0) return 0;
-  k_commit<<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  if (has_ext(p)) k_commit<true><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  else k_commit<false><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
   return sic_check_launch("k_commit");
 }
 

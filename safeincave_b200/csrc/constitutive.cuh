@@ -172,6 +172,158 @@ __device__ __forceinline__ double ddot_sym(const double a[6], const double b[6])
   return d + 2.0 * o;
 }
 
+
+// =============================================================================================
+// MunsonDawsonCreep, MohrCoulombViscoplastic, MatsuokaNakaiViscoplastic
+// =============================================================================================
+#define SIC_MD_SQRT_EPS 1.4901161193847656e-8   /* MaterialProps.py:2013 */
+#define SIC_MD_EPS_STRESS 1.0e-1               /* MaterialProps.py:2263 */
+#define SIC_MD_H_MIN 1.0e-12                   /* MaterialProps.py:2283 */
+
+// ---- MunsonDawsonCreep, MaterialProps.py:1971-2346 -------------------------------------------
+struct MunsonDawsonP { double A, Q, n, K0, c, m, alpha_w, beta_w, delta, mu; };
+
+__device__ __forceinline__ double clamp_min(double x, double lo) { return (x < lo) ? lo : x; }   // NaN stays NaN
+
+// _compute_md_fields (:2104-2167): deviator, von Mises stress (floored at 1 Pa), steady-state rate,
+// transient limit eps_t*, transient function F
+__device__ __forceinline__ void md_fields(const double s[6], double T, double zeta, const MunsonDawsonP& p,
+                                          double dev[6], double& sigma_safe, double& epsdot_ss, double& ets, double& F) {
+  const double mean = ((s[0] + s[1]) + s[2]) / 3.0;
+  dev[0] = s[0] - mean; dev[1] = s[1] - mean; dev[2] = s[2] - mean;
+  dev[3] = s[3]; dev[4] = s[4]; dev[5] = s[5];
+  const double a = s[0] - s[1], b = s[0] - s[2], c = s[1] - s[2];
+  const double sigma = sqrt(0.5 * (((a * a + b * b) + c * c) + 6.0 * ((s[3] * s[3] + s[4] * s[4]) + s[5] * s[5])));
+  sigma_safe = clamp_min(sigma, 1.0);
+  const double mu_safe = clamp_min(p.mu, 1.0);
+  epsdot_ss = (p.A * sic_exp((-p.Q) / (SIC_R_GAS * T))) * sic_pow(sigma_safe, p.n);
+  const double ratio = clamp_min(sigma_safe / mu_safe, 1.0e-30);
+  ets = (p.K0 * sic_exp(p.c * T)) * sic_pow(ratio, p.m);
+  ets = clamp_min(ets, 1.0e-50);
+  const double Delta = p.alpha_w + p.beta_w * sic_log10(ratio);
+  const double r_arg = 1.0 - (zeta / ets);
+  const double r2 = r_arg * r_arg;
+  double arg = (zeta <= ets) ? Delta * r2 : (-p.delta) * r2;
+  arg = (arg < -50.0) ? -50.0 : ((arg > 50.0) ? 50.0 : arg);
+  F = sic_exp(arg);
+}
+
+// compute_eps_ne_rate (:2187-2229)
+__device__ __forceinline__ void rate_munson_dawson(const double s[6], double T, double zeta, const MunsonDawsonP& p,
+                                                   double rate[6], double& F, double& ets) {
+  double dev[6], sigma_safe, epsdot_ss;
+  md_fields(s, T, zeta, p, dev, sigma_safe, epsdot_ss, ets, F);
+  const double scalar_rate = F * epsdot_ss;
+  const double f = 1.5 / sigma_safe;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) rate[k] = (f * dev[k]) * scalar_rate;
+}
+
+// compute_residue (:2169-2181)
+__device__ __forceinline__ double md_residue(const double s[6], double T, double zeta, double zeta_old, double dt,
+                                             const MunsonDawsonP& p) {
+  double dev[6], sigma_safe, epsdot_ss, ets, F;
+  md_fields(s, T, zeta, p, dev, sigma_safe, epsdot_ss, ets, F);
+  return (zeta - zeta_old) - ((F - 1.0) * epsdot_ss) * dt;
+}
+
+// ---- Drucker-Prager flow direction shared by MohrCoulomb / MatsuokaNakai (:1705-1731, 1927-1953) ------
+__device__ __forceinline__ void dp_flow_rate(const double c[6], double I1, double alpha_Q, bool is_tension, double lam,
+                                             double rate[6]) {
+  const double I2 = ((((c[0] * c[1] + c[1] * c[2]) + c[0] * c[2]) - c[3] * c[3]) - c[5] * c[5]) - c[4] * c[4];
+  const double J2 = clamp_min((1.0 / 3.0) * (I1 * I1) - I2, 1.0e-20);
+  const double inv = 1.0 / (2.0 * sqrt(J2));
+  double dQ[6];
+  dQ[0] = inv * ((2.0 / 3.0) * I1 - (c[1] + c[2])) - alpha_Q;
+  dQ[1] = inv * ((2.0 / 3.0) * I1 - (c[0] + c[2])) - alpha_Q;
+  dQ[2] = inv * ((2.0 / 3.0) * I1 - (c[0] + c[1])) - alpha_Q;
+  dQ[3] = inv * (2.0 * c[3]);
+  dQ[4] = inv * (2.0 * c[4]);
+  dQ[5] = inv * (2.0 * c[5]);
+  if (is_tension) {
+    dQ[0] = dQ[1] = dQ[2] = -1.0 / 3.0;
+    dQ[3] = dQ[4] = dQ[5] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) rate[k] = (-dQ[k]) * lam;
+}
+
+// ---- MohrCoulombViscoplastic.compute_eps_ne_rate, MaterialProps.py:1652-1746 ------------------
+struct MohrCoulombP { double mu_1, N_1, alpha_F, k_F, alpha_Q, sigma_t; };
+__device__ __forceinline__ void rate_mohr_coulomb(const double sig[6], const MohrCoulombP& p, double rate[6],
+                                                  double& Fvp_out) {
+  double c[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) c[k] = (-sig[k]) / SIC_MPA;
+  const double I1 = (c[0] + c[1]) + c[2];
+  const double I2 = ((((c[0] * c[1] + c[1] * c[2]) + c[0] * c[2]) - c[3] * c[3]) - c[5] * c[5]) - c[4] * c[4];
+  const double J2 = clamp_min((1.0 / 3.0) * (I1 * I1) - I2, 1.0e-20);
+  const double F_shear = (sqrt(J2) - p.alpha_F * I1) - p.k_F;
+  const double F_tension = (-I1) / 3.0 - p.sigma_t;
+  const double Fvp = (F_shear > F_tension || F_shear != F_shear) ? F_shear : F_tension;   // torch.maximum: NaN wins
+  Fvp_out = (F_tension != F_tension) ? F_tension : Fvp;
+  double lam = 0.0;
+  if (Fvp_out > 0.0) lam = p.mu_1 * sic_pow(Fvp_out / 1.0, p.N_1);
+  dp_flow_rate(c, I1, p.alpha_Q, F_tension > F_shear, lam, rate);
+}
+
+// ---- eigenvalues of a symmetric 3x3 (ascending): six cyclic Jacobi sweeps, fixed operation sequence ----
+// (torch.linalg.eigvalsh in the reference, MaterialProps.py:1882; the oracle restates THIS routine
+// operation for operation next to its LAPACK call so that device and oracle agree bit for bit)
+__device__ __forceinline__ void jacobi_rotate(double& app, double& aqq, double& apq, double& arp, double& arq) {
+  double t = 0.0;
+  if (apq != 0.0) {
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double at = fabs(theta);
+    t = 1.0 / (at + sqrt(theta * theta + 1.0));
+    if (theta < 0.0) t = -t;
+  }
+  const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+  app = app - t * apq;
+  aqq = aqq + t * apq;
+  apq = 0.0;
+  const double rp = c * arp - s * arq, rq = s * arp + c * arq;
+  arp = rp; arq = rq;
+}
+__device__ __forceinline__ void eigvals_sym3(const double c[6], double& e_lo, double& e_mid, double& e_hi) {
+  double a00 = c[0], a11 = c[1], a22 = c[2], a01 = c[3], a02 = c[4], a12 = c[5];
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    jacobi_rotate(a00, a11, a01, a02, a12);   // (p,q) = (0,1), r = 2
+    jacobi_rotate(a00, a22, a02, a01, a12);   // (0,2), r = 1
+    jacobi_rotate(a11, a22, a12, a01, a02);   // (1,2), r = 0
+  }
+  double x = a00, y = a11, z = a22, t;
+  if (y < x) { t = x; x = y; y = t; }
+  if (z < y) { t = y; y = z; z = t; }
+  if (y < x) { t = x; x = y; y = t; }
+  e_lo = x; e_mid = y; e_hi = z;
+}
+
+// ---- MatsuokaNakaiViscoplastic.compute_eps_ne_rate, MaterialProps.py:1835-1968 ------------------
+struct MatsuokaNakaiP { double mu_1, N_1, k_nfc, shift, alpha_Q, sigma_t; };
+__device__ __forceinline__ void rate_matsuoka_nakai(const double sig[6], const MatsuokaNakaiP& p, double rate[6],
+                                                    double& Fvp_out) {
+  double c[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) c[k] = (-sig[k]) / SIC_MPA;
+  double sig3, sig2, sig1;
+  eigvals_sym3(c, sig3, sig2, sig1);
+  const double s1 = sig1 + p.shift, s2 = sig2 + p.shift, s3 = sig3 + p.shift;
+  const double d12 = clamp_min(s1 + s2, 1.0e-20), d23 = clamp_min(s2 + s3, 1.0e-20), d31 = clamp_min(s3 + s1, 1.0e-20);
+  const double q12 = (s1 - s2) / d12, q23 = (s2 - s3) / d23, q31 = (s3 - s1) / d31;
+  const double f_nfc = sqrt(((q12 * q12 + q23 * q23) + q31 * q31) + 1.0e-30) - p.k_nfc;
+  const double p_mean = clamp_min(((s1 + s2) + s3) / 3.0, 1.0e-20);
+  const double F_shear = f_nfc * p_mean;
+  const double I1 = (c[0] + c[1]) + c[2];
+  const double F_tension = (-I1) / 3.0 - p.sigma_t;
+  const double Fvp = (F_shear > F_tension || F_shear != F_shear) ? F_shear : F_tension;
+  Fvp_out = (F_tension != F_tension) ? F_tension : Fvp;
+  double lam = 0.0;
+  if (Fvp_out > 0.0) lam = p.mu_1 * sic_pow(Fvp_out / 1.0, p.N_1);
+  dp_flow_rate(c, I1, p.alpha_Q, F_tension > F_shear, lam, rate);
+}
+
 // ---- NonElasticElement.compute_E, MaterialProps.py:640-675 ---------------------------------
 // Central FD with an ABSOLUTE step of 1e-2 Pa on a running copy (+=, -=, -=, +=),
 // shear columns doubled (T3).  consume(k, col) receives column k of E.  The k loop is kept

@@ -153,6 +153,9 @@ SIC_HD double sic_log(double x) {
 // pow(x, y) with C99 semantics for the cases the constitutive laws can reach
 // (negative base with integral exponent keeps its sign; negative base with a
 // fractional exponent is NaN, as torch/numpy give).
+// log10(x) = log(x) * (1/ln 10): one extra rounding on top of sic_log (MunsonDawsonCreep's Delta, MaterialProps.py:2153)
+SIC_HD double sic_log10(double x) { return sic_log(x) * 0.43429448190325182765; }
+
 SIC_HD double sic_pow(double x, double y) {
   if (y == 0.0) return 1.0;
   if (x == 1.0) return 1.0;

@@ -50,24 +50,35 @@ class ElemState:
         z = lambda rows: torch.zeros((rows, ns), dtype=torch.float64, device=device)
         self.kind = kind
         self.eps_old, self.rate_old, self.rate, self.eps_k = z(6), z(6), z(6), z(6)
-        self.desai = z(L.DESAI_ROWS) if kind == L.ELEM_DESAI else None
-        if self.desai is not None:
+        # internal-state block (sic_elem_t.desai): Desai 21 rows, Munson-Dawson 20, Mohr-Coulomb / Matsuoka-Nakai 1
+        self.desai = z(L.ISV_ROWS[kind]) if kind in L.ISV_ROWS else None
+        if kind == L.ELEM_DESAI:
             self.desai[L.DS_H].fill_(1.0)
+        elif kind == L.ELEM_MUNSON_DAWSON:            # MaterialProps.py:2052-2063
+            self.desai[L.MD_H].fill_(1.0)
+            self.desai[L.MD_F].fill_(1.0)
+            self.desai[L.MD_ETS].fill_(1.0)
 
     SNAP = ("rate", "rate_old", "eps_old", "eps_k")
+    # rows of the internal-state block that save_internal_state keeps (MomentumEquation.py:456-477)
+    SNAP_ROWS = {L.ELEM_DESAI: [L.DS_ALPHA, L.DS_QSI, L.DS_QSI_OLD, L.DS_FVP],
+                 L.ELEM_MUNSON_DAWSON: [L.MD_ZETA, L.MD_ZETA_OLD]}
 
     def snapshot(self):
-        """save_internal_state, MomentumEquation.py:456-477 (alpha, qsi, qsi_old, Fvp for Desai)."""
+        """save_internal_state, MomentumEquation.py:456-477 (alpha, qsi, qsi_old, Fvp for Desai; zeta, zeta_old
+        for Munson-Dawson)."""
         snap = {k: getattr(self, k).clone() for k in self.SNAP}
-        if self.desai is not None:
-            snap["desai"] = self.desai[[L.DS_ALPHA, L.DS_QSI, L.DS_QSI_OLD, L.DS_FVP]].clone()
+        rows = self.SNAP_ROWS.get(self.kind)
+        if rows:
+            snap["desai"] = self.desai[rows].clone()
         return snap
 
     def restore(self, snap):
         for k in self.SNAP:
             getattr(self, k).copy_(snap[k])
-        if self.desai is not None:
-            self.desai[[L.DS_ALPHA, L.DS_QSI, L.DS_QSI_OLD, L.DS_FVP]] = snap["desai"]
+        rows = self.SNAP_ROWS.get(self.kind)
+        if rows:
+            self.desai[rows] = snap["desai"]
 
 
 class Engine:

@@ -20,6 +20,11 @@ def oracle_material(case, n):
             mat.add(oc.PressureSolution(e["A"] * one, e["d"] * one, e["Q"] * one))
         elif k == "desai":
             mat.add(oc.Desai(e["alpha_0"] * one, **{p: e[p] * one for p in oc.DesaiParams.names}))
+        elif k == "munson_dawson":
+            mat.add(oc.MunsonDawson(**{p: e[p] * one for p in oc.MunsonDawsonParams.names}))
+        elif k in ("mohr_coulomb", "matsuoka_nakai"):
+            cls = oc.MohrCoulomb if k == "mohr_coulomb" else oc.MatsuokaNakai
+            mat.add(cls(*[e[p] * one for p in ("mu_1", "N_1", "cohesion", "friction_angle", "dilation_angle", "sigma_t")]))
     return mat
 
 

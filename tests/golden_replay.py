@@ -36,7 +36,15 @@ def build_oracle_material(g):
             mat.add(oc.Desai(P(kind, "alpha_0"), **kw))
         elif kind == "thermo":
             mat.add_thermoelastic(P(kind, "alpha"))
+        elif kind == "munson_dawson":
+            mat.add(oc.MunsonDawson(**{k: P(kind, k) for k in oc.MunsonDawsonParams.names}))
+        elif kind in ("mohr_coulomb", "matsuoka_nakai"):
+            cls = oc.MohrCoulomb if kind == "mohr_coulomb" else oc.MatsuokaNakai
+            mat.add(cls(*[P(kind, k) for k in INTERLAYER_NAMES]))
     return mat
+
+
+INTERLAYER_NAMES = ("mu_1", "N_1", "cohesion", "friction_angle", "dilation_angle", "sigma_t")
 
 
 def cell_rel_err(a, b):
@@ -53,7 +61,7 @@ def cell_rel_err(a, b):
 
 
 STATE_FIELDS = ("rate", "rate_old", "eps_old", "eps_k")
-ISV_FIELDS = ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old", "r", "h", "P")
+ISV_FIELDS = ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old", "r", "h", "P", "zeta", "zeta_old", "F")
 GOLD_NAME = {"rate": "eps_ne_rate", "rate_old": "eps_ne_rate_old", "eps_old": "eps_ne_old",
              "eps_k": "eps_ne_k"}
 
@@ -61,7 +69,8 @@ GOLD_NAME = {"rate": "eps_ne_rate", "rate_old": "eps_ne_rate_old", "eps_old": "e
 # (e.g. the Desai flow rate when Fvp is a round-off-sized number right after
 # compute_initial_hardening, or the residue r = alpha - alpha_0*(1+O(eps)))
 ATOL = {"rate": 1e-22, "rate_old": 1e-22, "eps_old": 1e-20, "eps_k": 1e-20, "r": 1e-15,
-        "B": 1e-20, "B_elem": 1e-20, "P": 1e-22, "Fvp": 1.0, "qsi": 1e-18, "eps_rhs": 1e-18}
+        "B": 1e-20, "B_elem": 1e-20, "P": 1e-22, "Fvp": 1.0, "qsi": 1e-18, "eps_rhs": 1e-18,
+        "zeta": 1e-20, "zeta_old": 1e-20}
 
 
 def err(a, b, atol=0.0):
@@ -89,7 +98,7 @@ def inject(mat, g, tag, with_tangent=False):
     """Overwrite the implementation's per-element state with the reference's record."""
     for i, e in enumerate(mat.elems):
         pre = f"{tag}/e{i}"
-        names = STATE_FIELDS + ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old")
+        names = STATE_FIELDS + ("alpha", "alpha_0", "Fvp", "qsi", "qsi_old", "zeta", "zeta_old", "F")
         if with_tangent:
             names = names + ("r", "h", "P")
         for f in names:
@@ -97,7 +106,8 @@ def inject(mat, g, tag, with_tangent=False):
             if key in g and hasattr(e, f):
                 setattr(e, f, gold(g, key).copy())
         if with_tangent and hasattr(e, "h_small"):
-            # the reference flags |h| < 1e-6 and resets h to 1, P to 0 (MaterialProps.py:1473-1498)
+            # the reference flags |h| < 1e-6 (Desai; 1e-12 MunsonDawson) and resets h to 1, P to 0
+            # (MaterialProps.py:1473-1498, 2275-2311)
             P = gold(g, f"{pre}/P")
             e.h_small = (gold(g, f"{pre}/h") == 1.0) & (np.abs(P).max(axis=1) == 0.0)
 
@@ -131,7 +141,7 @@ def replay(g, mat, isolate=True):
                 e.initial_hardening(sig, 0.0)
     mat.eval_rates(sig, 0.0 * theta, T)
     mat.commit_rates()
-    compare(mat, g, "init", "init", errs, STATE_FIELDS + ("alpha", "alpha_0", "Fvp"))
+    compare(mat, g, "init", "init", errs, STATE_FIELDS + ("alpha", "alpha_0", "Fvp", "F"))
     prev = "init"
     for step in range(int(g["n_steps"])):
         for it in range(int(g["n_iters"])):
@@ -163,14 +173,14 @@ def replay(g, mat, isolate=True):
                 eps_tot = oc.ddot(mat.C_inv, sig_k * scale) + eps_rhs
             sig = mat.post_phase(eps_tot, sig_k, T, dt, theta)
             errs.setdefault("post:sig", []).append(err(sig, gold(g, f"{tag}/sig")))
-            compare(mat, g, tag + "/post", "post", errs, ("rate", "alpha", "Fvp"))
+            compare(mat, g, tag + "/post", "post", errs, ("rate", "alpha", "Fvp", "zeta", "F"))
             prev = tag + "/post"
             if isolate:
                 sig = gold(g, f"{tag}/sig")
         if isolate:
             inject(mat, g, prev)
         mat.commit(sig, sig_k, dt, theta)
-        compare(mat, g, f"s{step}/commit", "commit", errs, ("rate_old", "eps_old", "qsi_old"))
+        compare(mat, g, f"s{step}/commit", "commit", errs, ("rate_old", "eps_old", "qsi_old", "zeta_old"))
         prev = f"s{step}/commit"
     return {k: max(v) for k, v in errs.items()}
 

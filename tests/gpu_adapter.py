@@ -8,7 +8,16 @@ from safeincave_b200 import _lib as L
 from safeincave_b200.engine import Engine
 
 KIND_NAME = {L.ELEM_KELVIN: "kelvin", L.ELEM_DISLOCATION: "dislocation",
-             L.ELEM_PRESSURE_SOL: "pressure_solution", L.ELEM_DESAI: "desai"}
+             L.ELEM_PRESSURE_SOL: "pressure_solution", L.ELEM_DESAI: "desai", L.ELEM_MUNSON_DAWSON: "munson_dawson",
+             L.ELEM_MOHR_COULOMB: "mohr_coulomb", L.ELEM_MATSUOKA_NAKAI: "matsuoka_nakai"}
+# name -> row of the element's internal-state block, per element kind
+ROWS = {
+    L.ELEM_DESAI: {"alpha": L.DS_ALPHA, "alpha_0": L.DS_ALPHA0, "Fvp": L.DS_FVP, "qsi": L.DS_QSI,
+                   "qsi_old": L.DS_QSI_OLD, "r": L.DS_R, "h": L.DS_H, "P": L.DS_P, "h_small": L.DS_HSMALL},
+    L.ELEM_MUNSON_DAWSON: {"zeta": L.MD_ZETA, "zeta_old": L.MD_ZETA_OLD, "F": L.MD_F, "r": L.MD_R, "h": L.MD_H,
+                           "P": L.MD_P, "h_small": L.MD_HSMALL},
+    L.ELEM_MOHR_COULOMB: {"Fvp": L.VP_FVP}, L.ELEM_MATSUOKA_NAKAI: {"Fvp": L.VP_FVP},
+}
 DS_ROW = {"alpha": L.DS_ALPHA, "alpha_0": L.DS_ALPHA0, "Fvp": L.DS_FVP, "qsi": L.DS_QSI,
           "qsi_old": L.DS_QSI_OLD, "r": L.DS_R, "h": L.DS_H}
 
@@ -34,25 +43,26 @@ class GpuElemView:
         eng, st = self._eng, self._st
         if name in ("rate", "rate_old", "eps_old", "eps_k"):
             return eng.get6(getattr(st, name))
-        if st.desai is not None:
-            if name in DS_ROW:
-                return eng.get1(st.desai[DS_ROW[name]])
+        rows = ROWS.get(st.kind, {})
+        if name in rows:
+            r = rows[name]
             if name == "P":
-                return eng.get6(st.desai[L.DS_P:L.DS_P + 6])
-            if name == "h_small":
-                return eng.get1(st.desai[L.DS_HSMALL]) != 0
+                return eng.get6(st.desai[r:r + 6])
+            v = eng.get1(st.desai[r])
+            return v != 0 if name == "h_small" else v
         raise AttributeError(name)
 
     def __setattr__(self, name, value):
         eng, st = self._eng, self._st
+        rows = ROWS.get(st.kind, {})
         if name in ("rate", "rate_old", "eps_old", "eps_k"):
             eng.put6(getattr(st, name), value)
-        elif st.desai is not None and name in DS_ROW:
-            eng.put1(st.desai[DS_ROW[name]], value)
-        elif st.desai is not None and name == "P":
-            eng.put6(st.desai[L.DS_P:L.DS_P + 6], value)
-        elif st.desai is not None and name == "h_small":
-            eng.put1(st.desai[L.DS_HSMALL], np.asarray(value, dtype=np.float64))
+        elif name in rows:
+            r = rows[name]
+            if name == "P":
+                eng.put6(st.desai[r:r + 6], value)
+            else:
+                eng.put1(st.desai[r], np.asarray(value, dtype=np.float64))
         else:
             raise AttributeError(name)
 
@@ -89,6 +99,11 @@ class GpuMaterial:
                 mat.add_to_non_elastic(sf.ViscoplasticDesai(*[P(kind, k) for k in names], P(kind, "alpha_0")))
             elif kind == "thermo":
                 mat.add_to_thermoelastic(sf.Thermoelastic(P(kind, "alpha")))
+            elif kind == "munson_dawson":
+                mat.add_to_non_elastic(sf.MunsonDawsonCreep(*[P(kind, k) for k in sf.MunsonDawsonCreep.param_names]))
+            elif kind in ("mohr_coulomb", "matsuoka_nakai"):
+                cls = sf.MohrCoulombViscoplastic if kind == "mohr_coulomb" else sf.MatsuokaNakaiViscoplastic
+                mat.add_to_non_elastic(cls(*[P(kind, k) for k in cls.param_names]))
         coords, cells = disjoint_tets(N)
         self.eng = self.engine_cls(coords, cells)
         mat.bind(self.eng)

@@ -20,3 +20,5 @@ test_cuda_vs_reference_goldens = G.test_cuda_vs_reference_goldens
 test_cuda_vs_oracle_all_quantities = G.test_cuda_vs_oracle_all_quantities
 test_float32_params_match_reference_stiffness = G.test_float32_params_match_reference_stiffness
 test_singular_tangent_falls_back_to_elastic = G.test_singular_tangent_falls_back_to_elastic
+test_cuda_vs_oracle_all_quantities_extended_elements = G.test_cuda_vs_oracle_all_quantities_extended_elements
+test_cuda_vs_reference_goldens_extended_elements = G.test_cuda_vs_reference_goldens_extended_elements

@@ -24,3 +24,5 @@ test_neumann_and_body_force = G.test_neumann_and_body_force
 test_time_steps_triaxial_cube = G.test_time_steps_triaxial_cube
 test_time_steps_triaxial_cube_with_desai = G.test_time_steps_triaxial_cube_with_desai
 test_krylov_solve_matches_direct = G.test_krylov_solve_matches_direct
+test_time_steps_triaxial_cube_munson_dawson = G.test_time_steps_triaxial_cube_munson_dawson
+test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai = G.test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai

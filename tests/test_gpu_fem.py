@@ -168,15 +168,16 @@ def run_both(sf, grid_name, case_fn, n_steps, levels=0, solver_opts=None, **kw):
     return eq, sim, hist, osim, ohist
 
 
-def check_fields(eq, osim, ohist, tol=1e-8):
+def check_fields(eq, osim, ohist, tol=1e-8, tol_state=None):
     eng = eq.engine
     last = ohist[-1]
+    tol_state = tol if tol_state is None else tol_state
     assert relerr(eq.X.reshape(-1).cpu().numpy(), last["u"]) < tol
     assert relerr(eng.get6(eng.sig), last["sig"]) < tol
     assert relerr(eng.get6(eng.eps), last["eps"]) < tol
     for e_gpu, e_or in zip(eng.elems, osim.mat.elems):
-        assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol
-        assert relerr(eng.get6(e_gpu.rate_old), e_or.rate_old) < tol
+        assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol_state
+        assert relerr(eng.get6(e_gpu.rate_old), e_or.rate_old) < tol_state
 
 
 def test_time_steps_triaxial_cube(sf):
@@ -193,6 +194,44 @@ def test_time_steps_triaxial_cube_with_desai(sf):
     eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 3, levels=1,
                                           elements=("kelvin", "dislocation", "desai"))
     check_fields(eq, osim, ohist, tol=1e-7)
+
+
+def test_time_steps_triaxial_cube_munson_dawson(sf):
+    """the fork's production creep model (Spring + Kelvin + MunsonDawsonCreep) through whole time
+    steps; zeta is carried, incremented inside the Newton loop and committed."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 4, levels=1,
+                                          elements=("kelvin", "munson_dawson"))
+    assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+    assert all(h["converged"] for h in hist)
+    # u, sigma, eps: 1e-8.  The element's own strain and zeta pass through h = dr/dzeta, a forward difference with a
+    # sqrt(eps)-sized step (MaterialProps.py:2013, 2257): on IDENTICAL inputs kernel and oracle agree bit for bit
+    # (test_cuda_vs_oracle_all_quantities_extended_elements), but here the iterative solve (rtol 1e-12) and the
+    # oracle's sparse LU hand them stresses that differ in the last digits, and the FD round-off (~1e-8) decorrelates.
+    check_fields(eq, osim, ohist, tol_state=1e-6)
+    eng = eq.engine
+    zeta = eng.get1(eng.elems[1].desai[0])
+    assert np.abs(osim.mat.elems[1].zeta).max() > 0
+    assert relerr(zeta, osim.mat.elems[1].zeta) < 1e-6      # zeta's Newton increment divides by an FD-derived h
+    assert relerr(eq.mat.elems_ne[1].zeta.numpy(), zeta) == 0.0   # host attribute pulls the device row
+
+
+def test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai(sf):
+    """interlayer viscoplasticity.  The triaxial load path (16 MPa axial on 4 MPa confinement,
+    c = 1 MPa, phi = 25 deg) crosses the yield surface, so the Perzyna flow is active in the later steps."""
+    from safeincave_b200 import cases
+    from oracle import constitutive as oc
+    for kind in ("mohr_coulomb", "matsuoka_nakai"):
+        weak = dict(cases.ELEMENT_LIBRARY[kind], cohesion=1.0, friction_angle=float(np.radians(25.0)),
+                    dilation_angle=float(np.radians(5.0)))          # mudstone-like: yields at the 16 MPa plateau
+        oc.EIGEN = "jacobi"
+        try:
+            eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 5, elements=("dislocation", weak))
+        finally:
+            oc.EIGEN = "lapack"
+        assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+        check_fields(eq, osim, ohist)
+        assert osim.mat.elems[1].Fvp.max() > 0, "load path never yields: test is vacuous"
 
 
 def test_time_steps_cavern_regular(sf):
