@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 8
+#define SIC_ABI_VERSION 9
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -325,6 +325,34 @@ int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts
 
 /* z = V-cycle(r) alone (tests, and users who bring their own Krylov method): reads levels[top].b, writes .x */
 int sic_mg_vcycle(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);
+
+/* ---- heat equation of the thermo-mechanical path (HeatEquation.py:304-343) ---------------- */
+/* Backward Euler, P1:  (M/dt + K + R) T = (M/dt) T_old + q  with  M = int rho cp phi_a phi_b dx,
+ * K = int k grad phi_a . grad phi_b dx, R = sum_robin int h phi_a phi_b ds, q_a = sum_neumann int q phi_a ds +
+ * sum_robin int h T_inf phi_a ds (HeatBC.py:283-334), Dirichlet nodes prescribed (HeatBC.py:247-281).  Matrix-free
+ * (exact P1 element matrices), Jacobi-preconditioned CG with device-resident scalars.  Replaces HeatDiffusion.solve. */
+typedef struct {
+  int32_t n_cells, cell_stride, n_nodes, n_tri;
+  const int32_t* conn;     /* [4][cell_stride]  as sic_problem_t */
+  const double* grad;      /* [12][cell_stride] */
+  const double* vol;       /* [cell_stride] */
+  const double* rho_cp;    /* [cell_stride] density * specific heat capacity (Material.density, .cp) */
+  const double* k;         /* [cell_stride] thermal conductivity (Material.k) */
+  const int32_t* tri;      /* [3][n_tri] boundary triangles */
+  const double* tri_area;  /* [n_tri] */
+  const double* tri_h;     /* [n_tri] Robin coefficient h of the facet's BC (0: none) */
+  const double* tri_q;     /* [n_tri] Neumann flux + h * T_inf of the facet's BCs at the current time */
+  const uint8_t* fixed;    /* [n_nodes] Dirichlet mask */
+} sic_heat_t;
+
+int64_t sic_heat_workspace_doubles(int n_nodes);
+/* One backward-Euler step.  T: in = initial guess with the prescribed values on fixed nodes, out = solution.
+ * ksp: rtol (relative to the residual of the zero guess, as PETSc's default), atol, max_it, check_every in;
+ * iterations, reason, rnorm out. */
+int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old, double* T, sic_ksp_t* ksp, double* work,
+                  void* stream);
+/* get_T_elems (HeatEquation.py:286-302): cell value = mean of the four nodal values */
+int sic_heat_cell_mean(const sic_heat_t* h, const double* T_nodes, double* T_cells, void* stream);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-free DFMA chains; returns achieved FLOP/s in *flops (used to record the FP64 peak) */

@@ -138,3 +138,94 @@ class Simulator_M(Simulator):
             if hasattr(output, "save_mesh"):
                 output.save_mesh()
         return self.history
+
+
+class Simulator_TM(Simulator):
+    """Thermo-mechanical simulator with the constructor / ``run()`` surface of the reference's Simulator_TM
+    (safeincave/Simulators.py:38-270): every step solves the heat equation, hands the cell temperatures to the
+    momentum equation (thermal strain + thermally activated creep) and iterates the momentum step.  As in the
+    reference: tolerance 1e-6, at most 20 iterations, NO dt-retry and an unconditional commit.  The
+    temperature never leaves the device."""
+
+    def __init__(self, eq_mom, eq_heat, t_control, outputs, compute_elastic_response: bool = True, verbose: bool = True):
+        self.eq_mom, self.eq_heat = eq_mom, eq_heat
+        self.t_control = t_control
+        self.outputs = outputs if outputs is not None else []
+        self.compute_elastic_response = compute_elastic_response
+        self.verbose = verbose
+        self.tol, self.maxiter = 1e-6, 20
+        self.history = []
+
+    def _save(self, t):
+        if not self.outputs:
+            return
+        eq = self.eq_mom
+        eq.compute_p_elems()
+        eq.compute_q_elems()
+        eq.compute_p_nodes()
+        eq.compute_q_nodes()
+        for output in self.outputs:
+            output.save_fields(t)
+
+    def initialize(self):
+        """Simulators.py:131-176."""
+        eq, heat, tc = self.eq_mom, self.eq_heat, self.t_control
+        for output in self.outputs:
+            output.initialize()
+        eq.set_T0(heat.get_T_elems())
+        eq.bc.update_dirichlet(tc.t)
+        eq.bc.update_neumann(tc.t)
+        if self.compute_elastic_response:
+            eq.solve_elastic_response()
+            eps = eq.compute_total_strain()
+            stress = eq.compute_elastic_stress(eps)
+        else:
+            eq.compute_total_strain()
+            stress = eq.sig
+        T_elems = heat.get_T_elems()
+        eq.set_T(T_elems)
+        eq.set_T0(T_elems)
+        eq.compute_eps_ne_rate(stress, tc.t)         # passes t, not dt (T7)
+        eq.update_eps_ne_rate_old()
+        self._save(0)
+
+    def step(self):
+        """One pass of the time loop body (Simulators.py:179-246)."""
+        eq, heat, tc = self.eq_mom, self.eq_heat, self.t_control
+        t0 = time.perf_counter()
+        tc.advance_time()
+        t, dt = tc.t, tc.dt
+        eq.bc.update_dirichlet(t)
+        eq.bc.update_neumann(t)
+        heat.solve(t, dt)                            # updates its own BCs (HeatEquation.py:306)
+        eq.set_T(heat.get_T_elems())
+        n_ne = len(eq.mat.elems_ne)
+        error, ite, ksp_its = 2 * self.tol, 0, 0
+        while error > self.tol and ite < self.maxiter:
+            eq.begin_iteration()
+            eq.solve(None, t, dt)
+            ksp_its += eq.ksp_log[-1][0]
+            want_err = not (eq.theta == 1.0 or n_ne == 0)
+            error = eq.newton_post(dt, with_error=want_err)
+            ite += 1
+        eq.commit(dt)
+        rec = dict(step=tc.step_counter, t=t, dt=dt, iterations=ite, error=float(error), ksp_iterations=ksp_its,
+                   heat_iterations=heat.ksp_log[-1][0], seconds=time.perf_counter() - t0)
+        self.history.append(rec)
+        return rec
+
+    def run(self):
+        tc = self.t_control
+        self.initialize()
+        while tc.keep_looping():
+            rec = self.step()
+            self._save(rec["t"])
+            if self.verbose and self.eq_mom.grid.mesh.comm.rank == 0:
+                print(f"{rec['step']:>6d} {tc.dt / tc.time_conversion:>10.4f} {rec['t'] / tc.time_conversion:>11.3f} / "
+                      f"{tc.t_final / tc.time_conversion:<10.3f} {rec['iterations']:>6d} {rec['error']:>12.4e} "
+                      f"{rec['ksp_iterations']:>8d} {rec['heat_iterations']:>5d}")
+                sys.stdout.flush()
+        for output in self.outputs:
+            if hasattr(output, "save_mesh"):
+                output.save_mesh()
+        return self.history

@@ -10,7 +10,8 @@ from .MaterialProps import (Material, NonElasticElement, Spring, Thermoelastic, 
                             MohrCoulombViscoplastic, MatsuokaNakaiViscoplastic)
 from .Grid import GridHandlerGMSH  # noqa: F401
 from .MomentumEquation import LinearMomentumBase, LinearMomentum, CellField  # noqa: F401
-from .Simulators import Simulator_M  # noqa: F401
+from .HeatEquation import HeatDiffusion  # noqa: F401
+from .Simulators import Simulator_M, Simulator_TM  # noqa: F401
 from .TimeHandler import TimeControllerBase, TimeController, TimeControllerParabolic  # noqa: F401
 from .Solver import KSP, PETSc  # noqa: F401
-from . import MomentumBC, Utils  # noqa: F401
+from . import HeatBC, MomentumBC, Utils  # noqa: F401

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 8
+SIC_ABI_VERSION = 9
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -35,6 +35,7 @@ EXPORTS = (
     "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
     "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle",
+    "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean",
 )
 
 
@@ -80,6 +81,12 @@ class SicMgOpts(ctypes.Structure):
 SIC_MG_MAX_LEVELS = 8
 
 
+class SicHeat(ctypes.Structure):
+    _fields_ = [("n_cells", c_int32), ("cell_stride", c_int32), ("n_nodes", c_int32), ("n_tri", c_int32),
+                ("conn", c_void_p), ("grad", c_void_p), ("vol", c_void_p), ("rho_cp", c_void_p), ("k", c_void_p),
+                ("tri", c_void_p), ("tri_area", c_void_p), ("tri_h", c_void_p), ("tri_q", c_void_p), ("fixed", c_void_p)]
+
+
 class SicHalo(ctypes.Structure):
     _fields_ = [("n_ranks", c_int32), ("rank", c_int32), ("n_peers", c_int32), ("n_shared_total", c_int32),
                 ("peer", c_int32 * SIC_MAX_PEERS), ("peer_off", c_int32 * (SIC_MAX_PEERS + 1)),
@@ -119,6 +126,11 @@ def declare(lib, single_gpu_only=False):
     lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
+    PHT = POINTER(SicHeat)
+    lib.sic_heat_workspace_doubles.argtypes = [c_int]
+    lib.sic_heat_workspace_doubles.restype = c_int64
+    lib.sic_heat_step.argtypes = [PHT, c_double, c_void_p, c_void_p, POINTER(SicKsp), c_void_p, c_void_p]
+    lib.sic_heat_cell_mean.argtypes = [PHT, c_void_p, c_void_p, c_void_p]
     if not single_gpu_only:
         lib.sic_comm_unique_id.argtypes = [c_void_p]
         lib.sic_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]

@@ -20,6 +20,7 @@ UNITS = [
     ("fem.cu", []),
     ("solver.cu", []),
     ("mg.cu", []),
+    ("heat.cu", []),
     ("comm.cu", []),
 ]
 

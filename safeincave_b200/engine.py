@@ -82,15 +82,16 @@ class ElemState:
 
 
 class Engine:
-    def __init__(self, coords, cells, device="cuda", operator_only=False):
+    def __init__(self, coords, cells, device="cuda", operator_only=False, geometry_only=False):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SicError("safeincave_b200 needs a CUDA device (no CPU fallback)")
-        self._setup(coords, cells, device, operator_only)
+        self._setup(coords, cells, device, operator_only, geometry_only)
 
-    def _setup(self, coords, cells, device, operator_only=False):
+    def _setup(self, coords, cells, device, operator_only=False, geometry_only=False):
         """Allocate and fill every buffer of sic_problem_t (torch index plumbing, once per mesh).
-        operator_only: a coarse multigrid level -- mesh, scatter plan and C_T, no constitutive state."""
+        operator_only: a coarse multigrid level -- mesh, scatter plan and C_T, no constitutive state.
+        geometry_only: connectivity, gradients and volumes only (the heat equation's view of the mesh)."""
         self.device = torch.device(device)
         coords = torch.as_tensor(coords, dtype=torch.float64).to(self.device).contiguous()
         cells = torch.as_tensor(cells).to(self.device, dtype=torch.int64).contiguous()
@@ -108,6 +109,10 @@ class Engine:
         self.grad[:, :self.N] = grad.reshape(self.N, 12).t()
         self.vol = torch.zeros(ns, dtype=torch.float64, device=dev)
         self.vol[:self.N] = vol
+        self.launches = 0
+        if geometry_only:
+            self.operator_only = True
+            return
         # the same geometry, tiled for the operator kernel (sic_geom_tile_t: grad[12][128], vol[128], conn[4][128])
         nt = ns // 128
         self.geom_tiles = torch.zeros((nt, 1920), dtype=torch.float64, device=dev)
