@@ -91,6 +91,12 @@ class LinearMomentum(LinearMomentumBase):
         self.eps_tot = CellField(eng, eng.eps)
         self._nodes_vol = None
         self.dist = None                    # safeincave_b200.distributed.DistContext when partitioned
+        # function-space tokens and the elastic-tangent Function the reference's example hooks touch
+        # (examples/mechanics/1_triaxial/main.py:13-24); see compat.py
+        from .compat import Space
+        self.DG0_1, self.DG0_3x3 = Space(eng.N, 1, "DG0_1"), Space(eng.N, 9, "DG0_3x3")
+        self.DG0_6x6, self.V = Space(eng.N, 36, "DG0_6x6"), Space(eng.M, 3, "V")
+        self._C_fun = None
         self.mg = None                      # multigrid.Multigrid, built on the first solve with PC type "mg"
         self.mg_options = {}                # nu, coarse_its, smooth_lo, coarse_lo, safety, power_its
 
@@ -108,6 +114,16 @@ class LinearMomentum(LinearMomentumBase):
     def run_after_solve(self):
         """Hook called after each linear solve (MomentumEquation.py:510-518)."""
         pass
+
+    @property
+    def C(self):
+        """The DG0 6x6 Function the reference fills in ``initialize()`` (``self.C.x.array[:] = flatten(mat.C)``,
+        MomentumEquation.py:785-797).  Kept only so that user overrides of ``initialize`` keep working: the kernels
+        read the elastic tangent from the material table."""
+        if self._C_fun is None:
+            from .compat import Function
+            self._C_fun = Function(self.DG0_6x6, "C")
+        return self._C_fun
 
     def set_T(self, T):
         self.engine.T[:self.engine.N] = to.as_tensor(T).to(self.engine.device, dtype=to.float64)

@@ -14,4 +14,5 @@ from .HeatEquation import HeatDiffusion  # noqa: F401
 from .Simulators import Simulator_M, Simulator_TM  # noqa: F401
 from .TimeHandler import TimeControllerBase, TimeController, TimeControllerParabolic  # noqa: F401
 from .Solver import KSP, PETSc  # noqa: F401
+from .OutputHandler import SaveFields  # noqa: F401
 from . import HeatBC, MomentumBC, Utils  # noqa: F401
