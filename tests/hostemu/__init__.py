@@ -79,7 +79,7 @@ def build(force=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"hostemu: compiling {name} failed:\n{out.decode()[-6000:]}")
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-lm"])
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-lm", "-lpthread"])
     return LIB
 
 
@@ -92,6 +92,12 @@ def load():
     if _emu is None:
         lib = ctypes.CDLL(build())
         L.declare(lib, single_gpu_only=True)
+        PH = ctypes.POINTER(L.SicHalo)
+        lib.sic_exchange.argtypes = [PH, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.sic_halo_sum.argtypes = [PH, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.sic_allreduce_sum.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.sic_emu_make_comm.argtypes = [ctypes.c_int, ctypes.c_int]
+        lib.sic_emu_make_comm.restype = ctypes.c_void_p
         _emu = lib
     return _emu
 

@@ -28,7 +28,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local   /* one block at a time PER emulated rank (= host thread) */
 #define __align__(n) alignas(n)
 #define __constant__ static
 
@@ -36,7 +36,7 @@ struct dim3 { unsigned x = 1, y = 1, z = 1; };
 struct uint2 { unsigned x, y; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 
-extern dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static const int warpSize = 32;
 
 namespace sic_emu {

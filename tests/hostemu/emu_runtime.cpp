@@ -6,7 +6,7 @@
 #include "cuda_emu.h"
 #include "safeincave_cuda.h"
 
-dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 extern "C" void sic_emu_switch(void** save_sp, void* load_sp);
 asm(R"(
@@ -36,12 +36,12 @@ namespace sic_emu {
 
 static const size_t kStack = 512 * 1024;
 struct Fiber { char* stack = nullptr; void* sp = nullptr; bool done = true; int ncoll = 0; };
-static std::vector<Fiber> g_fib;
-static std::vector<double> g_slots[2];
-static void* g_sched_sp = nullptr;
-static int g_cur = -1;              // fiber index, -1: direct mode
-static bool g_fiber_mode = false;
-static const std::function<void()>* g_body = nullptr;
+static thread_local std::vector<Fiber> g_fib;
+static thread_local std::vector<double> g_slots[2];
+static thread_local void* g_sched_sp = nullptr;
+static thread_local int g_cur = -1;              // fiber index
+static thread_local bool g_fiber_mode = false;
+static thread_local const std::function<void()>* g_body = nullptr;
 
 static void trampoline() {
   (*g_body)();
@@ -112,9 +112,95 @@ void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
 
 }  // namespace sic_emu
 
-// ---- multi-GPU entry points: the emulation is single-"device" ----------------------------------------
+// ---- multi-GPU entry points: every emulated rank is a host thread; they meet here ------------------------
+// sic_exchange / sic_halo_sum / sic_allreduce_sum with the semantics of csrc/comm.cu: halo sum of the interface
+// nodes (every rank first PUBLISHES what it sends to each neighbour, then everybody adds what it received) and
+// sums of scalars / vectors over the ranks in rank order (identical bits on every rank).
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+
+namespace {
+struct RankSlot {
+  std::vector<std::vector<double>> send;   // per neighbour (in the order of sic_halo_t.peer)
+  std::vector<int> peer;
+  std::vector<double> scal;
+  const double* big = nullptr;             // sic_allreduce_sum operand
+};
+std::mutex g_mu;
+std::condition_variable g_cv;
+int g_waiting = 0;
+unsigned long long g_generation = 0;
+RankSlot g_rank[SIC_MAX_PEERS];
+
+// all `n` ranks arrive, or -1 after 120 s (a rank died: its thread raised in Python)
+int rank_barrier(int n) {
+  std::unique_lock<std::mutex> lk(g_mu);
+  const unsigned long long gen = g_generation;
+  if (++g_waiting == n) { g_waiting = 0; ++g_generation; g_cv.notify_all(); return 0; }
+  if (!g_cv.wait_for(lk, std::chrono::seconds(120), [&] { return g_generation != gen; })) { --g_waiting; return -1; }
+  return 0;
+}
+struct EmuComm { int rank, n_ranks; };
+}  // namespace
+
+extern int sic_fail(const char* msg);
+
 extern "C" {
-int sic_exchange(const sic_halo_t* h, double*, int, double*, int, void*) { return h ? -1 : 0; }
-int sic_halo_sum(const sic_halo_t* h, double*, int, void*) { return h ? -1 : 0; }
+void* sic_emu_make_comm(int rank, int n_ranks) { return new EmuComm{rank, n_ranks}; }
+
+int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double* scal, int n_scal, void*) {
+  if (!h || h->n_ranks <= 1) return 0;
+  if (h->n_ranks > SIC_MAX_PEERS) return sic_fail("emulated sic_exchange: too many ranks");
+  RankSlot& me = g_rank[h->rank];
+  me.send.assign(h->n_peers, {});
+  me.peer.assign(h->peer, h->peer + h->n_peers);
+  if (ncomp > 0) {
+    for (int p = 0; p < h->n_peers; ++p) {
+      const int off = h->peer_off[p], cnt = h->peer_off[p + 1] - off;
+      me.send[p].resize((size_t)cnt * ncomp);
+      for (int k = 0; k < cnt; ++k)
+        for (int c = 0; c < ncomp; ++c) me.send[p][(size_t)k * ncomp + c] = vec[(size_t)h->idx[off + k] * ncomp + c];
+    }
+  }
+  me.scal.assign(scal, scal + (n_scal > 0 ? n_scal : 0));
+  if (rank_barrier(h->n_ranks)) return sic_fail("emulated sic_exchange: a rank did not arrive");
+  if (ncomp > 0) {
+    for (int p = 0; p < h->n_peers; ++p) {
+      const RankSlot& q = g_rank[h->peer[p]];
+      int back = -1;
+      for (size_t j = 0; j < q.peer.size(); ++j) if (q.peer[j] == h->rank) back = (int)j;
+      const int off = h->peer_off[p], cnt = h->peer_off[p + 1] - off;
+      if (back < 0 || q.send[back].size() != (size_t)cnt * ncomp) return sic_fail("emulated sic_exchange: halo plans of two ranks disagree");
+      for (int k = 0; k < cnt; ++k)
+        for (int c = 0; c < ncomp; ++c) vec[(size_t)h->idx[off + k] * ncomp + c] += q.send[back][(size_t)k * ncomp + c];
+    }
+  }
+  for (int j = 0; j < n_scal; ++j) {
+    double acc = 0.0;
+    for (int r = 0; r < h->n_ranks; ++r) acc += g_rank[r].scal[j];
+    scal[j] = acc;
+  }
+  if (rank_barrier(h->n_ranks)) return sic_fail("emulated sic_exchange: a rank did not arrive");
+  return 0;
+}
+
+int sic_halo_sum(const sic_halo_t* h, double* vec, int ncomp, void* st) { return sic_exchange(h, vec, ncomp, nullptr, 0, st); }
+
+int sic_allreduce_sum(void* comm, double* buf, int count, void*) {
+  if (!comm || !buf) return sic_fail("emulated sic_allreduce_sum: null");
+  const EmuComm* c = (const EmuComm*)comm;
+  if (c->n_ranks <= 1) return 0;
+  g_rank[c->rank].big = buf;
+  if (rank_barrier(c->n_ranks)) return sic_fail("emulated sic_allreduce_sum: a rank did not arrive");
+  std::vector<double> tot((size_t)count, 0.0);
+  for (int r = 0; r < c->n_ranks; ++r)
+    for (int k = 0; k < count; ++k) tot[k] += g_rank[r].big[k];
+  if (rank_barrier(c->n_ranks)) return sic_fail("emulated sic_allreduce_sum: a rank did not arrive");
+  for (int k = 0; k < count; ++k) buf[k] = tot[k];
+  if (rank_barrier(c->n_ranks)) return sic_fail("emulated sic_allreduce_sum: a rank did not arrive");
+  return 0;
+}
+
 int sic_p2p_error(void*) { return 0; }
 }

@@ -7,6 +7,7 @@ files compile UNMODIFIED IN MEANING as C++ against tests/hostemu/cuda_emu.h:
   asm volatile("ld.global[.nc].{f64,s32} %0, [%1];" : "=d|r"(dst) : "l"(ptr));   ->  dst = *(ptr);
   asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(ptr));  ->  two 32-bit loads
   #include "ebe_tma.cuh"   ->  #include "fem.cuh"   (the TMA/mbarrier variant is compiled out: SIC_EBE_IMPL == 3)
+  static T* g_xxx ...      ->  static thread_local T* g_xxx   (host-side singletons: one per emulated rank = host thread)
 """
 import re
 
@@ -103,6 +104,8 @@ def translate(src: str) -> str:
                  % (m.group(3), m.group(1), m.group(2)), s)
     s = _LD1.sub(lambda m: "%s = *(%s);" % (m.group(1), m.group(2)), s)
     s = translate_launches(s)
+    # host-side singletons of the drivers (pinned mirrors of the device scalars, timing events): one per emulated rank
+    s = re.sub(r"^static (\w+\*? g_\w+)", r"static thread_local \1", s, flags=re.M)
     if "asm volatile" in s or "<<<" in s:
         raise ValueError("untranslated CUDA construct left in the source")
     return s

@@ -1,0 +1,65 @@
+"""The multi-GPU code paths of the library (partition, halo plans, owner-weighted dot products, the `multi` branches
+of solver.cu) executed by several emulated RANKS -- one host thread each -- that meet in the emulated sic_exchange
+(tests/hostemu/ranks.py).  The partitioned run must reproduce the single-rank run: fields to 1e-8 and the same
+Newton history, as scripts/dist_check.py checks on real GPUs."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def sf():
+    import safeincave_b200 as sf
+    from tests.hostemu import EmuEngine
+    old = sf.LinearMomentum.engine_cls
+    sf.LinearMomentum.engine_cls = EmuEngine
+    yield sf
+    sf.LinearMomentum.engine_cls = old
+
+
+def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None):
+    from safeincave_b200 import cases, distributed
+    from safeincave_b200.mesh import TetMesh, morton_order, red_refine
+    from tests.hostemu.ranks import run_ranks
+    tm = TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz"))
+    for _ in range(levels):
+        tm = red_refine(tm)
+    tm = morton_order(tm)
+    gg = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    case = cases.triaxial_case(gg, n_steps=n_steps, ksp_override=ksp)
+    eq1, sim1 = cases.build(case, gg)
+    if setup:
+        setup(eq1, gg, None)
+    sim1.verbose = False
+    hist1 = sim1.run()
+
+    def body(ctx):
+        grid, part = distributed.partition_grid(ctx, tm)
+        eq, sim = cases.build(case, grid, part=part, ctx=ctx)
+        if setup:
+            setup(eq, grid, part)
+        sim.verbose = False
+        hist = sim.run()
+        ln = part.local_nodes
+        c0, c1 = part.cell_range
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        return dict(e_u=rel(eq.X, eq1.X[ln]), e_s=rel(eq.engine.sig[:, :eq.engine.N], eq1.engine.sig[:, c0:c1]),
+                    e_c=rel(eq.engine.elems[1].eps_old[:, :eq.engine.N], eq1.engine.elems[1].eps_old[:, c0:c1]),
+                    newton=[h["iterations"] for h in hist], ksp=[h["ksp_iterations"] for h in hist],
+                    peers=part.peers, n=eq.engine.N)
+
+    res = run_ranks(world, body)
+    assert sum(r["n"] for r in res) == tm.n_cells
+    for r in res:
+        assert r["newton"] == [h["iterations"] for h in hist1]
+        assert r["e_u"] < 1e-8 and r["e_s"] < 1e-8 and r["e_c"] < 1e-8, r
+    return res, hist1
+
+
+@pytest.mark.parametrize("world,ksp", [(2, "cg"), (3, "cg"), (2, "bicg")])
+def test_partitioned_block_jacobi_krylov_matches_single_rank(sf, world, ksp):
+    res, hist1 = partitioned_vs_single(sf, world, ksp)
+    assert all(len(r["peers"]) >= 1 for r in res)
