@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 9
+#define SIC_ABI_VERSION 10
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -302,6 +302,9 @@ typedef struct {
   /* work vectors, [3 n_nodes] each */
   double *x, *b, *r, *d, *t;
   double* pv;              /* [3 n_nodes] or NULL: power-iteration vector kept BETWEEN calls of sic_mg_setup (warm start) */
+  const sic_halo_t* halo;  /* FINEST level only, several GPUs: its cells are partitioned exactly as for sic_ksp_solve; all
+                              coarser levels are replicated on every rank.  The finest level's parent_a/b, rst_* then index
+                              the coarse level globally and `children` holds -1 for cells of other ranks.  NULL: one GPU */
 } sic_mg_level_t;
 
 typedef struct {
@@ -319,7 +322,7 @@ typedef struct {
 int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes);   /* of the FINEST level; one workspace serves all calls */
 int sic_mg_setup(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);
 
-/* CG preconditioned by one V-cycle, same contract as sic_ksp_solve (ksp->method is ignored; single GPU). */
+/* CG preconditioned by one V-cycle, same contract as sic_ksp_solve (ksp->method is ignored). */
 int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, sic_ksp_t* ksp,
                  const double* b_ext, double* x, double* work, void* stream);
 

@@ -196,13 +196,13 @@ class LinearMomentum(LinearMomentumBase):
     def _linear_solve_mg(self, x, rtol, atol, max_it):
         """CG preconditioned by a geometric-multigrid V-cycle on the grid's refinement hierarchy (csrc/mg.cu)."""
         eng, ksp = self.engine, self.solver
-        if self.dist is not None and self.dist.world > 1:
-            raise NotImplementedError("the multigrid preconditioner is single-GPU in this version")
         if ksp.getType().lower() != "cg":
             raise NotImplementedError("PC type 'mg' is implemented for KSP type 'cg'")
         if self.mg is None:
             from .multigrid import Multigrid
-            self.mg = Multigrid(eng, self.grid.hierarchy, **self.mg_options)
+            part = getattr(self.grid, "partition", None) if (self.dist is not None and self.dist.world > 1) else None
+            self.mg = Multigrid(eng, self.grid.hierarchy, part=part, coarse_fixed=self._coarse_dirichlet_mask,
+                                **self.mg_options)
         self.mg.setup(self.fixed, self.dinv)
         res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
                             check_every=ksp.mg_check_every, guess_nonzero=ksp.initial_guess_nonzero,
@@ -210,6 +210,15 @@ class LinearMomentum(LinearMomentumBase):
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
         return res
+
+    def _coarse_dirichlet_mask(self, level, mesh):
+        """Dirichlet mask (3 M,) of a coarse mesh of the hierarchy, from the boundary conditions' facet tags
+        (MomentumBC.py:231-245 applied to that mesh)."""
+        mask = np.zeros((mesh.n_nodes, 3), dtype=np.uint8)
+        for bc in self.bc.dirichlet_boundaries:
+            tag = self.grid.get_boundary_tag(bc.boundary_name)
+            mask[np.unique(mesh.tris[mesh.tri_tags == tag]), int(bc.component)] = 1
+        return mask.reshape(-1)
 
     def solve_elastic_response(self):
         """MomentumEquation.py:892-923."""

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 9
+SIC_ABI_VERSION = 10
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -70,7 +70,8 @@ class SicMgLevel(ctypes.Structure):
     _fields_ = [("prob", SicProblem), ("fixed", c_void_p), ("dinv", c_void_p), ("lambda_max", c_double),
                 ("parent_a", c_void_p), ("parent_b", c_void_p), ("rst_ptr", c_void_p), ("rst_idx", c_void_p),
                 ("children", c_void_p),
-                ("x", c_void_p), ("b", c_void_p), ("r", c_void_p), ("d", c_void_p), ("t", c_void_p), ("pv", c_void_p)]
+                ("x", c_void_p), ("b", c_void_p), ("r", c_void_p), ("d", c_void_p), ("t", c_void_p), ("pv", c_void_p),
+                ("halo", c_void_p)]
 
 
 class SicMgOpts(ctypes.Structure):

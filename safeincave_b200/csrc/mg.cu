@@ -17,6 +17,13 @@
 // prolongation reads the two parents of each fine node.  Dirichlet dofs are kept at zero on every level.
 // The outer CG keeps its scalars on the device (as solver.cu does) and the host looks at them every
 // `check_every` iterations; every kernel of the cycle is a no-op once the `done` flag is up.
+//
+// Several GPUs (levels[top].halo != NULL): the FINEST level is partitioned by cells exactly as in solver.cu
+// (interface nodes duplicated, vectors kept consistent, operator results completed by sic_exchange over NVLink,
+// dot products with owner weights + scalar exchange); every COARSER level is replicated on every rank.  The
+// finest level carries 7/8 of the work of a cycle, the replicated part costs each rank 1/7 of one fine-level
+// sweep, and the only extra traffic is one all-reduce of the first coarse right-hand side per cycle (and of
+// the first coarse C_T per tangent).  Transfers of the finest level index the coarse level GLOBALLY.
 #include <math.h>
 #include <string.h>
 
@@ -27,6 +34,7 @@ namespace sic {
 struct MgScal {
   double rz, pq, rr, rr0, rr_ref, alpha, beta, tol2;
   double pw;            // power iteration: ||Dinv K v||^2 with ||v|| = 1
+  double sum[2];        // this rank's partial sum of the running reduction (summed over ranks by sic_exchange)
   int done, iters, nanflag, reason;
 };
 static_assert(sizeof(MgScal) <= 64 * sizeof(double), "MgScal must fit the reserved workspace header");
@@ -34,11 +42,16 @@ static_assert(sizeof(MgScal) <= 64 * sizeof(double), "MgScal must fit the reserv
 #define SIC_MG_HEADER 64    /* doubles reserved for MgScal */
 #define SIC_MG_COUNTERS 8   /* doubles reserved for the ticket counters of grid_reduce */
 
-enum { MG_OP_REF = 0, MG_OP_INIT_RR, MG_OP_INIT_RZ, MG_OP_RR, MG_OP_RZ, MG_OP_PW };
+enum { MG_OP_REF = 0, MG_OP_INIT_RR, MG_OP_INIT_RZ, MG_OP_RR, MG_OP_RZ, MG_OP_PW, MG_OP_PQ };
 
 struct MgFin {   // what the last block of a reducing kernel does with the grid total
-  MgScal* S; int op; double rtol, atol; int guess;
+  MgScal* S; int op; double rtol, atol; int guess; int multi;
+  // one GPU: run the scalar recurrence at once; several: park the partial sum, k_mg_scal runs it after the exchange
   __device__ __forceinline__ void run(double tot) const {
+    if (multi) { S->sum[0] = tot; return; }
+    step(tot);
+  }
+  __device__ __forceinline__ void step(double tot) const {
     switch (op) {
       case MG_OP_REF: S->rr_ref = tot; break;
       case MG_OP_INIT_RR: {
@@ -59,9 +72,16 @@ struct MgFin {   // what the last block of a reducing kernel does with the grid 
         break;
       case MG_OP_RZ: S->beta = tot / S->rz; S->rz = tot; break;
       case MG_OP_PW: S->pw = tot; break;
+      case MG_OP_PQ: S->pq = tot; S->alpha = S->rz / tot; break;
     }
   }
 };
+
+// several GPUs: the scalar recurrence after the partial sums have been added over the ranks
+__global__ void k_mg_scal(MgFin fin, int skip_if_done) {
+  if (skip_if_done && fin.S->done) return;
+  fin.step(fin.S->sum[0]);
+}
 
 // ---- operator (the kernel of fem.cuh) ---------------------------------------------------------------
 __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, const double* __restrict__ x,
@@ -79,8 +99,8 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe_dot(sic_problem_t 
   block_partials<1, SIC_TILE_CELLS>(v, partials);
 }
 
-__global__ void __launch_bounds__(1024) k_mg_sum_pq(const double* __restrict__ partials, int n, MgScal* S) {
-  if (S->done) return;
+__global__ void __launch_bounds__(1024) k_mg_sum_pq(const double* __restrict__ partials, int n, MgFin fin) {
+  if (fin.S->done) return;
   __shared__ double sh[32];
   double a = 0.0;
   for (int k = threadIdx.x; k < n; k += 1024) a += partials[k];
@@ -91,8 +111,7 @@ __global__ void __launch_bounds__(1024) k_mg_sum_pq(const double* __restrict__ p
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int k = 0; k < 32; ++k) tot += sh[k];
-    S->pq = tot;
-    S->alpha = S->rz / tot;
+    fin.run(tot);       // MG_OP_PQ
   }
 }
 
@@ -110,16 +129,18 @@ __global__ void k_mg_zero_free(int nd, double* __restrict__ z, const double* __r
   if (d < nd) z[d] = fixed[d] ? x[d] : 0.0;
 }
 
-// sum a.b over all dofs
+// sum a.b over all dofs (w: owner weights on several GPUs, every node counted once; NULL on one)
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int n_nodes, const double* __restrict__ a,
-                                                           const double* __restrict__ b, MgFin fin, int skip_if_done,
+                                                           const double* __restrict__ b, const double* __restrict__ w,
+                                                           MgFin fin, int skip_if_done,
                                                            double* __restrict__ partials, unsigned* counter) {
   if (skip_if_done && fin.S->done) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
   if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v[0] += a[3 * (size_t)n + j] * b[3 * (size_t)n + j];
+    for (int j = 0; j < 3; ++j) v[0] += wn * a[3 * (size_t)n + j] * b[3 * (size_t)n + j];
   }
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
 }
@@ -128,13 +149,15 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int n_nodes, const d
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int n_nodes, double* __restrict__ x,
                                                                  double* __restrict__ r, const double* __restrict__ p,
                                                                  const double* __restrict__ q,
-                                                                 const uint8_t* __restrict__ fixed, MgFin fin,
+                                                                 const uint8_t* __restrict__ fixed,
+                                                                 const double* __restrict__ w, MgFin fin,
                                                                  double* __restrict__ partials, unsigned* counter) {
   if (fin.S->done) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const double alpha = fin.S->alpha;
   double v[1] = {0.0};
   if (n < n_nodes) {
+    const double wn = w ? w[n] : 1.0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const size_t d = 3 * (size_t)n + j;
@@ -144,7 +167,7 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int n_nodes, d
         rn = r[d] - alpha * q[d];
       }
       r[d] = rn;
-      v[0] += rn * rn;
+      v[0] += wn * rn * rn;
     }
   }
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
@@ -238,15 +261,18 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_resid(int nd, double* __
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_restrict(int n_coarse, const int32_t* __restrict__ ptr,
                                                                 const int32_t* __restrict__ idx,
                                                                 const double* __restrict__ r_f, double* __restrict__ b_c,
-                                                                const uint8_t* __restrict__ fixed_c, const int* done) {
+                                                                const uint8_t* __restrict__ fixed_c,
+                                                                const double* __restrict__ w_f, const int* done) {
   if (*done) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_coarse) return;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   const int e1 = __ldg(ptr + c + 1);
   for (int e = __ldg(ptr + c); e < e1; ++e) {
-    const size_t f = 3 * (size_t)__ldg(idx + e);
-    s0 += r_f[f]; s1 += r_f[f + 1]; s2 += r_f[f + 2];
+    const int fn = __ldg(idx + e);
+    const size_t f = 3 * (size_t)fn;
+    const double wn = w_f ? w_f[fn] : 1.0;      // several GPUs: a fine node is summed by its owner only
+    s0 += wn * r_f[f]; s1 += wn * r_f[f + 1]; s2 += wn * r_f[f + 2];
   }
   const size_t k = 3 * (size_t)c;
   b_c[k] = fixed_c[k] ? 0.0 : 0.5 * s0;
@@ -280,7 +306,8 @@ __global__ void __launch_bounds__(128) k_mg_ct_coarsen(int n_coarse, const int32
   for (int rc = 0; rc < 36; ++rc) {
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += __ldg(CT_f + SIC_CT_INDEX(rc, ch[j]));
+    for (int j = 0; j < 8; ++j)      // a child held by another rank is -1 here: partial sums, all-reduced by the caller
+      if (ch[j] >= 0) s += __ldg(CT_f + SIC_CT_INDEX(rc, ch[j]));
     CT_c[SIC_CT_INDEX(rc, c)] = 0.125 * s;
   }
 }
@@ -300,11 +327,13 @@ __global__ void k_mg_pw_init(int nd, double* __restrict__ v, double* __restrict_
 // w = Dinv t (t = K v), fixed dofs 0, stored over t's companion vector w ; sums w.w
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_pw_step(int n_nodes, const double* __restrict__ t,
                                                                double* __restrict__ w, const double* __restrict__ dinv,
-                                                               const uint8_t* __restrict__ fixed, MgFin fin,
+                                                               const uint8_t* __restrict__ fixed,
+                                                               const double* __restrict__ ow, MgFin fin,
                                                                double* __restrict__ partials, unsigned* counter) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
   if (n < n_nodes) {
+    const double own = ow ? ow[n] : 1.0;
     double tn[3], zn[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) tn[j] = fixed[3 * (size_t)n + j] ? 0.0 : t[3 * (size_t)n + j];
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_pw_step(int n_nodes, con
       const size_t k = 3 * (size_t)n + j;
       const double wn = fixed[k] ? 0.0 : zn[j];
       w[k] = wn;
-      v[0] += wn * wn;
+      v[0] += own * wn * wn;
     }
   }
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
@@ -347,12 +376,26 @@ static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_
     if (L.prob.abi_version != SIC_ABI_VERSION) return sic_fail("multigrid: sic_problem_t.abi_version mismatch");
     if (!L.fixed || !L.dinv || !L.x || !L.b || !L.r || !L.d || !L.t || !L.prob.CT)
       return sic_fail("multigrid: level with a null buffer");
+    const bool part = L.halo && L.halo->n_ranks > 1;
+    if (part && l != n_levels - 1) return sic_fail("multigrid: only the finest level may be partitioned (coarser ones are replicated)");
+    if (part && (!L.halo->owner_w || !L.halo->comm)) return sic_fail("multigrid: halo without owner weights / communicator");
+    if (part && n_levels < 2) return sic_fail("multigrid: a partitioned run needs at least two levels");
     if (l > 0) {
       if (!L.parent_a || !L.parent_b || !L.rst_ptr || !L.rst_idx || !L.children)
         return sic_fail("multigrid: level without transfer tables");
-      if (L.prob.n_cells != 8 * lv[l - 1].prob.n_cells) return sic_fail("multigrid: levels are not nested 1:8");
+      if (!part && L.prob.n_cells != 8 * lv[l - 1].prob.n_cells) return sic_fail("multigrid: levels are not nested 1:8");
     }
   }
+  return 0;
+}
+
+static inline const sic_halo_t* mg_halo(const sic_mg_level_t& L) { return (L.halo && L.halo->n_ranks > 1) ? L.halo : nullptr; }
+
+// t = K x on level L (t must be zero on entry); several GPUs: completed on the interface nodes by the halo sum
+static int mg_apply(const sic_mg_level_t& L, const double* x, double* t, const int* done, cudaStream_t st) {
+  const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+  if (cb > 0) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, x, t, done);
+  if (const sic_halo_t* h = mg_halo(L)) return sic_exchange(h, t, 3, nullptr, 0, (void*)st);
   return 0;
 }
 
@@ -384,15 +427,17 @@ static int mg_host_mirror() {
 static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, double lo, int zero_guess, const int* done,
                         cudaStream_t st) {
   const int nn = L.prob.n_nodes, nc = L.prob.n_cells;
-  const int nb = mg_blocks(nn, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
+  const int nb = mg_blocks(nn, SIC_VEC_THREADS);
+  (void)nc;
   const double lmax = L.lambda_max, lmin = lo * lmax;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double rho = 1.0 / sigma;
-  if (!zero_guess) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.x, L.t, done);   // t = K x (t is 0 on entry)
+  if (!zero_guess)
+    if (int rc = mg_apply(L, L.x, L.t, done, st)) return rc;                         // t = K x (t is 0 on entry)
   k_mg_cheb_first<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta, zero_guess,
                                                   done);
   for (int k = 1; k < its; ++k) {
-    k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    if (int rc = mg_apply(L, L.d, L.t, done, st)) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     k_mg_cheb_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
                                                    2.0 * rho_new / delta, done);
@@ -412,12 +457,17 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     const double* b = (l == top) ? b_top : L.b;
     if (int rc = mg_chebyshev(L, b, o->nu, o->smooth_lo, 1, done, st)) return rc;
     const int nn = L.prob.n_nodes, nd = 3 * nn, cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+    const sic_halo_t* h = mg_halo(L);
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[0], st);
-    k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    if (cb > 0) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
+    if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
     k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
+    // several GPUs: every fine node is restricted by its owner only, then the (replicated) coarse right-hand side is
+    // completed by one all-reduce over NVLink
     k_mg_restrict<<<mg_blocks(C.prob.n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(
-        C.prob.n_nodes, L.rst_ptr, L.rst_idx, L.r, C.b, C.fixed, done);
+        C.prob.n_nodes, L.rst_ptr, L.rst_idx, L.r, C.b, C.fixed, h ? h->owner_w : nullptr, done);
+    if (h) if (int rc = sic_allreduce_sum(h->comm, C.b, 3 * C.prob.n_nodes, (void*)st)) return rc;
   }
   {
     const sic_mg_level_t& L = lv[0];
@@ -443,18 +493,27 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (o->power_its_warm < 0) return sic_fail("sic_mg_setup: power_its_warm must be >= 0");
   if (int rc = mg_host_mirror()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // 1. Galerkin coarse tangents, fine to coarse
+  // 1. Galerkin coarse tangents, fine to coarse (several GPUs: every rank sums the children it holds, then one
+  //    all-reduce completes the first coarse level; the levels below are computed redundantly)
   for (int l = n_levels - 1; l >= 1; --l) {
     const int ncoarse = lv[l - 1].prob.n_cells;
     if (ncoarse > 0)
       k_mg_ct_coarsen<<<mg_blocks(ncoarse, 128), 128, 0, st>>>(ncoarse, lv[l].children, lv[l].prob.CT, lv[l - 1].prob.CT);
+    if (int rc = sic_check_launch("k_mg_ct_coarsen")) return rc;
+    if (const sic_halo_t* h = mg_halo(lv[l])) {
+      const int64_t cnt = 36 * (int64_t)lv[l - 1].prob.cell_stride;
+      if (cnt > 2147483647) return sic_fail("sic_mg_setup: coarse C_T too large for one all-reduce");
+      if (int rc = sic_allreduce_sum(h->comm, lv[l - 1].prob.CT, (int)cnt, stream)) return rc;
+    }
   }
-  if (int rc = sic_check_launch("k_mg_ct_coarsen")) return rc;
   MgWork W = mg_work(work);
   // 2. block-Jacobi blocks and 3. lambda_max(Dinv K) by power iteration, level by level (x: v, d: w, t: K v)
   for (int l = 0; l < n_levels; ++l) {
     sic_mg_level_t& L = lv[l];
-    if (int rc = sic_block_jacobi(&L.prob, L.dinv, L.fixed, nullptr, stream)) return rc;
+    const sic_halo_t* h = mg_halo(L);
+    const int multi = h ? 1 : 0;
+    const double* ow = h ? h->owner_w : nullptr;
+    if (int rc = sic_block_jacobi(&L.prob, L.dinv, L.fixed, h, stream)) return rc;
     if (o->power_its <= 0) {
       if (!(L.lambda_max > 0.0)) return sic_fail("sic_mg_setup: power_its = 0 needs lambda_max from an earlier call");
       continue;
@@ -472,11 +531,16 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     const int its = warm ? o->power_its_warm : o->power_its;
     if (!warm) k_mg_pw_init<<<db, SIC_VEC_THREADS, 0, st>>>(nd, v, L.t, L.fixed, 1.0);
     else if (int rc = sic_check_cuda(cudaMemsetAsync(L.t, 0, sizeof(double) * nd, st), "memset t")) return rc;
+    (void)cb;
+    const MgFin pw{W.S, MG_OP_PW, 0.0, 0.0, 0, multi};
     for (int it = 0; it < its; ++it) {
-      k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, v, L.t, never);
+      if (int rc = mg_apply(L, v, L.t, never, st)) return rc;
       // w = Dinv K v ; pw = w.w (= lambda^2 once v has unit length: from the second pass on, or at once when warm)
-      k_mg_pw_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.t, L.d, L.dinv, L.fixed, MgFin{W.S, MG_OP_PW, 0.0, 0.0, 0},
-                                                   W.partials, W.counter);
+      k_mg_pw_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.t, L.d, L.dinv, L.fixed, ow, pw, W.partials, W.counter);
+      if (multi) {
+        if (int rc = sic_exchange(h, nullptr, 0, W.S->sum, 1, stream)) return rc;
+        k_mg_scal<<<1, 1, 0, st>>>(pw, 0);
+      }
       if (it + 1 < its || L.pv) k_mg_pw_scale<<<db, SIC_VEC_THREADS, 0, st>>>(nd, v, L.d, L.t, W.S);
     }
     if (int rc = sic_check_launch("multigrid: power iteration")) return rc;
@@ -535,7 +599,18 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   const int check = ksp->check_every > 0 ? ksp->check_every : 4;
   const int guess = ksp->guess_nonzero ? 1 : 0;
   const double rtol = ksp->rtol, atol = ksp->atol;
-  auto fin = [&](int op) { return MgFin{S, op, rtol, atol, guess}; };
+  const sic_halo_t* halo = mg_halo(T);
+  const int multi = halo ? 1 : 0;
+  const double* ow = halo ? halo->owner_w : nullptr;
+  auto fin = [&](int op) { return MgFin{S, op, rtol, atol, guess, multi}; };
+  // several GPUs: add the partial sums of the last reducing kernel over the ranks (optionally together with the halo
+  // sum of `vec`: one exchange kernel), then run the scalar recurrence in a one-thread kernel -- still no host sync
+  auto reduce = [&](int op, double* vec3, int skip_if_done) -> int {
+    if (!multi) return 0;
+    if (int rc = sic_exchange(halo, vec3, vec3 ? 3 : 0, S->sum, 1, stream)) return rc;
+    k_mg_scal<<<1, 1, 0, st>>>(fin(op), skip_if_done);
+    return sic_check_launch("k_mg_scal");
+  };
   ksp->op_samples = 0;
   ksp->op_ms = 0.0;
   cudaEvent_t* ev = nullptr;
@@ -546,13 +621,16 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
 
   if (guess) {   // reference norm of rtol: the residual of the zero guess (prescribed values only), as PETSc's ||b||
     k_mg_zero_free<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, x, fixed);
-    if (int rc = sic_residual0(p, b_ext, pp, r, fixed, nullptr, stream)) return rc;
-    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, fin(MG_OP_REF), 0, W.partials, W.counter);
+    if (int rc = sic_residual0(p, b_ext, pp, r, fixed, halo, stream)) return rc;
+    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, ow, fin(MG_OP_REF), 0, W.partials, W.counter);
+    if (int rc = reduce(MG_OP_REF, nullptr, 0)) return rc;
   }
-  if (int rc = sic_residual0(p, b_ext, x, r, fixed, nullptr, stream)) return rc;
-  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
+  if (int rc = sic_residual0(p, b_ext, x, r, fixed, halo, stream)) return rc;
+  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, ow, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
+  if (int rc = reduce(MG_OP_INIT_RR, nullptr, 0)) return rc;
   if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, nullptr)) return rc;
-  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
+  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
+  if (int rc = reduce(MG_OP_INIT_RZ, nullptr, 1)) return rc;
   k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);   // p = z ; q = 0
 
   int launched = 0;
@@ -566,16 +644,22 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     if (g_mg_host->done || launched >= ksp->max_it) break;
     const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
     for (int k = 0; k < batch; ++k) {
-      k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
-      k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, S);
-      k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, fin(MG_OP_RR), W.partials, W.counter);
+      // q = K p with p.Kp summed per cell (cells are partitioned: no owner weights needed); several GPUs: the halo
+      // sum of q and the sum of p.Kp over the ranks travel in ONE exchange
+      if (cb > 0) k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
+      k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
+      if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
+      k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
+      if (int rc = reduce(MG_OP_RR, nullptr, 1)) return rc;
       if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, (k == 0) ? ev : nullptr)) return rc;
-      k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, fin(MG_OP_RZ), 1, W.partials, W.counter);
+      k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
+      if (int rc = reduce(MG_OP_RZ, nullptr, 1)) return rc;
       k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
     }
     launched += batch;
     if (int rc = sic_check_launch("mg-cg batch")) return rc;
   }
+  if (multi && halo->p2p && sic_p2p_error(halo->p2p)) return sic_fail("P2P exchange timed out waiting for a peer");
   ksp->iterations = g_mg_host->iters;
   ksp->rnorm = sqrt(g_mg_host->rr);
   ksp->rnorm0 = sqrt(g_mg_host->rr0);

@@ -94,13 +94,17 @@ def init(device=None) -> DistContext:
     return DistContext(rank, world, device, comm)
 
 
-def partition_grid(ctx: DistContext, tetmesh):
-    """Every rank holds the same global (Morton-ordered) mesh; returns (local grid, Partition)."""
+def partition_grid(ctx: DistContext, tetmesh, hierarchy=None):
+    """Every rank holds the same global (Morton-ordered) mesh; returns (local grid, Partition).
+    hierarchy: the GLOBAL multigrid hierarchy whose finest level is ``tetmesh`` (kept on the local grid for PC mg:
+    the finest level is distributed, the coarser ones replicated)."""
     part = build_partition(tetmesh.cells, tetmesh.n_nodes, ctx.rank, ctx.world,
                            device=ctx.device if ctx.device.type == "cuda" else "cpu")
     local = part.local_mesh(tetmesh)
     grid = GridHandlerGMSH.from_mesh(local, reorder=False)
     grid.partition = part
+    if hierarchy is not None:
+        grid.hierarchy = hierarchy
     return grid, part
 
 

@@ -77,6 +77,24 @@ def refine_hierarchy(base: TetMesh, levels: int, device="cpu") -> Hierarchy:
     return h
 
 
+def _localise(t: Transfer, part, n_coarse_nodes: int) -> Transfer:
+    """Transfer tables of the finest level for ONE rank of a cell partition: rows of the rank's local nodes / cells,
+    coarse side still in global numbering (the coarse level is replicated); children of other ranks become -1."""
+    ln = part.local_nodes.cpu().numpy()
+    c0, c1 = part.cell_range
+    pa, pb = t.parent_a[ln].astype(np.int64), t.parent_b[ln].astype(np.int64)
+    m = ln.size
+    rows = np.concatenate([pa, pb])
+    idx = np.concatenate([np.arange(m), np.arange(m)])
+    order = np.argsort(rows, kind="stable")
+    ptr = np.zeros(n_coarse_nodes + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum(np.bincount(rows, minlength=n_coarse_nodes))
+    ch = t.children.astype(np.int64)
+    ch = np.where((ch >= c0) & (ch < c1), ch - c0, -1)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return Transfer(i32(pa), i32(pb), i32(ptr), i32(idx[order]), i32(ch), t.inject)
+
+
 def prolongation_matrix(t: Transfer, n_coarse_nodes: int):
     """P (M_fine x M_coarse, scipy CSR) of one transfer: used by the tests to check the tables."""
     import scipy.sparse as sp
@@ -96,7 +114,11 @@ class Multigrid:
     the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=20, smooth_lo=0.1, coarse_lo=0.02,
-                 safety=1.15, power_its=16, power_its_warm=4):
+                 safety=1.15, power_its=16, power_its_warm=4, part=None, coarse_fixed=None):
+        """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one):
+        the finest level is distributed, the coarser ones are replicated on every rank (csrc/mg.cu).
+        coarse_fixed: callable(level index, TetMesh) -> uint8 (3 M,) Dirichlet mask of a coarse level; needed when the
+        finest level is partitioned (a rank cannot inject a mask it only holds a part of)."""
         import ctypes
 
         import torch
@@ -107,8 +129,19 @@ class Multigrid:
         if hierarchy.n_levels > L.SIC_MG_MAX_LEVELS:
             raise L.SicError(f"at most {L.SIC_MG_MAX_LEVELS} multigrid levels")
         fine = hierarchy.finest
-        if fine.n_cells != fine_engine.N or fine.n_nodes != fine_engine.M:
-            raise L.SicError("the hierarchy's finest level is not the mesh of the momentum equation")
+        self.part = part if (part is not None and part.n_ranks > 1) else None
+        if self.part is None:
+            if fine.n_cells != fine_engine.N or fine.n_nodes != fine_engine.M:
+                raise L.SicError("the hierarchy's finest level is not the mesh of the momentum equation")
+        else:
+            c0, c1 = self.part.cell_range
+            if c1 - c0 != fine_engine.N or int(self.part.local_nodes.numel()) != fine_engine.M:
+                raise L.SicError("the partition does not describe the momentum equation's local mesh")
+            if hierarchy.n_levels < 2 or coarse_fixed is None:
+                raise L.SicError("a partitioned multigrid needs >= 2 levels and the coarse Dirichlet masks (coarse_fixed)")
+            if fine_engine.halo is None:
+                raise L.SicError("attach the partition to the engine (Engine.set_partition) before building the multigrid")
+        self.coarse_fixed = coarse_fixed
         self.h, self.fine = hierarchy, fine_engine
         self.lib, dev = fine_engine.lib, fine_engine.device
         self.engines = [type(fine_engine)(m.coords, m.cells, device=dev, operator_only=True)
@@ -129,6 +162,8 @@ class Multigrid:
             lv.lambda_max = 0.0
             if l > 0:
                 t = hierarchy.transfers[l]
+                if self.part is not None and l == n - 1:
+                    t = _localise(t, self.part, hierarchy.meshes[l - 1].n_nodes)
                 tabs = {k: dt(getattr(t, k)) for k in ("parent_a", "parent_b", "rst_ptr", "rst_idx", "children", "inject")}
                 self._keep.append(tabs)
                 lv.parent_a, lv.parent_b = _ptr(tabs["parent_a"]), _ptr(tabs["parent_b"])
@@ -154,15 +189,22 @@ class Multigrid:
             lv = self.levels[l]
             lv.prob = eng.problem()
             lv.fixed, lv.dinv = _ptr(self.fixed[l]), _ptr(self.dinv[l])
+        if self.part is not None:
+            self.levels[n - 1].halo = self._ct.cast(self._ct.pointer(self.fine.halo), self._ct.c_void_p)
 
     def setup(self, fixed_fine, dinv_fine):
         """Once per tangent: inject the Dirichlet mask down the hierarchy, then sic_mg_setup (Galerkin C_T,
         block-Jacobi blocks of every level, lambda_max)."""
         L, torch = self._L, self._to
         self._refresh(fixed_fine, dinv_fine)
-        for l in range(len(self.engines) - 1, 0, -1):
-            inj = self._keep[l]["inject"].long()
-            self.fixed[l - 1].view(-1, 3).copy_(self.fixed[l].view(-1, 3)[inj])
+        if self.part is None:
+            for l in range(len(self.engines) - 1, 0, -1):
+                inj = self._keep[l]["inject"].long()
+                self.fixed[l - 1].view(-1, 3).copy_(self.fixed[l].view(-1, 3)[inj])
+        else:       # replicated coarse levels: every rank builds their masks from the boundary data of the coarse meshes
+            for l in range(len(self.engines) - 1):
+                m = self._to.as_tensor(self.coarse_fixed(l, self.h.meshes[l])).to(self.fixed[l].device, dtype=self._to.uint8)
+                self.fixed[l].copy_(m.reshape(-1))
         st = self.fine._stream()
         L.check(self.lib.sic_mg_setup(self.levels, len(self.engines), self._ct.byref(self.opts), self._ptr(self.work), st),
                 "sic_mg_setup")

@@ -44,14 +44,14 @@ def test_struct_layouts_match_the_header(tmp_path):
                  'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sic_problem_t), sizeof(sic_elem_t), sizeof(sic_ksp_t),'
                  ' offsetof(sic_problem_t, elems), offsetof(sic_problem_t, T), offsetof(sic_problem_t, n_singular),'
                  ' offsetof(sic_ksp_t, op_ms), sizeof(sic_mg_level_t), offsetof(sic_mg_level_t, lambda_max),'
-                 ' offsetof(sic_mg_level_t, t), sizeof(sic_mg_opts_t), offsetof(sic_mg_opts_t, power_its_warm), sizeof(sic_heat_t), offsetof(sic_heat_t, fixed)); return 0;}\n')
+                 ' offsetof(sic_mg_level_t, halo), sizeof(sic_mg_opts_t), offsetof(sic_mg_opts_t, power_its_warm), sizeof(sic_heat_t), offsetof(sic_heat_t, fixed)); return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.SicProblem), ctypes.sizeof(_lib.SicElem), ctypes.sizeof(_lib.SicKsp),
             _lib.SicProblem.elems.offset, _lib.SicProblem.T.offset, _lib.SicProblem.n_singular.offset,
             _lib.SicKsp.op_ms.offset, ctypes.sizeof(_lib.SicMgLevel), _lib.SicMgLevel.lambda_max.offset,
-            _lib.SicMgLevel.t.offset, ctypes.sizeof(_lib.SicMgOpts), _lib.SicMgOpts.power_its_warm.offset, ctypes.sizeof(_lib.SicHeat),
+            _lib.SicMgLevel.halo.offset, ctypes.sizeof(_lib.SicMgOpts), _lib.SicMgOpts.power_its_warm.offset, ctypes.sizeof(_lib.SicHeat),
             _lib.SicHeat.fixed.offset]
     assert got == want
 

@@ -20,16 +20,17 @@ def sf():
     sf.LinearMomentum.engine_cls = old
 
 
-def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None):
+def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None, multigrid=False):
     from safeincave_b200 import cases, distributed
-    from safeincave_b200.mesh import TetMesh, morton_order, red_refine
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
     from tests.hostemu.ranks import run_ranks
-    tm = TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz"))
-    for _ in range(levels):
-        tm = red_refine(tm)
-    tm = morton_order(tm)
-    gg = sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz")), levels)
+    tm = h.finest
+    gg = sf.GridHandlerGMSH.from_hierarchy(h)
     case = cases.triaxial_case(gg, n_steps=n_steps, ksp_override=ksp)
+    if multigrid:
+        setup = lambda eq, grid, part: eq.solver.getPC().setType("mg")
     eq1, sim1 = cases.build(case, gg)
     if setup:
         setup(eq1, gg, None)
@@ -37,7 +38,7 @@ def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None):
     hist1 = sim1.run()
 
     def body(ctx):
-        grid, part = distributed.partition_grid(ctx, tm)
+        grid, part = distributed.partition_grid(ctx, tm, hierarchy=h if multigrid else None)
         eq, sim = cases.build(case, grid, part=part, ctx=ctx)
         if setup:
             setup(eq, grid, part)
@@ -52,6 +53,8 @@ def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None):
                     peers=part.peers, n=eq.engine.N)
 
     res = run_ranks(world, body)
+    for r in res:
+        r["ksp1"] = [x["ksp_iterations"] for x in hist1]
     assert sum(r["n"] for r in res) == tm.n_cells
     for r in res:
         assert r["newton"] == [h["iterations"] for h in hist1]
@@ -63,3 +66,14 @@ def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None):
 def test_partitioned_block_jacobi_krylov_matches_single_rank(sf, world, ksp):
     res, hist1 = partitioned_vs_single(sf, world, ksp)
     assert all(len(r["peers"]) >= 1 for r in res)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_multigrid_matches_single_rank(sf, world):
+    """PC mg with the finest level distributed over the ranks and the coarser levels replicated (csrc/mg.cu): same
+    fields, same Newton history and the SAME Krylov iteration counts as the single-rank multigrid run (the algorithm is
+    identical; only the order of floating-point sums differs)."""
+    res, hist1 = partitioned_vs_single(sf, world, "cg", levels=2, n_steps=2, multigrid=True)
+    for r in res:
+        assert all(abs(a - b) <= 2 for a, b in zip(r["ksp"], r["ksp1"])), (r["ksp"], r["ksp1"])
+        assert max(r["ksp"]) < 250
