@@ -209,13 +209,57 @@ def probe_mg(levels=2, device="cuda:0"):
     return 0 if ok else 1
 
 
-def decide_pc(args, world, note):
+def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None):
+    """The same comparison as probe_mg for a run on several GPUs, IN PROCESS and collectively: one time step of the
+    cavern case on cavern_regular x8^levels, partitioned over the ranks, with block-Jacobi CG and with the multigrid
+    CG (finest level distributed, coarser levels replicated).  Every rank compares its own part; the verdict is the
+    minimum over the ranks, so all of them take the same decision."""
+    import torch
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases, distributed
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    dev, ok, msg = ctx.device, 1, ""
+    try:
+        h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", f"mesh_{mesh}.npz")), levels, device=dev)
+        gg = sf.GridHandlerGMSH.from_hierarchy(h)
+        case = case_fn(gg) if case_fn else cases.cavern_case(gg, n_steps=1, ksp_type="cg", rtol=1e-10)
+        out = {}
+        for pc in ("jacobi", "mg"):
+            grid, part = distributed.partition_grid(ctx, h.finest, hierarchy=h if pc == "mg" else None)
+            eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
+            if pc == "mg":
+                eq.solver.getPC().setType("mg")
+            sim.verbose = False
+            sim.initialize()
+            rec = sim.step()
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            out[pc] = (eq.X.clone(), [k[0] for k in eq.ksp_log], [k[1] for k in eq.ksp_log], rec)
+            del eq, sim
+        xj, xm = out["jacobi"][0], out["mg"][0]
+        err = float((xj - xm).abs().max() / xj.abs().max())
+        good = err < 1e-7 and all(r > 0 for r in out["mg"][2]) and max(out["mg"][1]) <= 80 and out["mg"][3]["converged"] \
+            and out["mg"][3]["iterations"] == out["jacobi"][3]["iterations"]
+        msg = f"rel_diff={err:.2e} mg_its<={max(out['mg'][1])} jacobi_its<={max(out['jacobi'][1])}"
+        ok = 1 if good else 0
+    except Exception as e:          # SicError (incl. a P2P wait that timed out), shape errors, ...
+        ok, msg = 0, f"exception on rank {ctx.rank}: {e!r}"
+    all_ok = ctx.max_over_ranks(float(1 - ok)) == 0.0        # the worst rank decides, identically everywhere
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return all_ok, ("MG_PROBE_OK " if all_ok else "MG_PROBE_FAIL ") + msg
+
+
+def decide_pc(args, world, note, ctx=None):
     if args.pc != "auto":
         return args.pc, "forced by --pc"
-    if world > 1:
-        return "jacobi", "multigrid path is single-GPU in this version"
     if args.levels < 1 or args.ksp != "cg":
         return "jacobi", "no refinement hierarchy / KSP type is not cg"
+    if world > 1:
+        ok, msg = probe_mg_ranks(ctx)
+        note(f"multigrid probe on {world} ranks: {msg}")
+        return ("mg" if ok else "jacobi"), msg
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-mg"], capture_output=True, text=True,
                            timeout=900)
@@ -248,7 +292,7 @@ def run_b200(args):
     local = dev.index or 0
     note(f"process group up, world {world}")
 
-    pc, pc_why = decide_pc(args, world, note)
+    pc, pc_why = decide_pc(args, world, note, ctx)
     tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
     if pc == "mg":
         from safeincave_b200.multigrid import refine_hierarchy
@@ -264,7 +308,7 @@ def run_b200(args):
     n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
     case = cases.cavern_case(grid_global, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
     if world > 1:            # strong scaling: the SAME mesh, cells partitioned along the Morton curve
-        grid, part = distributed.partition_grid(ctx, tm)
+        grid, part = distributed.partition_grid(ctx, tm, hierarchy=hierarchy if pc == "mg" else None)
         eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
     else:
         grid, part = grid_global, None
@@ -384,8 +428,10 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.levels, N), "n_cells": N, "n_nodes": M,
-                   "cells_per_gpu": N_loc, "partition": "Morton-curve chunks, interface nodes duplicated, NCCL halo sum "
-                   "+ 2 scalar allreduces per CG iteration" if world > 1 else "single GPU",
+                   "cells_per_gpu": N_loc, "partition": ("single GPU" if world == 1 else (
+                       "Morton-curve cell chunks, interface nodes duplicated, P2P halo sum + scalar sums over NVLink in one kernel"
+                       + ("; multigrid: finest level distributed, coarser levels replicated, one all-reduce of the coarse "
+                          "right-hand side per cycle" if pc == "mg" else ""))),
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
                    "preconditioner": ("geometric multigrid V(2,2), Chebyshev/block-Jacobi smoother, Galerkin coarse tangents, "
                                       f"{args.levels + 1} levels") if pc == "mg" else "nodal 3x3 block Jacobi",

@@ -98,6 +98,7 @@ def load():
         lib.sic_allreduce_sum.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.sic_emu_make_comm.argtypes = [ctypes.c_int, ctypes.c_int]
         lib.sic_emu_make_comm.restype = ctypes.c_void_p
+        lib.sic_emu_set_timeout.argtypes = [ctypes.c_int]
         _emu = lib
     return _emu
 

@@ -133,12 +133,13 @@ int g_waiting = 0;
 unsigned long long g_generation = 0;
 RankSlot g_rank[SIC_MAX_PEERS];
 
-// all `n` ranks arrive, or -1 after 120 s (a rank died: its thread raised in Python)
+int g_timeout_s = 120;
+// all `n` ranks arrive, or -1 after g_timeout_s (a rank died: its thread raised in Python)
 int rank_barrier(int n) {
   std::unique_lock<std::mutex> lk(g_mu);
   const unsigned long long gen = g_generation;
   if (++g_waiting == n) { g_waiting = 0; ++g_generation; g_cv.notify_all(); return 0; }
-  if (!g_cv.wait_for(lk, std::chrono::seconds(120), [&] { return g_generation != gen; })) { --g_waiting; return -1; }
+  if (!g_cv.wait_for(lk, std::chrono::seconds(g_timeout_s), [&] { return g_generation != gen; })) { --g_waiting; return -1; }
   return 0;
 }
 struct EmuComm { int rank, n_ranks; };
@@ -148,6 +149,7 @@ extern int sic_fail(const char* msg);
 
 extern "C" {
 void* sic_emu_make_comm(int rank, int n_ranks) { return new EmuComm{rank, n_ranks}; }
+void sic_emu_set_timeout(int seconds) { g_timeout_s = seconds > 0 ? seconds : 1; }
 
 int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double* scal, int n_scal, void*) {
   if (!h || h->n_ranks <= 1) return 0;

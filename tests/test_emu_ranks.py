@@ -77,3 +77,25 @@ def test_partitioned_multigrid_matches_single_rank(sf, world):
     for r in res:
         assert all(abs(a - b) <= 2 for a, b in zip(r["ksp"], r["ksp1"])), (r["ksp"], r["ksp1"])
         assert max(r["ksp"]) < 250
+
+
+def test_bench_multigrid_probe_on_emulated_ranks(sf):
+    """bench.py decides between multigrid and block-Jacobi for N > 1 with a collective in-process probe; run it here on
+    three emulated ranks (cube instead of the cavern so that it takes seconds), and check that a rank that raises makes
+    EVERY rank report failure instead of hanging."""
+    import bench
+    from safeincave_b200 import cases
+    from tests.hostemu.ranks import run_ranks
+    case_fn = lambda g: cases.triaxial_case(g, n_steps=1, ksp_override="cg")
+    res = run_ranks(3, lambda ctx: bench.probe_mg_ranks(ctx, levels=2, mesh="cube_coarse", case_fn=case_fn))
+    assert all(ok for ok, _ in res) and all(msg.startswith("MG_PROBE_OK") for _, msg in res), res
+
+    def broken(g):
+        raise RuntimeError("simulated failure")
+    from tests import hostemu
+    hostemu.load().sic_emu_set_timeout(3)          # the surviving rank gives up in the emulated exchange after 3 s
+    try:
+        res = run_ranks(2, lambda ctx: bench.probe_mg_ranks(ctx, levels=2, mesh="cube_coarse", case_fn=broken if ctx.rank == 1 else case_fn))
+    finally:
+        hostemu.load().sic_emu_set_timeout(120)
+    assert not any(ok for ok, _ in res), res
