@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 10
+#define SIC_ABI_VERSION 11
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -356,6 +356,16 @@ int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old, double* T
                   void* stream);
 /* get_T_elems (HeatEquation.py:286-302): cell value = mean of the four nodal values */
 int sic_heat_cell_mean(const sic_heat_t* h, const double* T_nodes, double* T_cells, void* stream);
+
+/* ---- output fields of a converged step (outside the timed hot path) --------------------------------------- */
+/* compute_p_elems / q_elems / p_nodes / q_nodes (MomentumEquation.py:287-324, 944-976) with the smoother of
+ * Grid.py:198-242: p = tr(sig)/3, q = sqrt(3 J2) per cell from p->sig; node value = volume-weighted average over the
+ * incident cells (grid.A_csr); element value = mean of its four node values (grid.B_csr).
+ *   node_vol  [n_nodes] sum of the incident cells' volumes: sic_node_volumes, once per mesh
+ *   p_elems / q_elems [n_cells] may be NULL.  Several GPUs: the nodal sums are completed by the halo sum. */
+int sic_node_volumes(const sic_problem_t* p, double* node_vol, const sic_halo_t* halo, void* stream);
+int sic_pq_fields(const sic_problem_t* p, const double* node_vol, double* p_nodes, double* q_nodes, double* p_elems,
+                  double* q_elems, const sic_halo_t* halo, void* stream);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-free DFMA chains; returns achieved FLOP/s in *flops (used to record the FP64 peak) */

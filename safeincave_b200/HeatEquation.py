@@ -27,6 +27,9 @@ class HeatDiffusion:
     def __init__(self, grid, device="cuda"):
         self.grid = grid
         tm = grid.tetmesh
+        if getattr(grid, "partition", None) is not None and grid.partition.n_ranks > 1:
+            raise NotImplementedError("HeatDiffusion runs on one GPU in this version (the heat solve is ~1 % of a "
+                                      "thermo-mechanical step); build it on the unpartitioned grid")
         self.engine = self.engine_cls(tm.coords, tm.cells, device=device, geometry_only=True)
         eng = self.engine
         dev = eng.device

@@ -340,38 +340,33 @@ class LinearMomentum(LinearMomentumBase):
             e.restore(s)
 
     # ------------------------------------------------------------------ p / q output fields
-    def _pq(self):
+    def _pq_fields(self):
+        """MomentumEquation.py:287-324, 944-976 with the smoother of Grid.py:198-242, on the device (csrc/fields.cu):
+        all four fields come out of one call (four small kernels; output only, outside the timed path)."""
+        import ctypes
         eng = self.engine
-        s = eng.sig[:, :eng.N]
-        I1 = s[0] + s[1] + s[2]
-        I2 = s[0] * s[1] + s[1] * s[2] + s[0] * s[2] - s[3] ** 2 - s[4] ** 2 - s[5] ** 2
-        return I1 / 3.0, to.sqrt(3 * ((1 / 3) * I1 ** 2 - I2))
-
-    def _to_nodes(self, f):
-        """Volume-weighted node average (grid.A_csr, Grid.py:226-233)."""
-        eng = self.engine
-        vol = eng.vol[:eng.N]
+        dev = eng.device
         if self._nodes_vol is None:
-            self._nodes_vol = to.zeros(eng.M, dtype=to.float64, device=eng.device)
-            for a in range(4):
-                self._nodes_vol.index_add_(0, eng.conn[a, :eng.N].long(), vol)
-        out = to.zeros(eng.M, dtype=to.float64, device=eng.device)
-        for a in range(4):
-            out.index_add_(0, eng.conn[a, :eng.N].long(), vol * f)
-        return out / self._nodes_vol
-
-    def _to_elems(self, fn):
-        eng = self.engine
-        return sum(fn[eng.conn[a, :eng.N].long()] for a in range(4)) / 4.0     # grid.B_csr, Grid.py:234-241
+            self._nodes_vol = to.zeros(max(eng.M, 1), dtype=to.float64, device=dev)
+            L.check(eng.lib.sic_node_volumes(eng._pp(), ctypes.c_void_p(self._nodes_vol.data_ptr()), eng._ph(), eng._stream()),
+                    "sic_node_volumes")
+            self._pq_buf = [to.zeros(max(n, 1), dtype=to.float64, device=dev) for n in (eng.M, eng.M, eng.N, eng.N)]
+        pn, qn, pe, qe = self._pq_buf
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        L.check(eng.lib.sic_pq_fields(eng._pp(), ptr(self._nodes_vol), ptr(pn), ptr(qn), ptr(pe), ptr(qe), eng._ph(),
+                                      eng._stream()), "sic_pq_fields")
+        eng.launches += 4
+        self.p_nodes, self.q_nodes = pn[:eng.M], qn[:eng.M]
+        self.p_elems, self.q_elems = pe[:eng.N], qe[:eng.N]
 
     def compute_p_nodes(self):
-        self.p_nodes = self._to_nodes(self._pq()[0])
+        self._pq_fields()
 
     def compute_q_nodes(self):
-        self.q_nodes = self._to_nodes(self._pq()[1])
+        self._pq_fields()
 
     def compute_p_elems(self):
-        self.p_elems = self._to_elems(self._to_nodes(self._pq()[0]))
+        self._pq_fields()
 
     def compute_q_elems(self):
-        self.q_elems = self._to_elems(self._to_nodes(self._pq()[1]))
+        self._pq_fields()

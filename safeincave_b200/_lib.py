@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 10
+SIC_ABI_VERSION = 11
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -35,7 +35,7 @@ EXPORTS = (
     "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
     "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle",
-    "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean",
+    "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean", "sic_node_volumes", "sic_pq_fields",
 )
 
 
@@ -127,6 +127,8 @@ def declare(lib, single_gpu_only=False):
     lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
+    lib.sic_node_volumes.argtypes = [PP, c_void_p, PH, c_void_p]
+    lib.sic_pq_fields.argtypes = [PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
     PHT = POINTER(SicHeat)
     lib.sic_heat_workspace_doubles.argtypes = [c_int]
     lib.sic_heat_workspace_doubles.restype = c_int64

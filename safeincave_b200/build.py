@@ -21,6 +21,7 @@ UNITS = [
     ("solver.cu", []),
     ("mg.cu", []),
     ("heat.cu", []),
+    ("fields.cu", []),
     ("comm.cu", []),
 ]
 

@@ -34,7 +34,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libsic_hostemu.so")
 # translation units of the single-GPU path (comm.cu = NCCL / CUDA IPC: not emulated)
 UNITS = [("common.cu", []), ("constitutive.cu", ["-ffp-contract=off"]), ("fem.cu", []), ("solver.cu", []),
-         ("mg.cu", []), ("heat.cu", [])]
+         ("mg.cu", []), ("heat.cu", []), ("fields.cu", [])]
 CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-mfma", "-w", "-x", "c++"]
 
 

@@ -108,6 +108,22 @@ def test_operator_rhs_blocks_strain(sf, grid_name):
     assert np.sqrt(num / den) == pytest.approx(oc.newton_error(prev, e), rel=1e-12)
 
 
+def test_pq_output_fields(sf):
+    """compute_p_elems / q_elems / p_nodes / q_nodes (csrc/fields.cu) against the oracle's CSR smoother (Grid.py:198-242)."""
+    grid = load_grid(sf, "cavern_regular")
+    tm = grid.tetmesh
+    eq = sf.LinearMomentum(grid, theta=0.5)
+    eng = eq.engine
+    rng = np.random.default_rng(9)
+    sig = -1e7 * (1 + rng.random((eng.N, 6))) * np.array([1, 1, 1, 0.1, 0.1, 0.1])
+    eng.put6(eng.sig, sig)
+    for f in (eq.compute_p_elems, eq.compute_q_elems, eq.compute_p_nodes, eq.compute_q_nodes):
+        f()
+    ref = fem.p_q_fields(tm.coords, tm.cells, sig)
+    for name in ("p_nodes", "q_nodes", "p_elems", "q_elems"):
+        assert relerr(getattr(eq, name).cpu().numpy(), ref[name]) < 1e-12, name
+
+
 def test_neumann_and_body_force(sf):
     from safeincave_b200 import cases
     grid = load_grid(sf, "cavern_regular")
