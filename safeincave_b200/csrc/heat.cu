@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_tris(sic_heat_t H, int
   }
 }
 
-// diagonal of M/dt + K (cells) -- the Robin part is added by k_heat_tris with x = 1 ... no: its diagonal is 2 w
+// diagonal of M/dt + K: per cell node 2 (cm V rho cp / 20) + V k |g_a|^2 ; the Robin boundary mass adds 2 (h A / 12) per
+// facet node (k_heat_diag_tris)
 __global__ void __launch_bounds__(SIC_EBE_THREADS) k_heat_diag_cells(sic_heat_t H, double cm, double* __restrict__ d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H.n_cells) return;

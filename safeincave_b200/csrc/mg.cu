@@ -423,7 +423,8 @@ static int mg_host_mirror() {
 }
 
 // One Chebyshev sweep of `its` steps on level L for eigenvalues in [lo, 1] * lambda_max; b: right-hand side.
-// zero_guess != 0: x starts from 0.  On return r is the residual BEFORE the last update d (see mg_true_residual).
+// zero_guess != 0: x starts from 0.  On return r is the residual BEFORE the last update d: the caller that needs
+// the true residual of x applies K to d once more (k_mg_resid).
 static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, double lo, int zero_guess, const int* done,
                         cudaStream_t st) {
   const int nn = L.prob.n_nodes, nc = L.prob.n_cells;

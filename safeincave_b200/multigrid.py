@@ -174,7 +174,9 @@ class Multigrid:
                 setattr(lv, k, _ptr(self.vec[l][k]))
         need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
         self.work = zeros(need)
-        self.launches_per_cycle = sum(2 * (2 * nu + 1) + 3 for _ in range(n - 1)) + 2 * coarse_its
+        # kernels per V-cycle (bench.py's gpu_launches): per level 2 nu operator + 2 nu smoother + residual, restriction,
+        # prolongation; coarsest level 2 coarse_its - 1
+        self.launches_per_cycle = (n - 1) * (4 * nu + 3) + 2 * coarse_its - 1
         self.setups = 0
 
     def _refresh(self, fixed_fine=None, dinv_fine=None):
