@@ -75,3 +75,61 @@ def test_reference_triaxial_example_runs_unmodified(tmp_path, monkeypatch):
     assert [h["iterations"] for h in sim.history] == [h["iters"] for h in ohist[1:]]
     assert rel(eq.X.reshape(-1).numpy(), ohist[-1]["u"]) < 5e-6
     assert rel(eq.engine.get6(eq.engine.sig), ohist[-1]["sig"]) < 5e-6
+
+
+@pytest.mark.skipif(not os.environ.get("SIC_SLOW"), reason="~13 min under emulation (25 608 cells, BiCGStab); set SIC_SLOW=1")
+def test_reference_thermomechanics_cavern_example_runs_unmodified(tmp_path, monkeypatch):
+    """BASELINE config 4's own script, examples/thermomechanics/2_cavern/main.py, on its own grid
+    (grids/cavern_overburden_coarse: salt + overburden, region-wise parameters): an equilibrium stage with Simulator_M and
+    a parabolic time controller, then the operation stage with HeatDiffusion + Simulator_TM (Dirichlet / Neumann / Robin
+    heat BCs, thermal strain, Kelvin + dislocation + pressure-solution creep).  Executed unmodified; two steps per stage."""
+    import safeincave_b200 as sf
+    from safeincave_b200 import compat
+    from tests.hostemu import EmuEngine
+    example = os.path.join(REF, "examples", "thermomechanics", "2_cavern", "main.py")
+    if not os.path.isfile(example):
+        pytest.skip("example not in the reference checkout")
+    monkeypatch.setattr(sf.LinearMomentum, "engine_cls", EmuEngine)
+    monkeypatch.setattr(sf.HeatDiffusion, "engine_cls", EmuEngine)
+    registered = compat.install()
+    sims = []
+    try:
+        work = tmp_path / "examples" / "thermomechanics" / "2_cavern"
+        work.mkdir(parents=True)
+        os.symlink(os.path.join(REF, "grids"), tmp_path / "grids")
+        monkeypatch.chdir(work)
+        real_tc, real_tcp = sf.TimeController, sf.TimeControllerParabolic
+
+        class TC(real_tc):
+            def __init__(self, dt, initial_time, final_time, time_unit="second"):
+                super().__init__(dt=dt, initial_time=initial_time, final_time=min(final_time, 2 * dt), time_unit=time_unit)
+
+        class TCP(real_tcp):
+            def keep_looping(self):
+                return self.step_counter < 2 and super().keep_looping()
+
+        monkeypatch.setattr(sf, "TimeController", TC)
+        monkeypatch.setattr(sf, "TimeControllerParabolic", TCP)
+        for name in ("Simulator_M", "Simulator_TM"):
+            base = getattr(sf, name)
+
+            class Rec(base):
+                def __init__(self, *a, **k):
+                    super().__init__(*a, **k)
+                    self.verbose = False
+                    sims.append(self)
+            monkeypatch.setattr(sf, name, Rec)
+        runpy.run_path(example, run_name="not_main")["main"]()
+    finally:
+        for name in registered:
+            for key in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+                del sys.modules[key]
+    sim_m, sim_tm = sims
+    assert len(sim_m.history) == 2 and all(h["converged"] for h in sim_m.history)
+    assert len(sim_tm.history) == 2 and all(h["error"] <= 1e-6 and h["heat_iterations"] > 0 for h in sim_tm.history)
+    eq = sim_tm.eq_mom
+    assert np.isfinite(eq.X.numpy()).all() and np.abs(eq.X.numpy()).max() > 0
+    T = sim_tm.eq_heat.T.x.array
+    assert 280.0 < T.min() and T.max() < 340.0          # geothermal profile, gas at 293 K on the cavern wall
+    for stage, field in (("equilibrium", "u"), ("operation", "u"), ("operation", "T"), ("operation", "q_elems")):
+        assert os.path.isfile(work / "output" / "case_1" / stage / field / f"{field}.xdmf")
