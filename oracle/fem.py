@@ -188,6 +188,7 @@ class OracleSimulatorM:
         self.u = np.zeros(3 * coords.shape[0])
         self.sig = np.zeros((cells.shape[0], 6))
         self.history = []
+        self.tol, self.maxiter, self.max_dt_cuts = 1e-8, 40, 3     # Simulators.py:399-402, 378-396
         self.after_initial_stress = None      # callable(material, sig) between initial stress and initial rates
 
     def _bc(self, t):
@@ -210,7 +211,8 @@ class OracleSimulatorM:
         b = b_ext + rhs_eps(self.coords, self.cells, CT, eps_rhs)
         return solve(K, b, dofs, vals)
 
-    def run(self, t0, dt_list):
+    def run(self, t0, dt_list, maxiter_list=None):
+        """maxiter_list: optional Newton-iteration cap per step (tests of the dt-retry path); default self.maxiter."""
         m, th = self.mat, self.theta
         t = t0
         if self.compute_elastic_response:                      # Simulators.py:346-354
@@ -225,13 +227,15 @@ class OracleSimulatorM:
         m.eval_rates(sig, t * th, self.T)                      # :364 passes t as dt (T7)
         m.commit_rates()                                       # :365
         self.history.append(dict(t=t, u=self.u.copy(), sig=sig.copy(), eps=eps.copy(), iters=0, error=0.0))
-        for dt in dt_list:
+        for k_step, dt in enumerate(dt_list):
             t = t + dt
+            if maxiter_list is not None:
+                self.maxiter = maxiter_list[k_step]
             sig_bak, eps_bak, snap = sig.copy(), eps.copy(), m.snapshot()
             dt_cur, cuts, converged = dt, 0, False
-            while not converged and cuts <= 3:
-                tol, err, ite = 1e-8, 2e-8, 0
-                while err > tol and ite < 40:
+            while not converged and cuts <= self.max_dt_cuts:
+                tol, err, ite = self.tol, 2 * self.tol, 0
+                while err > tol and ite < self.maxiter:
                     eps_k, sig_k = eps.copy(), sig.copy()
                     CT, eps_rhs = m.tangent_phase(sig_k, self.T, self.T0, dt_cur, th)
                     self.u = self._solve(CT, eps_rhs, t)
@@ -250,7 +254,7 @@ class OracleSimulatorM:
                     cuts += 1
                     sig, eps = sig_bak.copy(), eps_bak.copy()
                     m.restore(snap)
-                    if cuts <= 3:
+                    if cuts <= self.max_dt_cuts:
                         dt_cur = dt_cur / 2
                     else:
                         sig_k = sig_bak.copy()

@@ -27,3 +27,4 @@ test_krylov_solve_matches_direct = G.test_krylov_solve_matches_direct
 test_time_steps_triaxial_cube_munson_dawson = G.test_time_steps_triaxial_cube_munson_dawson
 test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai = G.test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai
 test_pq_output_fields = G.test_pq_output_fields
+test_dt_retry_and_restore_follow_the_reference = G.test_dt_retry_and_restore_follow_the_reference

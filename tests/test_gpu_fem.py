@@ -250,6 +250,32 @@ def test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai(sf):
         assert osim.mat.elems[1].Fvp.max() > 0, "load path never yields: test is vacuous"
 
 
+def test_dt_retry_and_restore_follow_the_reference(sf):
+    """SURVEY T13 / Simulators.py:378-396, 441-503: a step whose Newton loop does not converge is retried with dt/2
+    (at most 3 cuts) at the SAME target time and boundary values; when every retry fails the internal state is restored
+    and nothing is committed, and the clock still advances.  Forced here by allowing only 2 Newton iterations on the
+    first two steps, then lifting the cap: the run must track the oracle through failure, restore and recovery."""
+    from safeincave_b200 import cases
+    grid = load_grid(sf, "cube_coarse")
+    case = cases.triaxial_case(grid, n_steps=4)
+    eq, sim = cases.build(case, grid)
+    sim.verbose = False
+    osim = oracle_simulator(case, grid.tetmesh)
+    caps = [2, 2, 40, 40]
+    sim.initialize()
+    recs = []
+    for cap in caps:
+        sim.maxiter = cap
+        recs.append(sim.step())
+    orecs = osim.run(0.0, [case["dt"]] * 4, maxiter_list=caps)[1:]
+    assert [r["converged"] for r in recs] == [False, False, True, True]
+    assert [r["converged"] for r in recs] == [o["converged"] for o in orecs]
+    assert [r["iterations"] for r in recs] == [o["iters"] for o in orecs]
+    assert [r["dt_used"] for r in recs] == [o["dt_used"] for o in orecs]
+    assert recs[0]["dt_used"] == case["dt"] / 8                  # three halvings, then give up
+    check_fields(eq, osim, [orecs[-1]])
+
+
 def test_time_steps_cavern_regular(sf):
     """BASELINE config 2: cavern_regular (14 346 cells), fully implicit, cyclic gas pressure."""
     from safeincave_b200 import cases
