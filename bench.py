@@ -380,6 +380,14 @@ def run_b200(args):
                    "algorithmic_bytes": post_bytes},
         "block_jacobi_ms": prof.get("block_jacobi", (0, 0.0))[1] / max(prof.get("block_jacobi", (1, 0))[0], 1),
     }
+    if pc == "mg":       # where a multigrid step goes: per-tangent setup (Galerkin C_T, blocks, lambda_max) vs the Krylov loop
+        n_set, ms_set = prof.get("mg_setup", (0, 0.0))
+        n_sol, ms_sol = prof.get("mg_solve", (0, 0.0))
+        constitutive["mg"] = {"setup_ms_per_tangent": ms_set / max(n_set, 1), "solve_ms_per_tangent": ms_sol / max(n_sol, 1),
+                              "setup_share_of_step_time": ms_set / ms if ms > 0 else None,
+                              "solve_share_of_step_time": ms_sol / ms if ms > 0 else None,
+                              "krylov_iterations_per_solve": ksp_its / max(n_sol, 1),
+                              "lambda_max": eq.mg.lambda_max() if eq.mg is not None else None}
     fp64_peak = eng.fp64_peak()
 
     # ---- end-to-end through the public API with host buffers

@@ -203,10 +203,14 @@ class LinearMomentum(LinearMomentumBase):
             part = getattr(self.grid, "partition", None) if (self.dist is not None and self.dist.world > 1) else None
             self.mg = Multigrid(eng, self.grid.hierarchy, part=part, coarse_fixed=self._coarse_dirichlet_mask,
                                 **self.mg_options)
+        t = eng._tic("mg_setup")
         self.mg.setup(self.fixed, self.dinv)
+        eng._toc(t)
+        t = eng._tic("mg_solve")
         res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
                             check_every=ksp.mg_check_every, guess_nonzero=ksp.initial_guess_nonzero,
                             time_operator=eng.time_operator)
+        eng._toc(t)
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
         return res
