@@ -43,7 +43,7 @@ def eliminated(K, fixed):
 
 
 class OracleMG:
-    def __init__(self, meshes, transfers, CT_fine, fixed_fine, nu=2, coarse_its=20, smooth_lo=0.1, coarse_lo=0.02):
+    def __init__(self, meshes, transfers, CT_fine, fixed_fine, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01):
         """meshes / transfers: safeincave_b200.multigrid.Hierarchy fields; CT_fine (N,6,6); fixed_fine bool (3M,)."""
         from safeincave_b200.multigrid import prolongation_matrix
         n = len(meshes)

@@ -113,7 +113,7 @@ class Multigrid:
     The finest level IS the momentum equation's engine (its C_T is the tangent of the Newton iteration);
     the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
 
-    def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=20, smooth_lo=0.1, coarse_lo=0.02,
+    def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01,
                  safety=1.15, power_its=16, power_its_warm=4, part=None, coarse_fixed=None):
         """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one):
         the finest level is distributed, the coarser ones are replicated on every rank (csrc/mg.cu).
