@@ -276,6 +276,20 @@ int64_t sic_ksp_workspace_doubles(int n_nodes, int method);
 int sic_ksp_solve(const sic_problem_t* p, sic_ksp_t* ksp, const double* b_ext, double* x,
                   const uint8_t* fixed, const double* dinv, double* work, const sic_halo_t* halo, void* stream);
 
+/* Initial guess of the next Krylov solve by extrapolating the Newton iterates of the current time step (the
+ * reference starts every solve from zero, MomentumEquation.py:1023-1025; only the starting point changes, the solve
+ * still runs to rtol).  u0 = latest solution, u1, u2 (, u3) the ones before; n_iterates = 3 or 4.  Writes
+ *   x = u0 + a (u0 - u1) + b (u1 - u2),   (a, b) = least-squares fit of (u0 - u1) by (u1 - u2) and (u2 - u3),
+ * or a = <d1,d0>/<d0,d0>, b = 0 when only the one-term model explains the last increment; a = b = 0 (x = u0) when
+ * neither does, when the prediction is not a contraction, or with three iterates (nothing to validate against).
+ * Several GPUs: inner products use the owner weights of `halo` and are summed over the ranks (same a, b everywhere).
+ * work: sic_guess_workspace_doubles(n_nodes) doubles.  coef_out (host double[5], may be NULL; synchronises):
+ * {a, b, terms used, misfit of the one-term model, misfit of the two-term model}. */
+int64_t sic_guess_workspace_doubles(int n_nodes);
+int sic_guess_extrapolate(int n_nodes, int n_iterates, const double* u0, const double* u1, const double* u2,
+                          const double* u3, double* x, const sic_halo_t* halo, double* work, double* coef_out,
+                          void* stream);
+
 /* ---- part (3b): geometric multigrid preconditioner on a nested red-refinement hierarchy ------------- */
 /* The synthetic 10M-80M cell meshes of BASELINE config 5 are built by regular (Bey) refinement of a gmsh
  * grid, so every level of the hierarchy is available.  P1 spaces on nested meshes are nested, children of a

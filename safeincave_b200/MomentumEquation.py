@@ -98,6 +98,9 @@ class LinearMomentum(LinearMomentumBase):
         self.DG0_6x6, self.V = Space(eng.N, 36, "DG0_6x6"), Space(eng.M, 3, "V")
         self._C_fun = None
         self.mg = None                      # multigrid.Multigrid, built on the first solve with PC type "mg"
+        self._guess_ring, self._guess_n, self._guess_head = None, 0, 0     # last <= 4 Newton iterates of the step
+        self.guess_log = []                 # (a, b, terms) per extrapolated guess when self.guess_debug
+        self.guess_debug = False
         self.mg_options = {}                # nu, coarse_its, smooth_lo, coarse_lo, safety, power_its
 
     # ------------------------------------------------------------------ configuration
@@ -182,16 +185,42 @@ class LinearMomentum(LinearMomentumBase):
         if not ksp.initial_guess_nonzero:
             self.X.zero_()                                   # PETSc default: zero initial guess
         x = self.X.reshape(-1)
+        extrapolate = ksp.initial_guess_nonzero and ksp.guess_extrapolation
+        if extrapolate:
+            if self._guess_n == 0:
+                self._guess_push(x)                          # the step's starting point
+            elif self._guess_n >= 4:
+                coef = eng.guess_extrapolate(self._guess_iterates(), x, want_coef=self.guess_debug)
+                if coef is not None:
+                    self.guess_log.append(coef)
         to.where(self.fixed.bool(), self.u_prescribed, x, out=x)
         rtol, atol, max_it = ksp.effective()
         if ksp.uses_multigrid(self.grid):
-            return self._linear_solve_mg(x, rtol, atol, max_it)
-        eng.block_jacobi(self.dinv, self.fixed)
-        res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
-                            max_it=max_it, check_every=ksp.check_every, guess_nonzero=ksp.initial_guess_nonzero)
-        ksp.record(res)
-        self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+            res = self._linear_solve_mg(x, rtol, atol, max_it)
+        else:
+            eng.block_jacobi(self.dinv, self.fixed)
+            res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
+                                max_it=max_it, check_every=ksp.check_every, guess_nonzero=ksp.initial_guess_nonzero)
+            ksp.record(res)
+            self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+        if extrapolate:
+            self._guess_push(x)
         return res
+
+    # Newton iterates of the current time step, newest first, for the extrapolated Krylov guess
+    def _guess_push(self, x):
+        if self._guess_ring is None:
+            self._guess_ring = [to.empty_like(x) for _ in range(4)]
+        self._guess_head = (self._guess_head + 1) % 4
+        self._guess_ring[self._guess_head].copy_(x)
+        self._guess_n = min(self._guess_n + 1, 4)
+
+    def _guess_iterates(self):
+        return [self._guess_ring[(self._guess_head - k) % 4] for k in range(self._guess_n)]
+
+    def reset_guess_history(self):
+        """A new time step (or a restored one) starts: its iterates do not continue the old sequence."""
+        self._guess_n = 0
 
     def _linear_solve_mg(self, x, rtol, atol, max_it):
         """CG preconditioned by a geometric-multigrid V-cycle on the grid's refinement hierarchy (csrc/mg.cu)."""
@@ -228,7 +257,9 @@ class LinearMomentum(LinearMomentumBase):
         """MomentumEquation.py:892-923."""
         self.engine.elastic_tangent()
         self._elastic_tangent_live = True
+        self.reset_guess_history()
         self._linear_solve()
+        self.reset_guess_history()
 
     def solve(self, stress_k, t, dt):
         """MomentumEquation.py:978-1028: tangent + eps_rhs, assemble, solve, run_after_solve."""
@@ -329,9 +360,11 @@ class LinearMomentum(LinearMomentumBase):
         self._as_field(stress, eng.sig)
         self._as_field(stress_k, eng.sig_k)
         eng.commit(dt, self.theta)
+        self.reset_guess_history()
 
     def commit(self, dt):
         self.engine.commit(dt, self.theta)
+        self.reset_guess_history()
 
     # ------------------------------------------------------------------ dt-retry snapshot
     def save_internal_state(self):
@@ -342,6 +375,7 @@ class LinearMomentum(LinearMomentumBase):
         """MomentumEquation.py:479-494."""
         for e, s in zip(self.engine.elems, self._saved_state):
             e.restore(s)
+        self.reset_guess_history()
 
     # ------------------------------------------------------------------ p / q output fields
     def _pq_fields(self):

@@ -37,6 +37,9 @@ class KSP:
         self.min_max_it = 200000
         self.check_every = 25
         self.initial_guess_nonzero = False
+        # with initial_guess_nonzero: predict the next Newton iterate from the last three differences of the time
+        # step's iterates (sic_guess_extrapolate) instead of starting from the previous one; the solve still runs to rtol
+        self.guess_extrapolation = False
         self.single_reduction = False      # cg -> Chronopoulos-Gear CG; symmetric (elastic) tangents only, see header
         self.mg_max_it, self.mg_check_every = 500, 4
         self._its, self._rnorm, self._reason = 0, 0.0, 0
@@ -70,6 +73,12 @@ class KSP:
 
     def setInitialGuessNonzero(self, flag):
         self.initial_guess_nonzero = bool(flag)
+
+    def setGuessExtrapolation(self, flag):
+        """Not in petsc4py: see ``guess_extrapolation`` above (implies a nonzero initial guess)."""
+        self.guess_extrapolation = bool(flag)
+        if flag:
+            self.initial_guess_nonzero = True
 
     def setOperators(self, *a, **k):
         pass

@@ -32,7 +32,7 @@ EXPORTS = (
     "sic_last_error", "sic_abi_version", "sic_device_info", "sic_tangent", "sic_elastic_tangent",
     "sic_post", "sic_post_blocks", "sic_commit", "sic_commit_rates", "sic_desai_initial_hardening",
     "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
-    "sic_ksp_solve", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
+    "sic_ksp_solve", "sic_guess_workspace_doubles", "sic_guess_extrapolate", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
     "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle",
     "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean", "sic_node_volumes", "sic_pq_fields",
@@ -120,6 +120,10 @@ def declare(lib, single_gpu_only=False):
     lib.sic_ksp_workspace_doubles.argtypes = [c_int, c_int]
     lib.sic_ksp_workspace_doubles.restype = c_int64
     lib.sic_ksp_solve.argtypes = [PP, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p]
+    lib.sic_guess_workspace_doubles.argtypes = [c_int]
+    lib.sic_guess_workspace_doubles.restype = c_int64
+    lib.sic_guess_extrapolate.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, PH, c_void_p,
+                                          POINTER(c_double), c_void_p]
     lib.sic_fp64_peak.argtypes = [POINTER(c_double), c_void_p]
     PL, PO = POINTER(SicMgLevel), POINTER(SicMgOpts)
     lib.sic_mg_workspace_doubles.argtypes = [c_int, c_int]

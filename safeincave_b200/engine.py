@@ -368,6 +368,21 @@ class Engine:
         self.op_launches += (2 if method == L.KSP_BICGSTAB else 1) * int(ksp.iterations)
         return ksp
 
+    def guess_extrapolate(self, iterates, x, want_coef=False):
+        """x <- prediction of the next Newton iterate from ``iterates`` = [u0 (latest), u1, u2(, u3)]
+        (sic_guess_extrapolate).  Returns (a, b, terms, misfit1, misfit2) if want_coef (synchronises) else None."""
+        n = len(iterates)
+        need = int(self.lib.sic_guess_workspace_doubles(self.M))
+        w = getattr(self, "_guess_work", None)
+        if w is None or w.numel() < need:
+            w = self._guess_work = torch.zeros(need, dtype=torch.float64, device=self.device)
+        coef = (ctypes.c_double * 5)() if want_coef else None
+        L.check(self.lib.sic_guess_extrapolate(self.M, n, _ptr(iterates[0]), _ptr(iterates[1]), _ptr(iterates[2]),
+                                               _ptr(iterates[3]) if n > 3 else None, _ptr(x), self._ph(), _ptr(w),
+                                               coef, self._stream()), "sic_guess_extrapolate")
+        self.launches += 2 + (2 if self.halo is not None else 0)
+        return (coef[0], coef[1], int(coef[2]), coef[3], coef[4]) if want_coef else None
+
     def fp64_peak(self):
         out = ctypes.c_double(0.0)
         L.check(self.lib.sic_fp64_peak(ctypes.byref(out), self._stream()), "sic_fp64_peak")

@@ -144,3 +144,33 @@ def check_mg_equals_block_jacobi(sf, name, levels, case_fn, n_steps=1, tol=1e-8,
     assert relerr(em.X.reshape(-1).cpu().numpy(), ej.X.reshape(-1).cpu().numpy()) < tol
     assert relerr(em.engine.get6(em.engine.sig), ej.engine.get6(ej.engine.sig)) < tol
     return max(k[0] for k in em.ksp_log), max(k[0] for k in ej.ksp_log)
+
+
+def recurrence_sequence(n_nodes, lam=(0.7, 0.25), n_iter=4, seed=5, device="cpu"):
+    """Iterates u_k = u* + lam1^k v1 + lam2^k v2 (a two-mode linear recurrence): the next one is predicted exactly."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ustar, v1, v2 = (torch.randn(n_nodes, 3, generator=g, dtype=torch.float64) for _ in range(3))
+    seq = [ustar + lam[0] ** k * v1 + lam[1] ** k * v2 for k in range(n_iter + 1)]
+    return [u.to(device) for u in seq]       # seq[-1] is the iterate to predict from seq[:-1]
+
+
+def check_guess_extrapolation(engine, seq, local_nodes=None):
+    """sic_guess_extrapolate on the last four iterates of `seq[:-1]` must return seq[-1] (two-term model), fall back to the
+    one-term model on a one-mode sequence and to the plain warm start on a sequence that is no recurrence at all."""
+    import torch
+    pick = (lambda u: u[local_nodes].contiguous().reshape(-1)) if local_nodes is not None else (lambda u: u.contiguous().reshape(-1))
+    its = [pick(u) for u in seq[:-1]][::-1][:4]           # newest first
+    x = torch.empty_like(its[0])
+    a, b, used, f1, f2 = engine.guess_extrapolate(its, x, want_coef=True)
+    assert used == 2 and f2 < 1e-20, (a, b, used, f1, f2)
+    assert abs(a - 0.95) < 1e-9 and abs(b + 0.175) < 1e-9, (a, b)      # lam1 + lam2, -lam1 lam2
+    assert relerr(x.cpu().numpy(), pick(seq[-1]).cpu().numpy()) < 1e-12
+    # no validation possible with three iterates: plain warm start
+    a3 = engine.guess_extrapolate(its[:3], x, want_coef=True)
+    assert a3[2] == 0 and torch.equal(x, its[0])
+    # a sequence that stops dead (the uniform triaxial cube): d1 is not explained by the earlier increments
+    dead = [its[1] + 1e-3 * torch.roll(its[3], 7), its[1], its[2], its[3]]
+    ad = engine.guess_extrapolate(dead, x, want_coef=True)
+    assert ad[2] == 0 and torch.equal(x, dead[0]), ad
+    return a, b

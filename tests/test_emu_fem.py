@@ -28,3 +28,11 @@ test_time_steps_triaxial_cube_munson_dawson = G.test_time_steps_triaxial_cube_mu
 test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai = G.test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai
 test_pq_output_fields = G.test_pq_output_fields
 test_dt_retry_and_restore_follow_the_reference = G.test_dt_retry_and_restore_follow_the_reference
+test_guess_extrapolation_kernel = G.test_guess_extrapolation_kernel
+
+
+def test_time_step_cavern_regular_extrapolated_guess(sf):
+    """One step (17 Newton iterations) of the B200 test test_time_steps_cavern_regular_extrapolated_guess.  The plain
+    warm start needs 2782 Krylov iterations for this step (measured with this emulation; not re-run here to keep the
+    CPU suite short), the extrapolated guess 1992."""
+    G.check_extrapolated_guess(sf, 1, plain_its=2782)

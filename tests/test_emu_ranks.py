@@ -99,3 +99,30 @@ def test_bench_multigrid_probe_on_emulated_ranks(sf):
     finally:
         hostemu.load().sic_emu_set_timeout(120)
     assert not any(ok for ok, _ in res), res
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_guess_extrapolation_same_coefficients_on_every_rank(sf, world):
+    """sic_guess_extrapolate (solver.cu): exact on a two-mode recurrence; on several ranks the inner products use owner
+    weights and are summed in the exchange, so every rank applies the single-rank coefficients."""
+    from safeincave_b200 import cases, distributed
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    from tests.hostemu.ranks import run_ranks
+    from tests import mg_checks as C
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz")), 1)
+    tm = h.finest
+    gg = sf.GridHandlerGMSH.from_hierarchy(h)
+    case = cases.triaxial_case(gg, n_steps=1, ksp_override="cg")
+    seq = C.recurrence_sequence(tm.n_nodes)
+
+    def body(ctx):
+        if ctx.world == 1:
+            eq, _ = cases.build(case, gg)
+            return C.check_guess_extrapolation(eq.engine, seq)
+        grid, part = distributed.partition_grid(ctx, tm)
+        eq, _ = cases.build(case, grid, part=part, ctx=ctx)
+        return C.check_guess_extrapolation(eq.engine, seq, part.local_nodes)
+
+    res = run_ranks(world, body)
+    assert all(r == res[0] for r in res)

@@ -294,6 +294,38 @@ def test_time_steps_cavern_regular_warm_started_cg(sf):
     check_fields(eq, osim, ohist)
 
 
+def check_extrapolated_guess(sf, n_steps, plain_its=None):
+    """Krylov guess extrapolated from the Newton iterates of the step (sic_guess_extrapolate): same Newton history and
+    fields as the oracle's direct solves, and clearly fewer Krylov iterations than the plain warm start."""
+    from safeincave_b200 import cases
+    eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, n_steps, ksp_type="cg",
+                                          solver_opts=dict(initial_guess_nonzero=True, guess_extrapolation=True))
+    assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
+    check_fields(eq, osim, ohist)
+    its, its2 = sum(k[0] for k in eq.ksp_log), plain_its
+    if plain_its is None:
+        grid = load_grid(sf, "cavern_regular", 0)
+        eq2, sim2 = cases.build(cases.cavern_case(grid, n_steps=n_steps, ksp_type="cg"), grid)
+        eq2.solver.initial_guess_nonzero = True
+        sim2.run()
+        its2 = sum(k[0] for k in eq2.ksp_log)
+    assert all(k[1] > 0 for k in eq.ksp_log)
+    assert its < 0.8 * its2, f"extrapolated guess: {its} Krylov iterations, plain warm start: {its2}"
+    return its, its2
+
+
+def test_guess_extrapolation_kernel(sf):
+    from safeincave_b200 import cases
+    from tests import mg_checks as C
+    grid = load_grid(sf, "cube_coarse", 1)
+    eq, _ = cases.build(cases.triaxial_case(grid, n_steps=1), grid)
+    C.check_guess_extrapolation(eq.engine, C.recurrence_sequence(eq.engine.M, device=eq.engine.device))
+
+
+def test_time_steps_cavern_regular_extrapolated_guess(sf):
+    check_extrapolated_guess(sf, 2)
+
+
 def test_time_step_cavern_regular_config3_desai_pressure_solution(sf):
     """BASELINE config 3 physics on cavern_regular: Spring + Kelvin + DislocationCreep + PressureSolutionCreep +
     ViscoplasticDesai with compute_initial_hardening after the elastic response (theta = 0.5)."""
