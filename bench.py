@@ -42,9 +42,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ksp", default="cg")
     ap.add_argument("--rtol", type=float, default=1e-10)
-    ap.add_argument("--warm-start", type=int, default=1,
-                    help="1: Krylov initial guess = previous Newton iterate (KSP.setInitialGuessNonzero), rtol still "
-                         "relative to the zero-guess residual as in PETSc; 0: zero guess every solve")
+    ap.add_argument("--warm-start", type=int, default=2,
+                    help="2: Krylov initial guess extrapolated from the Newton iterates of the time step "
+                         "(sic_guess_extrapolate; falls back to 1 whenever the iterates are not a linear recurrence); "
+                         "1: guess = previous Newton iterate (KSP.setInitialGuessNonzero); 0: zero guess every solve.  "
+                         "rtol is always relative to the zero-guess residual, as in PETSc")
     ap.add_argument("--cgcg", type=int, default=0,
                     help="1: Chronopoulos-Gear CG (one reduction per iteration); only sound for SYMMETRIC tangents -- it "
                          "diverges on the reference's non-symmetric finite-difference tangent (SURVEY T3), hence off")
@@ -317,6 +319,7 @@ def run_b200(args):
     if pc == "mg":
         eq.solver.getPC().setType("mg")
     eq.solver.initial_guess_nonzero = bool(args.warm_start)
+    eq.solver.guess_extrapolation = args.warm_start >= 2
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
         eq.solver.respect_max_it, eq.solver.max_it = True, args.max_it
@@ -443,7 +446,8 @@ def run_b200(args):
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
                    "preconditioner": ("geometric multigrid V(2,2), Chebyshev/block-Jacobi smoother, Galerkin coarse tangents, "
                                       f"{args.levels + 1} levels") if pc == "mg" else "nodal 3x3 block Jacobi",
-                   "pc_choice": pc_why, "warm_start": bool(args.warm_start),
+                   "pc_choice": pc_why, "warm_start": {0: "zero guess", 1: "previous Newton iterate"}.get(
+                       args.warm_start, "extrapolated from the step's Newton iterates (sic_guess_extrapolate)"),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
         "clocks": clk, "gpu_launches": launches, "roofline": roofline, "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,

@@ -27,6 +27,7 @@ class Simulator_M(Simulator):
         self.outputs = outputs if outputs is not None else []
         self.compute_elastic_response = compute_elastic_response
         self.verbose = verbose
+        self.screen = None       # ScreenOutput.ScreenPrinter, created by run() when verbose (Simulators.py:307-308)
         self.tol, self.maxiter, self.max_dt_cuts = 1e-8, 40, 3
         self.history = []        # one dict per time step: iterations, error, converged, ksp iterations, seconds
         # optional callable(eq_mom, stress) run right after the initial stress is known and before the
@@ -125,15 +126,20 @@ class Simulator_M(Simulator):
 
     def run(self):
         tc = self.t_control
+        if self.verbose:        # report header, time-step table and log.txt as the reference prints them
+            from .ScreenOutput import ScreenPrinter
+            ScreenPrinter.reset_instance()
+            self.screen = ScreenPrinter(self.eq_mom.grid, self.eq_mom.solver, self.eq_mom.mat, self.outputs, tc.time_unit)
         self.initialize()
-        if self.verbose:
-            self._print(f"{'step':>6} {'dt':>10} {'t / t_final':>24} {'iters':>6} {'error':>12} {'ksp its':>8}")
         while tc.keep_looping():
             rec = self.step()
             self._save(rec["t"])
-            self._print(f"{rec['step']:>6d} {tc.dt / tc.time_conversion:>10.4f} "
-                        f"{rec['t'] / tc.time_conversion:>11.3f} / {tc.t_final / tc.time_conversion:<10.3f} "
-                        f"{rec['iterations']:>6d} {rec['error']:>12.4e} {rec['ksp_iterations']:>8d}")
+            if self.screen is not None:     # Simulators.py:527-536
+                current_time = "%.3f" % (rec["t"] / tc.time_conversion)
+                self.screen.print_row([tc.step_counter, tc.dt / tc.time_conversion,
+                                       f"{current_time} / {tc.t_final / tc.time_conversion}", rec["iterations"], rec["error"]])
+        if self.screen is not None:
+            self.screen.close()
         for output in self.outputs:
             if hasattr(output, "save_mesh"):
                 output.save_mesh()
@@ -216,15 +222,22 @@ class Simulator_TM(Simulator):
 
     def run(self):
         tc = self.t_control
+        screen = None
+        if self.verbose:        # Simulators.py:89-90: the momentum equation's grid, solver and material are reported
+            from .ScreenOutput import ScreenPrinter
+            ScreenPrinter.reset_instance()
+            screen = self.screen = ScreenPrinter(self.eq_mom.grid, self.eq_mom.solver, self.eq_mom.mat, self.outputs,
+                                                 tc.time_unit)
         self.initialize()
         while tc.keep_looping():
             rec = self.step()
             self._save(rec["t"])
-            if self.verbose and self.eq_mom.grid.mesh.comm.rank == 0:
-                print(f"{rec['step']:>6d} {tc.dt / tc.time_conversion:>10.4f} {rec['t'] / tc.time_conversion:>11.3f} / "
-                      f"{tc.t_final / tc.time_conversion:<10.3f} {rec['iterations']:>6d} {rec['error']:>12.4e} "
-                      f"{rec['ksp_iterations']:>8d} {rec['heat_iterations']:>5d}")
-                sys.stdout.flush()
+            if screen is not None:          # Simulators.py:257-265
+                current_time = "%.3f" % (rec["t"] / tc.time_conversion)
+                screen.print_row([tc.step_counter, tc.dt / tc.time_conversion,
+                                  f"{current_time} / {tc.t_final / tc.time_conversion}", rec["iterations"], rec["error"]])
+        if screen is not None:
+            screen.close()
         for output in self.outputs:
             if hasattr(output, "save_mesh"):
                 output.save_mesh()

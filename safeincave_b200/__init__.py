@@ -15,4 +15,5 @@ from .Simulators import Simulator_M, Simulator_TM  # noqa: F401
 from .TimeHandler import TimeControllerBase, TimeController, TimeControllerParabolic  # noqa: F401
 from .Solver import KSP, PETSc  # noqa: F401
 from .OutputHandler import SaveFields  # noqa: F401
+from .ScreenOutput import ScreenPrinter  # noqa: F401
 from . import HeatBC, MomentumBC, Utils  # noqa: F401

@@ -61,13 +61,13 @@ def _missing(name):
 def install(force=False):
     """Register the stand-ins in ``sys.modules`` (idempotent).  Returns the list of names that were registered."""
     import safeincave_b200 as sf
-    from . import Grid, HeatBC, HeatEquation, MaterialProps, MomentumBC, MomentumEquation, OutputHandler, Simulators, \
-        Solver, TimeHandler, Utils
+    from . import Grid, HeatBC, HeatEquation, MaterialProps, MomentumBC, MomentumEquation, OutputHandler, ScreenOutput, \
+        Simulators, Solver, TimeHandler, Utils
     done = []
     if force or "safeincave" not in sys.modules and _missing("safeincave"):
         sys.modules["safeincave"] = sf
-        for m in (Grid, HeatBC, HeatEquation, MaterialProps, MomentumBC, MomentumEquation, OutputHandler, Simulators,
-                  Solver, TimeHandler, Utils):
+        for m in (Grid, HeatBC, HeatEquation, MaterialProps, MomentumBC, MomentumEquation, OutputHandler, ScreenOutput,
+                  Simulators, Solver, TimeHandler, Utils):
             sys.modules["safeincave." + m.__name__.rsplit(".", 1)[1]] = m
         done.append("safeincave")
     if force or _missing("petsc4py"):
