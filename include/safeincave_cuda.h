@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 11
+#define SIC_ABI_VERSION 12
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 

@@ -99,6 +99,7 @@ class LinearMomentum(LinearMomentumBase):
         self._C_fun = None
         self.mg = None                      # multigrid.Multigrid, built on the first solve with PC type "mg"
         self._guess_ring, self._guess_n, self._guess_head = None, 0, 0     # last <= 4 Newton iterates of the step
+        self._solves_in_step, self._last_newton_error = 0, -1.0            # for the lagged multigrid setup (Solver.KSP)
         self.guess_log = []                 # (a, b, terms) per extrapolated guess when self.guess_debug
         self.guess_debug = False
         self.mg_options = {}                # nu, coarse_its, smooth_lo, coarse_lo, safety, power_its
@@ -221,6 +222,7 @@ class LinearMomentum(LinearMomentumBase):
     def reset_guess_history(self):
         """A new time step (or a restored one) starts: its iterates do not continue the old sequence."""
         self._guess_n = 0
+        self._solves_in_step, self._last_newton_error = 0, -1.0
 
     def _linear_solve_mg(self, x, rtol, atol, max_it):
         """CG preconditioned by a geometric-multigrid V-cycle on the grid's refinement hierarchy (csrc/mg.cu)."""
@@ -232,9 +234,13 @@ class LinearMomentum(LinearMomentumBase):
             part = getattr(self.grid, "partition", None) if (self.dist is not None and self.dist.world > 1) else None
             self.mg = Multigrid(eng, self.grid.hierarchy, part=part, coarse_fixed=self._coarse_dirichlet_mask,
                                 **self.mg_options)
-        t = eng._tic("mg_setup")
-        self.mg.setup(self.fixed, self.dinv)
-        eng._toc(t)
+        lag = ksp.mg_setup_first > 0 and self.mg.setups > 0 and not self._elastic_tangent_live \
+            and self._solves_in_step >= ksp.mg_setup_first and 0.0 <= self._last_newton_error <= ksp.mg_setup_error
+        if not lag:
+            t = eng._tic("mg_setup")
+            self.mg.setup(self.fixed, self.dinv)
+            eng._toc(t)
+        self._solves_in_step += 1
         t = eng._tic("mg_solve")
         res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
                             check_every=ksp.mg_check_every, guess_nonzero=ksp.initial_guess_nonzero,
@@ -333,8 +339,11 @@ class LinearMomentum(LinearMomentumBase):
             self.dist.all_reduce_sum(eng.err_out)
         num, den = eng.err_out.tolist()                      # device -> host read of the step result
         if den == 0.0:
-            return float("nan") if num != 0.0 else 0.0
-        return float(np.sqrt(num) / np.sqrt(den))
+            err = float("nan") if num != 0.0 else 0.0
+        else:
+            err = float(np.sqrt(num) / np.sqrt(den))
+        self._last_newton_error = err if err == err else -1.0
+        return err
 
     def begin_iteration(self):
         """eps_tot_k <- eps_tot, stress_k <- stress (Simulators.py:407-410) by swapping buffers."""

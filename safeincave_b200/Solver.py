@@ -42,6 +42,11 @@ class KSP:
         self.guess_extrapolation = False
         self.single_reduction = False      # cg -> Chronopoulos-Gear CG; symmetric (elastic) tangents only, see header
         self.mg_max_it, self.mg_check_every = 500, 4
+        # PC mg: rebuild the preconditioner (Galerkin coarse tangents, block-Jacobi blocks, lambda_max) only on the
+        # first `mg_setup_first` Newton iterations of a time step and afterwards only while the Newton error is above
+        # `mg_setup_error`; in between the previous tangent's preconditioner is kept (the Krylov operator itself is
+        # always the current tangent, so only the convergence RATE can change).  0: rebuild for every tangent.
+        self.mg_setup_first, self.mg_setup_error = 0, 1e-3
         self._its, self._rnorm, self._reason = 0, 0.0, 0
         self.total_iterations = 0
 

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 11
+SIC_ABI_VERSION = 12
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
