@@ -55,6 +55,9 @@ def parse():
                     help="preconditioner of the Krylov solve: mg = geometric multigrid V-cycle on the refinement hierarchy "
                          "(csrc/mg.cu, single GPU), jacobi = nodal 3x3 block Jacobi; auto = mg when a probe solve on a "
                          "smaller mesh (run in a child process) reproduces the block-Jacobi solution, else jacobi")
+    ap.add_argument("--mg-lag", type=int, default=2,
+                    help="PC mg: rebuild the preconditioner on the first MG_LAG Newton iterations of a time step and "
+                         "afterwards only while the Newton error is above 1e-3 (KSP.mg_setup_first); 0: for every tangent")
     ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -178,7 +181,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # multigrid probe: does the V-cycle preconditioned CG reproduce the block-Jacobi CG solution on this box?
 # ----------------------------------------------------------------------------------------------
-def probe_mg(levels=2, device="cuda:0"):
+def apply_solver_settings(solver, warm_start, mg_lag):
+    """The Krylov settings of the timed run (also used by the multigrid probes, so that they test what is timed)."""
+    solver.initial_guess_nonzero = bool(warm_start)
+    solver.guess_extrapolation = warm_start >= 2
+    solver.mg_setup_first = int(mg_lag)
+
+
+def probe_mg(levels=2, device="cuda:0", warm_start=2, mg_lag=2):
     """Elastic response of the cavern case on cavern_regular x8^levels with both preconditioners (both are this
     repo's CUDA paths).  Prints MG_PROBE_OK / MG_PROBE_FAIL; run in a child process so that a device fault in the
     newer code path cannot take the benchmark down with it."""
@@ -195,6 +205,7 @@ def probe_mg(levels=2, device="cuda:0"):
     for pc in ("jacobi", "mg"):
         eq, sim = cases.build(case, grid, device=dev)
         eq.solver.getPC().setType("mg" if pc == "mg" else "asm")
+        apply_solver_settings(eq.solver, warm_start, mg_lag)
         sim.verbose = False
         sim.initialize()
         rec = sim.step()
@@ -211,7 +222,7 @@ def probe_mg(levels=2, device="cuda:0"):
     return 0 if ok else 1
 
 
-def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None):
+def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None, warm_start=2, mg_lag=2):
     """The same comparison as probe_mg for a run on several GPUs, IN PROCESS and collectively: one time step of the
     cavern case on cavern_regular x8^levels, partitioned over the ranks, with block-Jacobi CG and with the multigrid
     CG (finest level distributed, coarser levels replicated).  Every rank compares its own part; the verdict is the
@@ -232,6 +243,7 @@ def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None):
             eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
             if pc == "mg":
                 eq.solver.getPC().setType("mg")
+            apply_solver_settings(eq.solver, warm_start, mg_lag)
             sim.verbose = False
             sim.initialize()
             rec = sim.step()
@@ -259,12 +271,12 @@ def decide_pc(args, world, note, ctx=None):
     if args.levels < 1 or args.ksp != "cg":
         return "jacobi", "no refinement hierarchy / KSP type is not cg"
     if world > 1:
-        ok, msg = probe_mg_ranks(ctx)
+        ok, msg = probe_mg_ranks(ctx, warm_start=args.warm_start, mg_lag=args.mg_lag)
         note(f"multigrid probe on {world} ranks: {msg}")
         return ("mg" if ok else "jacobi"), msg
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-mg"], capture_output=True, text=True,
-                           timeout=900)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-mg", "--warm-start", str(args.warm_start),
+                            "--mg-lag", str(args.mg_lag)], capture_output=True, text=True, timeout=900)
         tail = [ln for ln in r.stdout.splitlines() if ln.startswith("MG_PROBE")]
         msg = tail[-1] if tail else f"probe exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] }"
         note(f"multigrid probe: {msg}")
@@ -318,8 +330,7 @@ def run_b200(args):
     sim.verbose = False
     if pc == "mg":
         eq.solver.getPC().setType("mg")
-    eq.solver.initial_guess_nonzero = bool(args.warm_start)
-    eq.solver.guess_extrapolation = args.warm_start >= 2
+    apply_solver_settings(eq.solver, args.warm_start, args.mg_lag)
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
         eq.solver.respect_max_it, eq.solver.max_it = True, args.max_it
@@ -390,6 +401,7 @@ def run_b200(args):
                               "setup_share_of_step_time": ms_set / ms if ms > 0 else None,
                               "solve_share_of_step_time": ms_sol / ms if ms > 0 else None,
                               "krylov_iterations_per_solve": ksp_its / max(n_sol, 1),
+                              "setups": n_set, "solves": n_sol, "setup_lag": args.mg_lag,
                               "lambda_max": eq.mg.lambda_max() if eq.mg is not None else None}
     fp64_peak = eng.fp64_peak()
 
@@ -467,7 +479,7 @@ def run_b200(args):
 if __name__ == "__main__":
     a = parse()
     if a.probe_mg:
-        sys.exit(probe_mg())
+        sys.exit(probe_mg(warm_start=a.warm_start, mg_lag=a.mg_lag))
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -10,6 +10,7 @@ here with this repository's own MSH reader (safeincave_b200/mesh.py) and stored 
     tests/files/cube_coarse/geom.msh          -> tests/golden/mesh_cube_coarse.npz      (23 nodes / 48 tets, MSH 2.2)
     grids/cavern_regular/geom.msh             -> tests/golden/mesh_cavern_regular.npz   (3577 / 14346, MSH 4.1)
     grids/cavern_overburden_coarse/geom.msh   -> tests/golden/mesh_cavern_overburden_coarse.npz (5916 / 25608, MSH 2.2)
+    grids/cavern_irregular_finemesh/geom.msh  -> tests/golden/mesh_cavern_irregular_finemesh.npz (BASELINE configs[2])
 """
 import os
 import sys
@@ -23,6 +24,7 @@ JOBS = [
     ("tests/files/cube_coarse/geom.msh", "mesh_cube_coarse.npz"),
     ("grids/cavern_regular/geom.msh", "mesh_cavern_regular.npz"),
     ("grids/cavern_overburden_coarse/geom.msh", "mesh_cavern_overburden_coarse.npz"),
+    ("grids/cavern_irregular_finemesh/geom.msh", "mesh_cavern_irregular_finemesh.npz"),
 ]
 
 if __name__ == "__main__":

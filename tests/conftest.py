@@ -31,7 +31,8 @@ _FIRST_TIME_ON_GPU = (
     "test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai", "test_dt_retry_and_restore_follow_the_reference",
     "test_heat_steps_cube", "test_heat_steps_cavern_regular", "test_thermomechanical_steps_cube",
     "test_thermomechanical_step_cavern_regular", "test_time_steps_cavern_regular_extrapolated_guess",
-    "test_guess_extrapolation_kernel",
+    "test_guess_extrapolation_kernel", "test_lagged_multigrid_setup",
+    "test_operator_rhs_blocks_strain_configs2_grid",
 )
 
 

@@ -20,6 +20,7 @@ def sf():
 
 
 test_operator_rhs_blocks_strain = G.test_operator_rhs_blocks_strain
+test_operator_rhs_blocks_strain_configs2_grid = G.test_operator_rhs_blocks_strain_configs2_grid
 test_neumann_and_body_force = G.test_neumann_and_body_force
 test_time_steps_triaxial_cube = G.test_time_steps_triaxial_cube
 test_time_steps_triaxial_cube_with_desai = G.test_time_steps_triaxial_cube_with_desai

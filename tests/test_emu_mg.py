@@ -37,3 +37,7 @@ def test_setup_vcycle_solve_cavern_regular(sf):
 def test_time_steps_cube_mg_equals_block_jacobi(sf):
     from safeincave_b200 import cases
     C.check_mg_equals_block_jacobi(sf, "cube_coarse", 2, cases.triaxial_case, n_steps=2, ksp_override="cg")
+
+
+def test_lagged_multigrid_setup(sf):
+    C.check_lagged_setup(sf)

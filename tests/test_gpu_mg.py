@@ -38,3 +38,7 @@ def test_time_step_cavern_regular_mg_equals_block_jacobi(sf):
     from safeincave_b200 import cases
     its_mg, its_bj = C.check_mg_equals_block_jacobi(sf, "cavern_regular", 1, cases.cavern_case)
     assert its_mg <= 40 and its_bj > 10 * its_mg
+
+
+def test_lagged_multigrid_setup(sf):
+    C.check_lagged_setup(sf)
