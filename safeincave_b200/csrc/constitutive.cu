@@ -150,11 +150,13 @@ __device__ __forceinline__ void md_linearise(const double sig_k[6], double T, do
 
 // =============================================================================================
 // tangent phase: LinearMomentum.compute_CT + compute_eps_rhs (MomentumEquation.py:799-820, 868-890)
-// EXT = false: the elements of BASELINE configs 1-4; EXT = true adds the SURVEY 8f elements (the host
-// picks the instantiation from the material, so the configs that do not use them run unchanged code).
+// SET (sic_element_set): 0 = Kelvin / DislocationCreep / PressureSolutionCreep, 1 = + ViscoplasticDesai (together the
+// elements of BASELINE configs 1-4), 2 = + the SURVEY 8f elements; the host picks the instantiation from the material.
 // =============================================================================================
-template <bool EXT>
-__global__ void __launch_bounds__(SIC_CELL_THREADS) k_tangent(sic_problem_t P, double dt, double theta) {
+// SET 0: 168 registers (3 resident CTAs per SM) at the price of 72 bytes of spills; the larger sets need all 255.
+template <int SET>
+__global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(sic_problem_t P, double dt, double theta) {
+  constexpr bool DESAI = SET >= 1, EXT = SET >= 2;   // element set of the instantiation (see sic_element_set)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
   const int ns = P.cell_stride;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_tangent(sic_problem_t P, d
       PressureSolP pp{row[off], row[off + 1], row[off + 2]};
       fd_columns([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk,
                  [&](int k, const double* col) { add_col(G, k, col); });
-    } else if (el.kind == SIC_ELEM_DESAI) {
+    } else if (DESAI && el.kind == SIC_ELEM_DESAI) {
       DesaiP dp = load_desai(row, off);
       double* ds = el.desai;
       const double alpha = ds[(size_t)SIC_DS_ALPHA * ns + i];
@@ -348,10 +350,11 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_elastic_tangent(sic_proble
 // =============================================================================================
 // post-solve phase of one Newton iteration (Simulators.py:416-436)
 // =============================================================================================
-template <bool EXT>
+template <int SET>
 __global__ void __launch_bounds__(SIC_CELL_THREADS) k_post(sic_problem_t P, const double* __restrict__ u, double dt,
                                                           double theta, double kelvin_phi2, int flags,
                                                           double* __restrict__ err_scratch) {
+  constexpr bool DESAI = SET >= 1, EXT = SET >= 2;   // element set of the instantiation (see sic_element_set)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int ns = P.cell_stride;
   const bool live = i < P.n_cells;
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_post(sic_problem_t P, cons
         const sic_elem_t& el = P.elems[e];
         const int off = el.param_off;
         double rate[6];
-        if (el.kind == SIC_ELEM_DESAI) {
+        if (DESAI && el.kind == SIC_ELEM_DESAI) {
           DesaiP dp = load_desai(row, off);
           double* ds = el.desai;
           double alpha = ds[(size_t)SIC_DS_ALPHA * ns + i];
@@ -533,8 +536,9 @@ __global__ void k_post_err_final(const double* __restrict__ scratch, int n_block
 // =============================================================================================
 // commit of a converged step (Simulators.py:509-517)
 // =============================================================================================
-template <bool EXT>
+template <int SET>
 __global__ void __launch_bounds__(SIC_CELL_THREADS) k_commit(sic_problem_t P, double dt, double theta) {
+  constexpr bool DESAI = SET >= 1, EXT = SET >= 2;   // element set of the instantiation (see sic_element_set)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
   const int ns = P.cell_stride;
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_commit(sic_problem_t P, do
     } else if (el.kind == SIC_ELEM_PRESSURE_SOL) {
       PressureSolP pp{row[off], row[off + 1], row[off + 2]};
       fd_columns([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk, acc);
-    } else if (el.kind == SIC_ELEM_DESAI) {
+    } else if (DESAI && el.kind == SIC_ELEM_DESAI) {
       DesaiP dp = load_desai(row, off);
       double* ds = el.desai;
       DesaiLin L;
@@ -718,18 +722,31 @@ static int check_problem(const sic_problem_t* p) {
 
 static inline int cell_blocks(int n) { return (n + SIC_CELL_THREADS - 1) / SIC_CELL_THREADS; }
 
-// does the material use one of the SURVEY 8f elements (-> the EXT instantiations of the kernels)?
-static inline bool has_ext(const sic_problem_t* p) {
-  for (int e = 0; e < p->n_elems; ++e)
-    if (p->elems[e].kind > SIC_ELEM_DESAI) return true;
-  return false;
+// Which instantiation of k_tangent / k_post / k_commit a material runs: 0 = Kelvin / DislocationCreep /
+// PressureSolutionCreep only (BASELINE configs 1-2 and the bench), 1 = + ViscoplasticDesai (configs 3-4), 2 = + the
+// SURVEY 8f elements.  The smaller sets are the same code with the unused branches compiled out: fewer registers
+// (the Desai linearisation is what pushes the full kernels to 255 registers with spills), hence more resident warps.
+static inline int sic_element_set(const sic_problem_t* p) {
+  int set = 0;
+  for (int e = 0; e < p->n_elems; ++e) {
+    if (p->elems[e].kind > SIC_ELEM_DESAI) return 2;
+    if (p->elems[e].kind == SIC_ELEM_DESAI) set = 1;
+  }
+  return set;
 }
+#define SIC_LAUNCH_SET(kernel, p, grid, stream, ...)                                                     \
+  do {                                                                                                   \
+    switch (sic_element_set(p)) {                                                                        \
+      case 0: kernel<0><<<grid, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break;        \
+      case 1: kernel<1><<<grid, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break;        \
+      default: kernel<2><<<grid, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); break;       \
+    }                                                                                                    \
+  } while (0)
 
 extern "C" int sic_tangent(const sic_problem_t* p, double dt, double theta, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (p->n_cells == 0) return 0;
-  if (has_ext(p)) k_tangent<true><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
-  else k_tangent<false><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  SIC_LAUNCH_SET(k_tangent, p, cell_blocks(p->n_cells), stream, *p, dt, theta);
   return sic_check_launch("k_tangent");
 }
 
@@ -750,8 +767,7 @@ extern "C" int sic_post(const sic_problem_t* p, const double* u, double dt, doub
     return sic_fail("sic_post: SIC_POST_ERROR needs SIC_POST_STRAIN, err_out and err_scratch");
   if (p->n_cells == 0) return 0;
   const int nb = cell_blocks(p->n_cells);
-  if (has_ext(p)) k_post<true><<<nb, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, u, dt, theta, kelvin_phi2, flags, err_scratch);
-  else k_post<false><<<nb, SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, u, dt, theta, kelvin_phi2, flags, err_scratch);
+  SIC_LAUNCH_SET(k_post, p, nb, stream, *p, u, dt, theta, kelvin_phi2, flags, err_scratch);
   if (int rc = sic_check_launch("k_post")) return rc;
   if (flags & SIC_POST_ERROR) {
     k_post_err_final<<<1, 1024, 0, (cudaStream_t)stream>>>(err_scratch, nb, err_out);
@@ -763,8 +779,7 @@ extern "C" int sic_post(const sic_problem_t* p, const double* u, double dt, doub
 extern "C" int sic_commit(const sic_problem_t* p, double dt, double theta, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (p->n_cells == 0 || p->n_elems == 0) return 0;
-  if (has_ext(p)) k_commit<true><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
-  else k_commit<false><<<cell_blocks(p->n_cells), SIC_CELL_THREADS, 0, (cudaStream_t)stream>>>(*p, dt, theta);
+  SIC_LAUNCH_SET(k_commit, p, cell_blocks(p->n_cells), stream, *p, dt, theta);
   return sic_check_launch("k_commit");
 }
 
