@@ -67,6 +67,19 @@ class _Geometry:
         self.x = x
 
 
+class _MeshTags:
+    """Stand-in for dolfinx.mesh.MeshTags (what get_boundaries / get_subdomains return, Grid.py:392-412): entity
+    indices and their gmsh physical tags, in THIS package's entity numbering."""
+
+    def __init__(self, dim, indices, values):
+        self.dim = dim
+        self.indices = np.asarray(indices, dtype=np.int32)
+        self.values = np.asarray(values, dtype=np.int32)
+
+    def find(self, tag):
+        return self.indices[self.values == tag]
+
+
 class _Mesh:
     def __init__(self, coords, cells):
         self.geometry = _Geometry(coords)
@@ -117,6 +130,12 @@ class GridHandlerGMSH:
         return grid
 
     # --- tag queries (Grid.py:392-494)
+    def get_boundaries(self):
+        return _MeshTags(2, np.arange(self.tetmesh.tris.shape[0]), self.tetmesh.tri_tags)
+
+    def get_subdomains(self):
+        return _MeshTags(3, np.arange(self.tetmesh.n_cells), self.tetmesh.cell_tags)
+
     def get_boundary_names(self):
         return list(self.dolfin_tags[2].keys())
 
