@@ -59,6 +59,8 @@ def parse():
                     help="PC mg: rebuild the preconditioner on the first MG_LAG Newton iterations of a time step and "
                          "afterwards only while the Newton error is above 1e-3 (KSP.mg_setup_first); 0: for every tangent")
     ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-fallback", action="store_true",
+                    help="N = 1: do not retry with the configurations measured earlier when the run fails its own checks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -368,6 +370,13 @@ def run_b200(args):
     clk = clocks.stop()
     note(f"timed steps done: {ms / args.steps:.1f} ms/step")
     launches = eng.launches - launches0
+    # a bench line is only printed for a run that did what it claims: every step converged (no dt-retry), every
+    # Krylov solve of the timed steps reached its tolerance, no NaN
+    n_solves = sum(r["iterations"] for r in recs)
+    bad = [k for k in eq.ksp_log[-n_solves:] if k[1] <= 0]
+    if not all(r["converged"] and r["dt_used"] == r["dt"] for r in recs) or bad or not bool(torch.isfinite(eq.X).all()):
+        raise RuntimeError(f"timed steps invalid: converged={[r['converged'] for r in recs]}, "
+                           f"failed Krylov solves={len(bad)} of {n_solves} (first: {bad[:1]})")
     iters = sum(r["iterations"] for r in recs)
     ksp_its = sum(r["ksp_iterations"] for r in recs)
     value = N * iters / (ms * 1e-3)
@@ -482,5 +491,31 @@ if __name__ == "__main__":
         sys.exit(probe_mg(warm_start=a.warm_start, mg_lag=a.mg_lag))
     if a.impl == "reference":
         run_reference(a)
-    else:
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 or a.no_fallback:
         run_b200(a)
+    else:
+        # One GPU: the defaults include code paths whose first B200 run is this one.  If the run
+        # raises or fails its own validity checks, fall back -- in a fresh process, the CUDA context may be gone -- to
+        # the configurations measured before, most recent first; the line says which one produced it (config.fallback).
+        try:
+            run_b200(a)
+        except Exception as exc:      # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            tiers = [("multigrid CG, plain warm start, setup per tangent", ["--pc", "mg", "--warm-start", "1", "--mg-lag", "0"]),
+                     ("block-Jacobi CG, plain warm start", ["--pc", "jacobi", "--warm-start", "1", "--mg-lag", "0"])]
+            base = [sys.executable, os.path.abspath(__file__), "--no-fallback", "--steps", str(a.steps), "--warmup", str(a.warmup),
+                    "--levels", str(a.levels), "--ksp", a.ksp, "--rtol", str(a.rtol)]
+            base += (["--no-cpu-baseline"] if a.no_cpu_baseline else []) + (["--no-e2e"] if a.no_e2e else [])
+            for why, flags in tiers:
+                print(f"[bench] default configuration failed ({exc!r}); retrying with: {why}", file=sys.stderr, flush=True)
+                r = subprocess.run(base + flags, capture_output=True, text=True, timeout=3000)
+                sys.stderr.write(r.stderr[-4000:])
+                lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                if r.returncode == 0 and lines:
+                    line = json.loads(lines[-1])
+                    line["config"]["fallback"] = f"{why}; the default configuration failed with {exc!r}"
+                    print(json.dumps(line), flush=True)
+                    break
+            else:
+                raise
