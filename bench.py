@@ -191,8 +191,10 @@ def apply_solver_settings(solver, warm_start, mg_lag):
 
 
 def probe_mg(levels=2, device="cuda:0", warm_start=2, mg_lag=2):
-    """Elastic response of the cavern case on cavern_regular x8^levels with both preconditioners (both are this
-    repo's CUDA paths).  Prints MG_PROBE_OK / MG_PROBE_FAIL; run in a child process so that a device fault in the
+    """One time step of the cavern case on cavern_regular x8^levels with both preconditioners (both are this repo's
+    CUDA paths): same fields (1e-7), every multigrid solve converged in <= 80 iterations, the same number of Newton
+    iterations (+-1: the two Krylov methods stop at different points below rtol, which moves the Newton measure by a
+    few per cent of the 1e-8 threshold it is compared with).  Prints MG_PROBE_OK / MG_PROBE_FAIL; run in a child process so that a device fault in the
     newer code path cannot take the benchmark down with it."""
     import torch
     import safeincave_b200 as sf
@@ -219,7 +221,7 @@ def probe_mg(levels=2, device="cuda:0", warm_start=2, mg_lag=2):
     err = float((xj - xm).abs().max() / xj.abs().max())
     its_m, its_j = out["mg"][1], out["jacobi"][1]
     ok = err < 1e-7 and all(r > 0 for r in out["mg"][2]) and max(its_m) <= 80 and out["mg"][3]["converged"] \
-        and out["mg"][3]["iterations"] == out["jacobi"][3]["iterations"]
+        and abs(out["mg"][3]["iterations"] - out["jacobi"][3]["iterations"]) <= 1
     print(f"{'MG_PROBE_OK' if ok else 'MG_PROBE_FAIL'} rel_diff={err:.2e} mg_its={its_m} jacobi_its={its_j}", flush=True)
     return 0 if ok else 1
 
@@ -256,7 +258,7 @@ def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None, warm_star
         xj, xm = out["jacobi"][0], out["mg"][0]
         err = float((xj - xm).abs().max() / xj.abs().max())
         good = err < 1e-7 and all(r > 0 for r in out["mg"][2]) and max(out["mg"][1]) <= 80 and out["mg"][3]["converged"] \
-            and out["mg"][3]["iterations"] == out["jacobi"][3]["iterations"]
+            and abs(out["mg"][3]["iterations"] - out["jacobi"][3]["iterations"]) <= 1
         msg = f"rel_diff={err:.2e} mg_its<={max(out['mg'][1])} jacobi_its<={max(out['jacobi'][1])}"
         ok = 1 if good else 0
     except Exception as e:          # SicError (incl. a P2P wait that timed out), shape errors, ...
