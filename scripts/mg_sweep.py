@@ -212,6 +212,8 @@ elif os.environ.get("SWEEP") == "3":       # third sweep: fewer smoothing steps 
     for pre, post in (((1, 2), (1, 2)), ((1, 3), (1, 3)), ((1, 2), (1, 3)), ((1, 4), (1, 4)), ((0, 2), (2, 2)), ((1, 2), (2, 2))):
         for cit, clo in ((30, 0.01),):
             configs.append((pre, post, 0.1, cit, clo, 1))
+elif os.environ.get("SWEEP") == "5":       # fifth sweep: W-cycle with the 30-step coarse solve
+    configs += [(2, 2, 0.1, 30, 0.01, 1), (2, 2, 0.1, 30, 0.01, 2), (2, 2, 0.1, 60, 0.005, 2)]
 elif os.environ.get("SWEEP") == "4":       # fourth sweep: kind of Chebyshev polynomial
     for kind in (1, 4, 5):
         for pre, post in ((2, 2), (1, 1), (3, 3)):

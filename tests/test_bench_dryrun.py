@@ -1,0 +1,111 @@
+"""bench.py's GPU arm executed end to end on the HOST (tests/hostemu engine, stubbed CUDA events / pinned memory) on a
+small stand-in workload: the JSON line is assembled by code that otherwise only ever runs on the B200 box at round end,
+so a typo there would cost the round's headline number.  Checks the line's contract (keys, units, roofline and e2e
+objects), both preconditioner branches and the validity gate; the numbers themselves mean nothing here."""
+import json
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+@pytest.fixture()
+def dry(monkeypatch):
+    import bench
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases, distributed
+    from safeincave_b200.engine import Engine
+    from safeincave_b200.mesh import TetMesh
+    from tests.hostemu import EmuEngine
+
+    class DryEngine(EmuEngine):            # keep the product's event-based profiling hooks (stub events)
+        _tic = Engine._tic
+
+        def fp64_peak(self):               # the DFMA micro-benchmark would take minutes on the emulator
+            return 1.0e12
+
+    monkeypatch.setattr(sf.LinearMomentum, "engine_cls", DryEngine)
+    monkeypatch.setattr(distributed, "init", lambda device=None: distributed.DistContext(0, 1, torch.device("cpu")))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    # stand-in workload: the 48-cell cube with a body force (non-uniform stress, 5-6 Newton iterations per step)
+    load = TetMesh.load_npz
+    monkeypatch.setattr(TetMesh, "load_npz", staticmethod(lambda path: load(os.path.join(GOLD, "mesh_cube_coarse.npz"))))
+
+    def case(grid, n_steps=None, ksp_type="cg", rtol=1e-10, **kw):
+        c = cases.triaxial_case(grid, n_steps=n_steps, ksp_override=ksp_type)
+        c["g"] = [0.0, 0.0, -5e3]
+        c["ksp"]["rtol"] = rtol
+        return c
+    monkeypatch.setattr(cases, "cavern_case", case)
+    return bench
+
+
+def run(bench, capsys, *flags):
+    argv = ["bench.py", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + list(flags)
+    old = sys.argv
+    sys.argv = argv
+    try:
+        bench.run_b200(bench.parse())
+    finally:
+        sys.argv = old
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    return json.loads(lines[0])
+
+
+def check_contract(line, pc):
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e"):
+        assert key in line, key
+    assert line["metric"] == "cell_updates_per_s" and line["unit"] == "cell-updates/s" and line["dtype"] == "f64"
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
+    assert line["vs_baseline"] is None and line["data"] == "synthetic" and "workload" in line["config"]
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["gpu_launches"] > 0
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and r["achieved"] > 0
+    assert r["frac"] == pytest.approx(r["achieved"] / r["peak"])
+    e = line["e2e"]
+    assert e["value"] > 0 and e["unit"] == line["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert line["config"]["newton_iterations"] >= 8 and line["config"]["krylov_iterations"] > 0
+    assert "extrapolated" in line["config"]["warm_start"]
+    assert ("multigrid" in line["config"]["preconditioner"]) == (pc == "mg")
+
+
+def test_bench_line_multigrid(dry, capsys):
+    line = run(dry, capsys, "--pc", "mg", "--levels", "2")
+    check_contract(line, "mg")
+    mg = line["constitutive"]["mg"]
+    assert mg["setup_lag"] == 2 and 0 < mg["setups"] < mg["solves"] and len(mg["lambda_max"]) == 3
+
+
+def test_bench_line_block_jacobi(dry, capsys):
+    line = run(dry, capsys, "--pc", "jacobi", "--levels", "1", "--warm-start", "1")
+    assert "previous Newton iterate" in line["config"]["warm_start"]
+    line["config"]["warm_start"] = "extrapolated"      # the rest of the contract is the same
+    check_contract(line, "jacobi")
+
+
+def test_bench_refuses_a_run_that_did_not_converge(dry, capsys):
+    with pytest.raises(RuntimeError, match="timed steps invalid"):
+        run(dry, capsys, "--pc", "jacobi", "--levels", "1", "--max-it", "3")
