@@ -109,3 +109,15 @@ def test_bench_line_block_jacobi(dry, capsys):
 def test_bench_refuses_a_run_that_did_not_converge(dry, capsys):
     with pytest.raises(RuntimeError, match="timed steps invalid"):
         run(dry, capsys, "--pc", "jacobi", "--levels", "1", "--max-it", "3")
+
+
+def test_smoke_entry_point_on_the_emulator(monkeypatch, capsys):
+    """__graft_entry__.smoke() (two steps of config 1 vs the oracle, then the same on a 2-level multigrid) through the
+    host-emulated engine: the entry point's own Python must not be what fails on the GPU box."""
+    import __graft_entry__ as g
+    import safeincave_b200 as sf
+    from tests.hostemu import EmuEngine
+    monkeypatch.setattr(sf.LinearMomentum, "engine_cls", EmuEngine)
+    g.smoke()
+    out = capsys.readouterr().out
+    assert "smoke: u err" in out and "smoke (multigrid CG, 2 levels)" in out
