@@ -121,3 +121,31 @@ def test_smoke_entry_point_on_the_emulator(monkeypatch, capsys):
     g.smoke()
     out = capsys.readouterr().out
     assert "smoke: u err" in out and "smoke (multigrid CG, 2 levels)" in out
+
+
+def test_bench_line_two_emulated_ranks(dry, capsys, monkeypatch):
+    """The N > 1 branch of run_b200 (collective in-process multigrid probe, Morton-chunk partition, finest level
+    distributed / coarse levels replicated, max-over-ranks timing, rank 0 prints) on two emulated ranks."""
+    import threading
+
+    from safeincave_b200 import distributed
+    from tests.hostemu.ranks import run_ranks
+    local = threading.local()
+    monkeypatch.setattr(distributed, "init", lambda device=None: local.ctx)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--levels", "2",
+                                      "--no-cpu-baseline"])
+    # the probe's stand-in mesh is the cube as well (TetMesh.load_npz is redirected by the fixture)
+
+    def body(ctx):
+        local.ctx = ctx
+        dry.run_b200(dry.parse())
+        return ctx.rank
+
+    assert sorted(run_ranks(2, body)) == [0, 1]
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                   # rank 0 alone prints
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and "cpu_baseline" not in line
+    assert line["config"]["cells_per_gpu"] * 2 == line["config"]["n_cells"]
+    assert "MG_PROBE_OK" in line["config"]["pc_choice"] and "multigrid" in line["config"]["preconditioner"]
+    assert "finest level distributed" in line["config"]["partition"]
