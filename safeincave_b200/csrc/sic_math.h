@@ -158,6 +158,11 @@ SIC_HD double sic_log10(double x) { return sic_log(x) * 0.43429448190325182765; 
 
 SIC_HD double sic_pow(double x, double y) {
   if (y == 0.0) return 1.0;
+  // Exact small-integer exponents: one correctly rounded product IS the correctly rounded power, for every x
+  // (incl. negative, infinite and NaN arguments), and it is what the creep laws of every BASELINE configuration ask
+  // for 12 times per cell and tangent: DislocationCreep's q^(n-1) with n = 3.
+  if (y == 2.0) return x * x;
+  if (y == 1.0) return x;
   if (x == 1.0) return 1.0;
   if (x != x || y != y) return x + y;
   double sign = 1.0;
