@@ -73,7 +73,7 @@ def assemble_K(coords, cells, CT):
     grad, vol = tet_geometry(coords, cells)
     B = B_matrices(grad)
     WC = W_VOIGT[None, :, None] * CT                                    # (N,6,6)
-    Ke = np.einsum("n,nia,nij,njb->nab", vol, B, WC, B)                 # (N,12,12)
+    Ke = vol[:, None, None] * np.matmul(B.transpose(0, 2, 1), np.matmul(WC, B))   # (N,12,12): V B^T (W C_T B)
     dofs = cell_dofs(cells)
     rows = np.repeat(dofs, 12, axis=1).ravel()
     cols = np.tile(dofs, (1, 12)).ravel()
