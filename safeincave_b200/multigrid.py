@@ -114,7 +114,7 @@ class Multigrid:
     the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01,
-                 safety=1.15, power_its=16, power_its_warm=4, part=None, coarse_fixed=None):
+                 safety=1.15, power_its=32, power_its_warm=4, part=None, coarse_fixed=None):
         """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one):
         the finest level is distributed, the coarser ones are replicated on every rank (csrc/mg.cu).
         coarse_fixed: callable(level index, TetMesh) -> uint8 (3 M,) Dirichlet mask of a coarse level; needed when the

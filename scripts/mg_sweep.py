@@ -112,7 +112,7 @@ def lam_max(l, its=15):
         lam = np.linalg.norm(w) / np.linalg.norm(v)
         v = w / np.linalg.norm(w)
     return lam
-lam = [1.1 * lam_max(l) for l in range(LEVELS + 1)]
+lam = [float(os.environ.get('SAFETY', '1.1')) * lam_max(l, int(os.environ.get('POWER_ITS', '15'))) for l in range(LEVELS + 1)]
 print("lambda_max(Dinv K) estimates", lam)
 
 
@@ -212,6 +212,8 @@ elif os.environ.get("SWEEP") == "3":       # third sweep: fewer smoothing steps 
     for pre, post in (((1, 2), (1, 2)), ((1, 3), (1, 3)), ((1, 2), (1, 3)), ((1, 4), (1, 4)), ((0, 2), (2, 2)), ((1, 2), (2, 2))):
         for cit, clo in ((30, 0.01),):
             configs.append((pre, post, 0.1, cit, clo, 1))
+elif os.environ.get("SWEEP") == "6":       # sixth sweep: safety factor on lambda_max (set through SAFETY, see below)
+    configs += [(2, 2, 0.1, 30, 0.01, 1)]
 elif os.environ.get("SWEEP") == "5":       # fifth sweep: W-cycle with the 30-step coarse solve
     configs += [(2, 2, 0.1, 30, 0.01, 1), (2, 2, 0.1, 30, 0.01, 2), (2, 2, 0.1, 60, 0.005, 2)]
 elif os.environ.get("SWEEP") == "4":       # fourth sweep: kind of Chebyshev polynomial
