@@ -149,3 +149,9 @@ def test_bench_line_two_emulated_ranks(dry, capsys, monkeypatch):
     assert line["config"]["cells_per_gpu"] * 2 == line["config"]["n_cells"]
     assert "MG_PROBE_OK" in line["config"]["pc_choice"] and "multigrid" in line["config"]["preconditioner"]
     assert "finest level distributed" in line["config"]["partition"]
+
+
+def test_single_gpu_multigrid_probe(dry, capsys):
+    """bench.probe_mg (what `--pc auto` runs in a child process on one GPU) with the timed run's solver settings."""
+    assert dry.probe_mg(levels=2, device="cpu", warm_start=2, mg_lag=2) == 0
+    assert "MG_PROBE_OK" in capsys.readouterr().out
