@@ -340,6 +340,11 @@ int sic_mg_setup(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts
 int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, sic_ksp_t* ksp,
                  const double* b_ext, double* x, double* work, void* stream);
 
+/* Opt-in (environment SIC_MG_FUSED_COARSE=1, one GPU): the coarsest level's Chebyshev sweep runs as ONE cooperative launch
+ * (k_mg_coarse_fused) instead of two launches per step.  How many such launches this process has made (0: the switch is
+ * off or the cooperative launch was refused and the launch-per-step sweep is used). */
+long long sic_mg_fused_coarse_launches(void);
+
 /* z = V-cycle(r) alone (tests, and users who bring their own Krylov method): reads levels[top].b, writes .x */
 int sic_mg_vcycle(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);
 

@@ -34,7 +34,7 @@ EXPORTS = (
     "sic_apply", "sic_residual0", "sic_block_jacobi", "sic_neumann", "sic_ksp_workspace_doubles",
     "sic_ksp_solve", "sic_guess_workspace_doubles", "sic_guess_extrapolate", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
-    "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle",
+    "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle", "sic_mg_fused_coarse_launches",
     "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean", "sic_node_volumes", "sic_pq_fields",
 )
 
@@ -128,6 +128,7 @@ def declare(lib, single_gpu_only=False):
     PL, PO = POINTER(SicMgLevel), POINTER(SicMgOpts)
     lib.sic_mg_workspace_doubles.argtypes = [c_int, c_int]
     lib.sic_mg_workspace_doubles.restype = c_int64
+    lib.sic_mg_fused_coarse_launches.restype = c_int64
     lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]

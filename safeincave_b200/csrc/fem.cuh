@@ -80,6 +80,13 @@ __device__ __forceinline__ double ldg_f64(const double* p) {
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+// coherent (L2) load: for vectors that OTHER CTAs of the same launch have written before a grid-wide barrier -- the
+// non-coherent path above may only be used for data that is read-only for the whole kernel
+__device__ __forceinline__ double ldcg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ int ldg_s32(const int* p) {
   int v;
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -165,7 +172,8 @@ struct TileScratch {                      // shared memory of one operator CTA (
   int eoff[4 * SIC_TILE_CELLS + 1];       // per unique node: offset into ent
 };
 
-template <int MODE>
+// XCOH: gather x through the coherent path (x was written earlier in the SAME launch, k_mg_coarse_fused).
+template <int MODE, bool XCOH = false>
 __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const double* __restrict__ x,
                                                    double* __restrict__ y, TileScratch& sc,
                                                    const int* done_flag = nullptr) {
@@ -198,7 +206,8 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) ua[3 * a + j] = ldg_f64(x + 3 * (size_t)node[a] + j);
+    for (int j = 0; j < 3; ++j)
+      ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
   }
   // scatter plan of the tile -> shared memory (depends only on q0, requested first)
   const int nq = q1 - q0, ebase = tile * 4 * SIC_TILE_CELLS;

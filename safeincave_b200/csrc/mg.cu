@@ -28,6 +28,10 @@
 #include <string.h>
 
 #include "fem.cuh"
+#ifndef SIC_HOSTEMU
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#endif
 
 namespace sic {
 
@@ -188,15 +192,9 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_p(int nd, double* __r
 // ---- Chebyshev smoother -------------------------------------------------------------------------------
 // First step.  zero_guess: r = b, x = d = Dinv r / theta.  Otherwise t holds K x: r = b - t, d = Dinv r / theta,
 // x += d.  Leaves t = 0 for the next operator application.
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_first(int n_nodes, const double* __restrict__ b,
-                                                                  double* __restrict__ r, double* __restrict__ d,
-                                                                  double* __restrict__ x, double* __restrict__ t,
-                                                                  const double* __restrict__ dinv,
-                                                                  const uint8_t* __restrict__ fixed, double inv_theta,
-                                                                  int zero_guess, const int* done) {
-  if (*done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_nodes) return;
+__device__ __forceinline__ void mg_cheb_first_node(int n, const double* __restrict__ b, double* r, double* d, double* x,
+                                                   double* t, const double* __restrict__ dinv,
+                                                   const uint8_t* __restrict__ fixed, double inv_theta, int zero_guess) {
   double rn[3], zn[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -216,21 +214,30 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_first(int n_nodes, 
     x[k] = zero_guess ? dn : x[k] + dn;
   }
 }
-
-// Step k >= 1.  t holds K d: r -= t ; d = a d + c Dinv r ; x += d ; t = 0.
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, double* __restrict__ r,
-                                                                 double* __restrict__ d, double* __restrict__ x,
-                                                                 double* __restrict__ t, const double* __restrict__ dinv,
-                                                                 const uint8_t* __restrict__ fixed, double a, double c,
-                                                                 const int* done) {
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_first(int n_nodes, const double* __restrict__ b,
+                                                                  double* __restrict__ r, double* __restrict__ d,
+                                                                  double* __restrict__ x, double* __restrict__ t,
+                                                                  const double* __restrict__ dinv,
+                                                                  const uint8_t* __restrict__ fixed, double inv_theta,
+                                                                  int zero_guess, const int* done) {
   if (*done) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_nodes) return;
+  mg_cheb_first_node(n, b, r, d, x, t, dinv, fixed, inv_theta, zero_guess);
+}
+
+// Step k >= 1.  t holds K d: r -= t ; d = a d + c Dinv r ; x += d ; t = 0.
+// TCOH: t was accumulated by OTHER CTAs of the same launch (k_mg_coarse_fused): read it at L2, not through this SM's L1
+template <bool TCOH = false>
+__device__ __forceinline__ void mg_cheb_step_node(int n, double* r, double* d, double* x, double* t,
+                                                  const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
+                                                  double a, double c) {
   double rn[3], zn[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const size_t k = 3 * (size_t)n + j;
-    const double v = fixed[k] ? 0.0 : r[k] - t[k];
+    const double tk = TCOH ? __ldcg(t + k) : t[k];
+    const double v = fixed[k] ? 0.0 : r[k] - tk;
     rn[j] = v;
     r[k] = v;
     t[k] = 0.0;
@@ -244,6 +251,49 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, d
     x[k] += dn;
   }
 }
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, double* __restrict__ r,
+                                                                 double* __restrict__ d, double* __restrict__ x,
+                                                                 double* __restrict__ t, const double* __restrict__ dinv,
+                                                                 const uint8_t* __restrict__ fixed, double a, double c,
+                                                                 const int* done) {
+  if (*done) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  mg_cheb_step_node(n, r, d, x, t, dinv, fixed, a, c);
+}
+
+#ifndef SIC_HOSTEMU
+// ---- coarsest level in ONE launch (opt-in: SIC_MG_FUSED_COARSE=1) -----------------------------------------
+// The coarsest level (the gmsh grid: 14 346 cells = 113 CTAs, < one wave of a B200) runs `coarse_its` Chebyshev steps per
+// V-cycle; as separate launches every step is an operator kernel (~10 us) plus a vector kernel (~6 us), both pure
+// latency: ~0.5 ms per cycle, 10-15 % of a Krylov iteration at 7.35 M cells and the largest part of one on 8 GPUs.
+// Here all steps run in one cooperative launch (one CTA per tile, grid-wide barriers of cooperative groups between
+// the operator and the vector phase); the phases are the SAME device functions as the kernels above
+// (ebe_tile_scatter, mg_cheb_first_node, mg_cheb_step_node).  Vectors written in one phase and gathered in the next
+// (d, t) are read through the coherent path (XCOH / plain loads): the read-only cache is not covered by grid.sync().
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): off unless SIC_MG_FUSED_COARSE=1.
+#define SIC_MG_MAX_COARSE_ITS 64
+struct MgCoarseCoef { double a[SIC_MG_MAX_COARSE_ITS], c[SIC_MG_MAX_COARSE_ITS]; double inv_theta; int its; };
+
+__global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_coarse_fused(sic_problem_t P, const double* __restrict__ b, double* r,
+                                                                     double* d, double* x, double* t,
+                                                                     const double* __restrict__ dinv,
+                                                                     const uint8_t* __restrict__ fixed, MgCoarseCoef cf,
+                                                                     const int* done) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  if (*done) return;                                   // uniform over the grid: no barrier is reached by anybody
+  __shared__ TileScratch sc;
+  const int nn = P.n_nodes, gsz = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int n = gtid; n < nn; n += gsz) mg_cheb_first_node(n, b, r, d, x, t, dinv, fixed, cf.inv_theta, 1);
+  grid.sync();
+  for (int k = 1; k < cf.its; ++k) {
+    ebe_tile_scatter<0, true>(P, d, t, sc, nullptr);   // t += K d (t is zero on entry: both node functions leave it so)
+    grid.sync();
+    for (int n = gtid; n < nn; n += gsz) mg_cheb_step_node<true>(n, r, d, x, t, dinv, fixed, cf.a[k], cf.c[k]);
+    grid.sync();
+  }
+}
+#endif
 
 // r -= t (t = K d of the last smoothing step): the true residual of x ; t = 0
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_resid(int nd, double* __restrict__ r, double* __restrict__ t,
@@ -447,6 +497,60 @@ static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, doubl
   return sic_check_launch("multigrid: Chebyshev sweep");
 }
 
+// The coarsest-level sweep as one cooperative launch (k_mg_coarse_fused).  Returns true if it was launched; false means
+// "use mg_chebyshev": not asked for, not a single-GPU replicated level, too many steps, or the grid is not co-resident.
+static long long g_fused_coarse_launches = 0;
+extern "C" long long sic_mg_fused_coarse_launches(void) { return g_fused_coarse_launches; }
+
+static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, double lo, const int* done, cudaStream_t st) {
+#ifdef SIC_HOSTEMU
+  (void)L; (void)b; (void)its; (void)lo; (void)done; (void)st;
+  return false;
+#else
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SIC_MG_FUSED_COARSE"); enabled = (e && e[0] == '1') ? 1 : 0; }
+  if (!enabled || mg_halo(L) || its < 2 || its > SIC_MG_MAX_COARSE_ITS || L.prob.n_cells <= 0) return false;
+  const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+  static int max_blocks = -1;
+  if (max_blocks < 0) {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mg_coarse_fused, SIC_TILE_CELLS, 0);
+    max_blocks = coop ? sms * per_sm : 0;
+  }
+  if (cb > max_blocks) return false;
+  MgCoarseCoef cf;
+  const double lmax = L.lambda_max, lmin = lo * lmax;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  cf.inv_theta = 1.0 / theta;
+  cf.its = its;
+  cf.a[0] = cf.c[0] = 0.0;
+  for (int k = 1; k < its; ++k) {       // the recurrence of mg_chebyshev
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    cf.a[k] = rho_new * rho;
+    cf.c[k] = 2.0 * rho_new / delta;
+    rho = rho_new;
+  }
+  sic_problem_t P = L.prob;
+  const double* bb = b;
+  double *r = L.r, *d = L.d, *x = L.x, *t = L.t;
+  const double* dinv = L.dinv;
+  const uint8_t* fixed = L.fixed;
+  const int* dn = done;
+  void* args[] = {&P, &bb, &r, &d, &x, &t, &dinv, &fixed, &cf, &dn};
+  if (cudaLaunchCooperativeKernel((const void*)k_mg_coarse_fused, dim3(cb), dim3(SIC_TILE_CELLS), args, 0, st) != cudaSuccess) {
+    cudaGetLastError();      // clear; fall back to the launch-per-step sweep for good
+    enabled = 0;
+    return false;
+  }
+  g_fused_coarse_launches += 1;
+  return true;
+#endif
+}
+
 // V(nu,nu) cycle: reads `b_top` as the right-hand side of the finest level, leaves the result in levels[top].x.
 // `done` points at a device int: every kernel is a no-op once it is non-zero.
 static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, const double* b_top, const int* done,
@@ -473,7 +577,8 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
   {
     const sic_mg_level_t& L = lv[0];
     const double* b = (top == 0) ? b_top : L.b;
-    if (int rc = mg_chebyshev(L, b, o->coarse_its, o->coarse_lo, 1, done, st)) return rc;
+    if (!mg_coarse_fused(L, b, o->coarse_its, o->coarse_lo, done, st))
+      if (int rc = mg_chebyshev(L, b, o->coarse_its, o->coarse_lo, 1, done, st)) return rc;
   }
   for (int l = 1; l <= top; ++l) {
     const sic_mg_level_t& L = lv[l];

@@ -15,6 +15,7 @@ run default          --pc mg                               # extrapolated guess 
 run plain_warmstart  --pc mg --warm-start 1 --mg-lag 0     # what profiles/r1_bench_mg_levels3.json measured, + new coarse solve
 run extrap_only      --pc mg --warm-start 2 --mg-lag 0
 run lag_only         --pc mg --warm-start 1 --mg-lag 2
+SIC_MG_FUSED_COARSE=1 run fused_coarse   --pc mg            # opt-in: coarsest-level sweep as one cooperative launch
 run jacobi_extrap    --pc jacobi --levels 2                # block-Jacobi CG with the extrapolated guess, 918k cells
 run jacobi_plain     --pc jacobi --levels 2 --warm-start 1
 run levels4          --pc mg --levels 4 --steps 2 --warmup 2   # 58.8M cells (about 50 GB)

@@ -32,7 +32,7 @@ _FIRST_TIME_ON_GPU = (
     "test_heat_steps_cube", "test_heat_steps_cavern_regular", "test_thermomechanical_steps_cube",
     "test_thermomechanical_step_cavern_regular", "test_time_steps_cavern_regular_extrapolated_guess",
     "test_guess_extrapolation_kernel", "test_lagged_multigrid_setup",
-    "test_operator_rhs_blocks_strain_configs2_grid",
+    "test_operator_rhs_blocks_strain_configs2_grid", "test_fused_coarse_level_sweep_matches_the_oracle",
 )
 
 
