@@ -100,6 +100,7 @@ class LinearMomentum(LinearMomentumBase):
         self.mg = None                      # multigrid.Multigrid, built on the first solve with PC type "mg"
         self._guess_ring, self._guess_n, self._guess_head = None, 0, 0     # last <= 4 Newton iterates of the step
         self._solves_in_step, self._last_newton_error = 0, -1.0            # for the lagged multigrid setup (Solver.KSP)
+        self._last_mg_its = None            # Krylov iterations of the previous multigrid solve of this time step
         self.guess_log = []                 # (a, b, terms) per extrapolated guess when self.guess_debug
         self.guess_debug = False
         self.mg_options = {}                # nu, coarse_its, smooth_lo, coarse_lo, safety, power_its
@@ -223,6 +224,7 @@ class LinearMomentum(LinearMomentumBase):
         """A new time step (or a restored one) starts: its iterates do not continue the old sequence."""
         self._guess_n = 0
         self._solves_in_step, self._last_newton_error = 0, -1.0
+        self._last_mg_its = None
 
     def _linear_solve_mg(self, x, rtol, atol, max_it):
         """CG preconditioned by a geometric-multigrid V-cycle on the grid's refinement hierarchy (csrc/mg.cu)."""
@@ -242,9 +244,16 @@ class LinearMomentum(LinearMomentumBase):
             eng._toc(t)
         self._solves_in_step += 1
         t = eng._tic("mg_solve")
+        # iterations launched between two looks at the device's `done` flag: the Krylov counts of a step decrease from
+        # one Newton iteration to the next, so the previous count bounds the batch (a converged solve turns the rest of its
+        # batch into ~170 no-op launches per iteration)
+        check = ksp.mg_check_every
+        if ksp.initial_guess_nonzero and self._last_mg_its is not None:
+            check = max(1, min(check, self._last_mg_its))
         res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
-                            check_every=ksp.mg_check_every, guess_nonzero=ksp.initial_guess_nonzero,
+                            check_every=check, guess_nonzero=ksp.initial_guess_nonzero,
                             time_operator=eng.time_operator)
+        self._last_mg_its = int(res.iterations)
         eng._toc(t)
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
