@@ -242,3 +242,56 @@ class Simulator_TM(Simulator):
             if hasattr(output, "save_mesh"):
                 output.save_mesh()
         return self.history
+
+
+class Simulator_T(Simulator):
+    """Heat-diffusion-only simulator with the surface of the reference's Simulator_T (safeincave/Simulators.py:543-640):
+    every step updates the heat boundary conditions, solves the backward-Euler heat equation (csrc/heat.cu through
+    HeatDiffusion.solve) and saves the fields.  The step table reports 0 iterations / 0 error, as the reference's does."""
+
+    def __init__(self, eq_heat, t_control, outputs, compute_elastic_response: bool = True, verbose: bool = True):
+        self.eq_heat = eq_heat
+        self.t_control = t_control
+        self.outputs = outputs if outputs is not None else []
+        self.verbose = verbose
+        self.screen = None
+        self.history = []
+
+    def step(self):
+        heat, tc = self.eq_heat, self.t_control
+        t0 = time.perf_counter()
+        tc.advance_time()
+        t, dt = tc.t, tc.dt
+        heat.bc.update_dirichlet(t)
+        heat.bc.update_neumann(t)
+        heat.solve(t, dt)
+        rec = dict(step=tc.step_counter, t=t, dt=dt, iterations=0, error=0.0, heat_iterations=heat.ksp_log[-1][0],
+                   seconds=time.perf_counter() - t0)
+        self.history.append(rec)
+        return rec
+
+    def run(self):
+        tc = self.t_control
+        if self.verbose:
+            from .ScreenOutput import ScreenPrinter
+            ScreenPrinter.reset_instance()
+            self.screen = ScreenPrinter(self.eq_heat.grid, self.eq_heat.solver, getattr(self.eq_heat, "mat", None), self.outputs,
+                                        tc.time_unit)
+        for output in self.outputs:
+            output.initialize()
+        for output in self.outputs:
+            output.save_fields(0)
+        while tc.keep_looping():
+            rec = self.step()
+            for output in self.outputs:
+                output.save_fields(rec["t"])
+            if self.screen is not None:
+                current_time = "%.3f" % (rec["t"] / tc.time_conversion)
+                self.screen.print_row([tc.step_counter, tc.dt / tc.time_conversion,
+                                       f"{current_time} / {tc.t_final / tc.time_conversion}", 0, 0])
+        if self.screen is not None:
+            self.screen.close()
+        for output in self.outputs:
+            if hasattr(output, "save_mesh"):
+                output.save_mesh()
+        return self.history

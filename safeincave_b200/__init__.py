@@ -11,7 +11,7 @@ from .MaterialProps import (Material, NonElasticElement, Spring, Thermoelastic, 
 from .Grid import GridHandlerGMSH  # noqa: F401
 from .MomentumEquation import LinearMomentumBase, LinearMomentum, CellField  # noqa: F401
 from .HeatEquation import HeatDiffusion  # noqa: F401
-from .Simulators import Simulator_M, Simulator_TM  # noqa: F401
+from .Simulators import Simulator_M, Simulator_TM, Simulator_T  # noqa: F401
 from .TimeHandler import TimeControllerBase, TimeController, TimeControllerParabolic  # noqa: F401
 from .Solver import KSP, PETSc  # noqa: F401
 from .OutputHandler import SaveFields  # noqa: F401

@@ -133,3 +133,51 @@ def test_reference_thermomechanics_cavern_example_runs_unmodified(tmp_path, monk
     assert 280.0 < T.min() and T.max() < 340.0          # geothermal profile, gas at 293 K on the cavern wall
     for stage, field in (("equilibrium", "u"), ("operation", "u"), ("operation", "T"), ("operation", "q_elems")):
         assert os.path.isfile(work / "output" / "case_1" / stage / field / f"{field}.xdmf")
+
+
+def test_reference_thermal_cavern_example_runs_unmodified(tmp_path, monkeypatch, capsys):
+    """examples/thermal/2_cavern/main.py (heat diffusion around a cavern on grids/cavern_regular: geothermal initial field,
+    Dirichlet / Neumann / Robin conditions, parabolic time controller, Simulator_T) executed unmodified, two steps."""
+    import safeincave_b200 as sf
+    from safeincave_b200 import compat
+    from tests.hostemu import EmuEngine
+    example = os.path.join(REF, "examples", "thermal", "2_cavern", "main.py")
+    if not os.path.isfile(example):
+        pytest.skip("example not in the reference checkout")
+    monkeypatch.setattr(sf.HeatDiffusion, "engine_cls", EmuEngine)
+    registered = compat.install()
+    sims = []
+    try:
+        work = tmp_path / "examples" / "thermal" / "2_cavern"
+        work.mkdir(parents=True)
+        os.symlink(os.path.join(REF, "grids"), tmp_path / "grids")
+        monkeypatch.chdir(work)
+        real_tc, real_tcp = sf.TimeController, sf.TimeControllerParabolic
+
+        class TC(real_tc):
+            def __init__(self, dt, initial_time, final_time, time_unit="second"):
+                super().__init__(dt=dt, initial_time=initial_time, final_time=min(final_time, 2 * dt), time_unit=time_unit)
+
+        class TCP(real_tcp):
+            def keep_looping(self):
+                return self.step_counter < 2 and super().keep_looping()
+
+        class Rec(sf.Simulator_T):
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                sims.append(self)
+
+        monkeypatch.setattr(sf, "TimeController", TC)
+        monkeypatch.setattr(sf, "TimeControllerParabolic", TCP)
+        monkeypatch.setattr(sf, "Simulator_T", Rec)
+        runpy.run_path(example, run_name="not_main")["main"]()
+    finally:
+        for name in registered:
+            for key in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+                del sys.modules[key]
+    (sim,) = sims
+    assert len(sim.history) == 2 and all(h["heat_iterations"] > 0 for h in sim.history)
+    T = sim.eq_heat.T.x.array
+    assert np.isfinite(T).all() and 270.0 < T.min() and T.max() < 340.0
+    assert os.path.isfile(work / "output" / "case_0" / "T" / "T.xdmf") and os.path.isfile(work / "output" / "case_0" / "log.txt")
+    assert "Total time:" in capsys.readouterr().out
