@@ -223,6 +223,11 @@ class ViscoplasticDesai(NonElasticElement):
         ds[L.DS_ALPHA, :engine.N] = a0       # :1089
         ds[L.DS_ALPHA0, engine.N:] = 1.0
         ds[L.DS_ALPHA, engine.N:] = 1.0
+        pending = self.__dict__.pop("_pending_hardening", None)
+        if pending is not None:               # compute_initial_hardening was called before the element was attached
+            keep = engine.sig.clone()
+            self.compute_initial_hardening(pending[0], pending[1])
+            engine.sig.copy_(keep)
 
     def _row(self, r):
         return self._state().desai[r, :self._engine.N].cpu()
@@ -247,7 +252,17 @@ class ViscoplasticDesai(NonElasticElement):
         """MaterialProps.py:1248-1288 on the device.  ``stress``: (N,3,3) tensor (host or device)."""
         eng = self._engine
         if eng is None:
-            raise RuntimeError("compute_initial_hardening needs the material attached (set_material) first")
+            # the reference's scripts call this BEFORE add_to_non_elastic / set_material (Simulators.py:1271-1276,
+            # nobian/Simulation/Run.py:1500-1504): keep the stress and run the kernel when the element is attached
+            if stress is None:
+                raise RuntimeError("compute_initial_hardening(None) needs the material attached (set_material) first")
+            s = stress.to_tensor() if hasattr(stress, "to_tensor") else to.as_tensor(stress)
+            if s.ndim == 3:
+                s = tensor_to_voigt(s.double())
+            self._pending_hardening = (s.detach().double().cpu().clone(), float(Fvp_0))
+            return
+        if hasattr(stress, "to_tensor"):       # a CellField handle (LinearMomentum.sig)
+            stress = None if stress.buf.data_ptr() == eng.sig.data_ptr() else stress.to_tensor()
         if stress is not None:
             s = to.as_tensor(stress)
             if s.ndim == 3:
@@ -396,6 +411,8 @@ class Material:
             raise ValueError(f"at most {L.SIC_MAX_ELEMS} non-elastic elements")
         self.elems_ne.append(elem)
         elem._material = self
+        if self._engine is not None:      # the material is shared by reference with the equation in the reference
+            self.bind(self._engine)       # (Simulators.py:1276 adds Desai without a second set_material)
 
     def rebind(self):
         """Rebuild the parameter table on the device after a parameter tensor was re-assigned; state is kept."""
@@ -458,12 +475,21 @@ class Material:
         return table, ids, layout
 
     def bind(self, engine: Engine):
+        """Attach to the device engine.  Called again by a later ``set_material`` of the same engine -- the reference's
+        staged runs add ViscoplasticDesai after the equilibrium stage and call ``mom_eq.set_material(mat)`` a second
+        time (Simulators.py:1213-1326, nobian/Simulation/Run.py:1503-1506) -- elements that are already attached keep
+        their state (in the reference it lives in the element objects), new ones start from zero."""
         table, ids, layout = self.build_table(device=engine.device)
+        keep = [e._index if (e._engine is engine and 0 <= e._index < len(engine.elems)
+                             and engine.elems[e._index].kind == e.kind) else None for e in self.elems_ne]
         engine.set_material(table.numpy(), ids, layout["spring_off"], layout["thermo_off"], layout["n_thermo"],
-                            layout["specs"])
+                            layout["specs"], keep=keep)
         self._engine, self._layout, self._table, self._ids = engine, layout, table, ids.cpu()
-        for i, e in enumerate(self.elems_ne):
-            e._bind(engine, i)
+        for i, (e, k) in enumerate(zip(self.elems_ne, keep)):
+            if k is None:
+                e._bind(engine, i)
+            else:
+                e._index = i
 
     # ------------------------------------------------------------------ reference attributes (lazy)
     def _rows66(self, k0):

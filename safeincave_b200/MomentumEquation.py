@@ -40,6 +40,12 @@ class CellField:
     def numpy(self):
         return self.to_tensor().numpy()
 
+    @property
+    def x(self):
+        """``mom_eq.sig.x.array`` of the reference's DG0 3x3 Function (flat, 9 per cell; Simulators.py:1273,
+        nobian/Simulation/Run.py:1500): a host copy."""
+        return _DofArray(lambda: self.to_tensor().reshape(-1).numpy())
+
     def __array__(self, dtype=None):
         return self.numpy()
 
@@ -203,11 +209,30 @@ class LinearMomentum(LinearMomentumBase):
             eng.block_jacobi(self.dinv, self.fixed)
             res = eng.ksp_solve(ksp.method(), self.b_ext, x, self.fixed, self.dinv, rtol=rtol, atol=atol,
                                 max_it=max_it, check_every=ksp.check_every, guess_nonzero=ksp.initial_guess_nonzero)
-            ksp.record(res)
-            self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+            self._record_solve(res)
         if extrapolate:
             self._guess_push(x)
         return res
+
+    def _record_solve(self, res):
+        """Keep the Krylov result where PETSc keeps it (KSP.getConvergedReason ...) and say so when a solve did not reach
+        its tolerance -- PETSc would not raise either, but the reference's users see it in -ksp_converged_reason."""
+        import sys
+        self.solver.record(res)
+        its, reason, rnorm = int(res.iterations), int(res.reason), float(res.rnorm)
+        self.ksp_log.append((its, reason, rnorm))
+        if reason <= 0:
+            what = {-3: "the iteration limit", -9: "a non-finite residual"}.get(reason, f"reason {reason}")
+            self.ksp_failures = getattr(self, "ksp_failures", 0) + 1
+            if self.ksp_failures <= 5 and self.grid.mesh.comm.rank == 0:
+                print(f"[KSP] linear solve stopped on {what} after {its} iterations (residual {rnorm:.3e})"
+                      + ("; further messages suppressed" if self.ksp_failures == 5 else ""), file=sys.stderr)
+
+    def last_solve_is_nan(self):
+        """True when the last linear solve met a non-finite right-hand side or residual (reason -9).  The solver leaves
+        the displacement untouched in that case, so the strain would not move and the Newton measure would read 0: the
+        time loop must treat it as the NaN the reference's KSP would have returned (Simulators.py:437-439)."""
+        return bool(self.ksp_log) and self.ksp_log[-1][1] == -9
 
     # Newton iterates of the current time step, newest first, for the extrapolated Krylov guess
     def _guess_push(self, x):
@@ -255,8 +280,7 @@ class LinearMomentum(LinearMomentumBase):
                             time_operator=eng.time_operator)
         self._last_mg_its = int(res.iterations)
         eng._toc(t)
-        ksp.record(res)
-        self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
+        self._record_solve(res)
         return res
 
     def _coarse_dirichlet_mask(self, level, mesh):
@@ -342,6 +366,9 @@ class LinearMomentum(LinearMomentumBase):
         if with_error:
             flags |= L.POST_ERROR
         eng.post(self.X, dt, self.theta, self._kelvin_phi2, flags)
+        if self.last_solve_is_nan():
+            self._last_newton_error = -1.0
+            return float("nan")
         if not with_error:
             return 0.0
         if self.dist is not None and self.dist.world > 1:    # cells are partitioned: plain sums over ranks

@@ -82,6 +82,9 @@ class Simulator_M(Simulator):
         tc.advance_time()
         t, dt = tc.t, tc.dt
         sig_bak, eps_bak = eng.sig.clone(), eng.eps.clone()
+        # the reference starts every KSP solve from zero, so a failed attempt cannot leak into the retry; with a warm
+        # start (KSP.setInitialGuessNonzero / setGuessExtrapolation) the displacement is part of what a retry restores
+        X_bak = eq.X.clone() if (eq.solver is not None and eq.solver.initial_guess_nonzero) else None
         eq.save_internal_state()
         n_ne = len(eq.mat.elems_ne)
         dt_current, dt_cut, converged = dt, 0, False
@@ -106,6 +109,8 @@ class Simulator_M(Simulator):
                 eng.sig.copy_(sig_bak)
                 eng.eps.copy_(eps_bak)
                 eq.restore_internal_state()
+                if X_bak is not None:
+                    eq.X.copy_(X_bak)
                 if dt_cut <= self.max_dt_cuts:
                     print(f"[SOLVER] Step {tc.step_counter}: {'NaN' if np.isnan(error) else 'no convergence'} "
                           f"after {ite} iters — halving dt ({dt_current / tc.time_conversion:.4f} -> "
@@ -114,8 +119,10 @@ class Simulator_M(Simulator):
                     dt_current = dt_current / 2
                 else:
                     eng.sig_k.copy_(sig_bak)
+                    dump = self._dump_nan_diagnostic(t, dt_current)
                     print(f"[SOLVER] All {self.max_dt_cuts} retries failed at step {tc.step_counter} "
-                          f"(t={t / tc.time_conversion:.1f}h); state restored, step not committed", file=sys.stderr)
+                          f"(t={t / tc.time_conversion:.1f}h); state restored, step not committed. "
+                          f"Diagnostic saved to {dump}", file=sys.stderr)
         if converged:
             eq.commit(dt_current)      # update_internal_variables; update_eps_ne_rate_old; update_eps_ne_old
         rec = dict(step=tc.step_counter, t=t, dt=dt, dt_used=dt_current, iterations=ite, error=float(error),
@@ -123,6 +130,32 @@ class Simulator_M(Simulator):
         self.history.append(rec)
         self.on_step_end(rec)
         return rec
+
+    nan_diagnostic = True     # write nan_diagnostic.pt when every dt-retry of a step failed (Simulators.py:463-503)
+
+    def _dump_nan_diagnostic(self, t, dt):
+        """Simulators.py:476-498: the restored state of the failed step as a ``torch.save`` dictionary with the
+        reference's keys, pulled from the device (``G``/``B`` per element are not stored on the device -- the commit
+        kernel recomputes them -- so the dump holds the material's total tangent C_T instead of ``G_total``)."""
+        if not self.nan_diagnostic:
+            return None
+        import os
+        import torch as to
+        eq, eng = self.eq_mom, self.eq_mom.engine
+        rank = eq.grid.mesh.comm.rank
+        path = os.path.join(os.getcwd(), "nan_diagnostic.pt" if rank == 0 else f"nan_diagnostic_rank{rank}.pt")
+        diag = {"step": self.t_control.step_counter, "t": t, "dt": dt, "stress": eq.sig.to_tensor(),
+                "stress_backup": eq.sig.to_tensor(), "eps_tot": eq.eps_tot.to_tensor()}
+        for idx, e in enumerate(eq.mat.elems_ne):
+            prefix = f"elem_{idx}_{e.name}"
+            diag[f"{prefix}_eps_ne_rate"] = e.eps_ne_rate
+            if hasattr(e, "alpha"):
+                for k in ("alpha", "alpha_0", "h", "r", "Fvp", "qsi"):
+                    diag[f"{prefix}_{k}"] = getattr(e, k)
+        diag["C_inv"] = eq.mat.C_inv
+        diag["CT"] = to.as_tensor(eng.get_CT())
+        to.save(diag, path)
+        return path
 
     def run(self):
         tc = self.t_control

@@ -21,11 +21,15 @@ DESAI_TRIAXIAL = dict(mu_1=5.3665857009859815e-11, N_1=3.1, a_1=1.96501849692283
                       eta=0.8275682807874163, n=3.0, beta_1=0.0048, beta=0.995, m=-0.5,
                       gamma=0.095, sigma_t=5.0, alpha_0=0.0022)         # 1_triaxial/main.py:78-89
 
+# nobian/Simulation/Run.py:1456-1462 (scenario A, CCC Zuidwending) with the fixed shape parameters of :1486-1492
+DESAI_CAVERN_A = dict(DESAI_TRIAXIAL, mu_1=6.89e-12, N_1=3.0, a_1=1.80e-5, eta=0.82, alpha_0=2.0e-3)
+
 ELEMENT_LIBRARY = {
     "kelvin": dict(kind="kelvin", eta=105e11, E=10 * GPa, nu=0.32),                    # 1_triaxial/main.py:66-69
     "dislocation": dict(kind="dislocation", A=1.9e-20, Q=51600.0, n=3.0),              # :72-75
     "pressure_solution": dict(kind="pressure_solution", A=1.29e-19, d=0.01, Q=13184.0),  # thermomechanics/2_cavern/main.py:82-87
     "desai": dict(kind="desai", **DESAI_TRIAXIAL),
+    "desai_cavern": dict(kind="desai", **DESAI_CAVERN_A),
     # nobian/Simulation/Run.py:1262-1276 (scenario A, Munson-Dawson model; mu = E0 / (2 (1 + nu0)))
     "munson_dawson": dict(kind="munson_dawson", A=18.31 * (1e-6) ** 4.99 / (365 * 24 * 3600.0), Q=6356.0 * 8.32, n=4.99,
                           K0=7.0e-7, c=9.02e-3, m=3.0, alpha_w=-13.2, beta_w=-7.738, delta=0.58, mu=20.425e9 / 2.5),
@@ -96,6 +100,61 @@ def cavern_case(grid, elements=("dislocation",), theta=0.0, dt_hours=2.0, p_ref=
     if n_steps is not None:
         case["t_final_run"] = n_steps * case["dt"]
     return case
+
+
+def _staged(make_case, creep, desai, n_eq, n_op):
+    case_eq = make_case(tuple(creep), n_eq, True)
+    case_eq["desai_initial_hardening"] = False
+    for bc in case_eq["neumann"] + case_eq["dirichlet"]:      # time-constant boundary values (Simulators.py:1156-1158)
+        bc["values"] = [bc["values"][0]] * len(bc["values"])
+    case_op = make_case(tuple(creep) + (desai,), n_op, False)
+    case_op["desai_initial_hardening"] = False
+    case_op["stage_elements"] = case_op["elements"][len(creep):]
+    return case_eq, case_op
+
+
+def staged_cavern_cases(grid, n_eq=2, n_op=2, dt_eq_hours=0.5, dt_op_hours=0.5, theta=0.5, ksp_type="bicg", rtol=1e-12,
+                        creep=("kelvin", "dislocation", "pressure_solution"), desai="desai_cavern"):
+    """BASELINE config 3 the way the reference runs it (Simulators.py:1089-1191 run_equilibrium, :1213-1326
+    run_operation; nobian/Simulation/Run.py:1399-1510): an EQUILIBRIUM stage with the creep elements only and every
+    boundary value held at its first entry (:1156-1158), then ViscoplasticDesai is created, its hardening variable is
+    initialised on the equilibrium stress (compute_initial_hardening(stress, Fvp_0=0.0), :1271-1274), it is added to the
+    SAME material, and the OPERATION stage runs with compute_elastic_response=False (:1321-1324).
+    Returns (case_eq, case_op); case_op["stage_elements"] are the elements to add between the stages."""
+    return _staged(lambda els, n, is_eq: cavern_case(grid, elements=els, theta=theta, n_steps=n, ksp_type=ksp_type, rtol=rtol,
+                                                     dt_hours=dt_eq_hours if is_eq else dt_op_hours),
+                   creep, desai, n_eq, n_op)
+
+
+def staged_triaxial_cases(grid, n_eq=2, n_op=3, creep=("kelvin", "dislocation"), desai="desai"):
+    """The same two-stage workflow on the triaxial cube of BASELINE config 1 (what Simulators.py:1089-1326 runs for a
+    GUI input file): equilibrium at the initial confining + axial load, then Desai (1_triaxial/main.py:78-89) with its
+    hardening initialised on the equilibrium stress, then the axial load ramp."""
+    return _staged(lambda els, n, is_eq: triaxial_case(grid, elements=els, n_steps=n), creep, desai, n_eq, n_op)
+
+
+def add_operation_stage(case_op, eq, grid, verbose=False, outputs=None):
+    """The lines between the two stages of the reference's scripts (Run.py:1494-1506, Simulators.py:1257-1276) and the
+    operation stage's boundary conditions / simulator, on an equation that has run the equilibrium stage."""
+    import safeincave_b200 as sf
+    one = to.ones(grid.n_elems, dtype=to.float64)
+    mat = eq.mat
+    for e in case_op["stage_elements"]:
+        desai = sf.ViscoplasticDesai(*[e[p] * one for p in sf.ViscoplasticDesai.param_names], e["alpha_0"] * one, "desai")
+        stress_to = to.as_tensor(eq.sig.x.array.reshape((eq.n_elems, 3, 3)))      # Run.py:1500
+        desai.compute_initial_hardening(stress_to, Fvp_0=0.0)
+        mat.add_to_non_elastic(desai)
+    eq.set_material(mat)
+    bc = momBC.BcHandler(eq)
+    for d in case_op["dirichlet"]:
+        bc.add_boundary_condition(momBC.DirichletBC(d["boundary"], d["component"], d["values"], d["time_values"]))
+    for nb in case_op["neumann"]:
+        bc.add_boundary_condition(momBC.NeumannBC(nb["boundary"], nb["direction"], nb["density"], nb["ref_pos"],
+                                                  nb["values"], nb["time_values"], g=nb["gravity"]))
+    eq.set_boundary_conditions(bc)
+    tc = sf.TimeController(dt=case_op["dt"], initial_time=0.0, final_time=case_op.get("t_final_run", case_op["t_final"]),
+                           time_unit="second")
+    return sf.Simulator_M(eq, tc, outputs or [], compute_elastic_response=False, verbose=verbose)
 
 
 def cell_temperature(case, coords, cells):

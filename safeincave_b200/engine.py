@@ -179,7 +179,7 @@ class Engine:
         self.tile_nint = torch.bincount(utile[interior], minlength=nt).to(torch.int32).contiguous()
 
     # ------------------------------------------------------------------ material
-    def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False):
+    def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False, keep=None):
         table = torch.as_tensor(np.ascontiguousarray(table), dtype=torch.float64)
         self.mat_table = table.to(self.device).contiguous()
         mid = torch.as_tensor(mat_id).to(self.device, dtype=torch.int32)
@@ -188,7 +188,12 @@ class Engine:
         self.spring_off, self.thermo_off, self.n_thermo = int(spring_off), int(thermo_off), int(n_thermo)
         if len(elem_specs) > L.SIC_MAX_ELEMS:
             raise L.SicError(f"at most {L.SIC_MAX_ELEMS} non-elastic elements are supported")
-        if not keep_state or len(elem_specs) != len(self.elems):
+        if keep is not None:
+            # second set_material of a staged run (Simulators.py:1213-1326, nobian/Simulation/Run.py:1503-1506): the
+            # elements that were already attached keep their device state, new ones start from zero
+            self.elems = [self.elems[k] if (k is not None and k >= 0) else ElemState(s.kind, self.ns, self.device)
+                          for k, s in zip(keep, elem_specs)]
+        elif not keep_state or len(elem_specs) != len(self.elems):
             self.elems = [ElemState(s.kind, self.ns, self.device) for s in elem_specs]
         self.elem_specs = list(elem_specs)
         self._prob = None

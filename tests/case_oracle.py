@@ -46,3 +46,30 @@ def oracle_simulator(case, tm):
                     e.initial_hardening(sig, 0.0)
         sim.after_initial_stress = hook
     return sim
+
+
+def oracle_operation_stage(case_op, tm, osim_eq):
+    """The operation stage of a staged run (Simulators.py:1213-1326; nobian/Simulation/Run.py:1494-1510) on the
+    material, displacement and stress the oracle's equilibrium stage left behind: Desai is created, its hardening
+    variable initialised on that stress (Fvp_0 = 0), and the new simulator starts WITHOUT an elastic response."""
+    one = np.ones(tm.n_cells)
+    for e in case_op["stage_elements"]:
+        desai = oc.Desai(e["alpha_0"] * one, **{p: e[p] * one for p in oc.DesaiParams.names})
+        desai.initial_hardening(osim_eq.sig, 0.0)
+        osim_eq.mat.add(desai)
+    sim = oracle_simulator(dict(case_op, elements=[]), tm)
+    sim.mat = osim_eq.mat
+    sim.compute_elastic_response = False
+    sim.u, sim.sig = osim_eq.u.copy(), osim_eq.sig.copy()
+    return sim
+
+
+def oracle_staged_run(case_eq, case_op, tm):
+    """Both stages; returns (equilibrium simulator, its history, operation simulator, its history)."""
+    osim_eq = oracle_simulator(case_eq, tm)
+    n_eq = int(round(case_eq["t_final_run"] / case_eq["dt"]))
+    h_eq = osim_eq.run(0.0, [case_eq["dt"]] * n_eq)
+    osim_op = oracle_operation_stage(case_op, tm, osim_eq)
+    n_op = int(round(case_op["t_final_run"] / case_op["dt"]))
+    h_op = osim_op.run(0.0, [case_op["dt"]] * n_op)
+    return osim_eq, h_eq, osim_op, h_op

@@ -22,18 +22,9 @@ def _built_oracle():
     yield
 
 
-# GPU tests of code that has so far only been through the host emulation (tests/hostemu) -- the round's GPU budget
-# was spent before it was written.  They run LAST under `-m gpu -x`, so that a surprise in them cannot hide the
-# B200-verified parity tests behind an early stop.  Remove a name once it has passed on a B200.
-_FIRST_TIME_ON_GPU = (
-    "test_cuda_vs_oracle_all_quantities_extended_elements", "test_cuda_vs_reference_goldens_extended_elements",
-    "test_pq_output_fields", "test_time_steps_triaxial_cube_munson_dawson",
-    "test_time_steps_triaxial_cube_mohr_coulomb_and_matsuoka_nakai", "test_dt_retry_and_restore_follow_the_reference",
-    "test_heat_steps_cube", "test_heat_steps_cavern_regular", "test_thermomechanical_steps_cube",
-    "test_thermomechanical_step_cavern_regular", "test_time_steps_cavern_regular_extrapolated_guess",
-    "test_guess_extrapolation_kernel", "test_lagged_multigrid_setup",
-    "test_operator_rhs_blocks_strain_configs2_grid", "test_fused_coarse_level_sweep_matches_the_oracle",
-)
+# GPU tests that have not yet passed on a B200 run LAST under `-m gpu -x`, so that a surprise in them cannot hide the
+# verified parity tests behind an early stop.  Empty: every GPU test passed on a B200 (gpurun_out/r2_gputest*.log).
+_FIRST_TIME_ON_GPU = ()
 
 
 def pytest_collection_modifyitems(config, items):

@@ -37,3 +37,7 @@ def test_time_step_cavern_regular_extrapolated_guess(sf):
     warm start needs 2782 Krylov iterations for this step (measured with this emulation; not re-run here to keep the
     CPU suite short), the extrapolated guess 1992."""
     G.check_extrapolated_guess(sf, 1, plain_its=2782)
+
+
+test_staged_triaxial_cube_with_desai = G.test_staged_triaxial_cube_with_desai
+test_nan_step_is_restored_under_a_warm_started_solver = G.test_nan_step_is_restored_under_a_warm_started_solver

@@ -192,6 +192,7 @@ def run_both(sf, grid_name, case_fn, n_steps, levels=0, solver_opts=None, **kw):
     hist = sim.run()
     osim = oracle_simulator(case, tm)
     ohist = osim.run(0.0, [case["dt"]] * n_steps)
+    assert all(h["converged"] for h in ohist[1:]) and np.isfinite(ohist[-1]["u"]).all(), "the oracle run diverged"
     return eq, sim, hist, osim, ohist
 
 
@@ -220,7 +221,7 @@ def test_time_steps_triaxial_cube_with_desai(sf):
     from safeincave_b200 import cases
     eq, sim, hist, osim, ohist = run_both(sf, "cube_coarse", cases.triaxial_case, 3, levels=1,
                                           elements=("kelvin", "dislocation", "desai"))
-    check_fields(eq, osim, ohist, tol=1e-7)
+    check_fields(eq, osim, ohist, tol=1e-8)
 
 
 def test_time_steps_triaxial_cube_munson_dawson(sf):
@@ -287,6 +288,37 @@ def test_dt_retry_and_restore_follow_the_reference(sf):
     check_fields(eq, osim, [orecs[-1]])
 
 
+def test_nan_step_is_restored_under_a_warm_started_solver(sf, tmp_path, monkeypatch):
+    """with KSP.setInitialGuessNonzero / setGuessExtrapolation a failed attempt leaves NaN in the displacement
+    and every retry (and every later step) would start from it.  Step 1 is poisoned with a NaN temperature: all retries
+    fail, the state AND the displacement are restored, nan_diagnostic.pt is written with the reference's keys
+    (Simulators.py:463-503); step 2 then follows the oracle (whose step 1 fails by an iteration cap instead)."""
+    from safeincave_b200 import cases
+    monkeypatch.chdir(tmp_path)
+    grid = load_grid(sf, "cube_coarse", 1)
+    case = cases.triaxial_case(grid, n_steps=2, ksp_override="cg")
+    eq, sim = cases.build(case, grid)
+    eq.solver.setGuessExtrapolation(True)
+    sim.verbose = False
+    sim.initialize()
+    T_ok = eq.engine.T.clone()
+    eq.engine.T[3] = float("nan")
+    r0 = sim.step()
+    assert not r0["converged"] and np.isnan(r0["error"]) and r0["dt_used"] == case["dt"] / 8
+    assert torch.isfinite(eq.X).all() and torch.isfinite(eq.engine.sig).all()
+    diag = torch.load(os.path.join(str(tmp_path), "nan_diagnostic.pt"))
+    assert {"step", "t", "dt", "stress", "stress_backup", "eps_tot", "C_inv", "elem_0_kelvin_eps_ne_rate",
+            "elem_1_creep_eps_ne_rate"} <= set(diag)
+    assert diag["stress"].shape == (eq.engine.N, 3, 3) and diag["step"] == 1
+    eq.engine.T.copy_(T_ok)
+    r1 = sim.step()
+    assert r1["converged"]
+    osim = oracle_simulator(case, grid.tetmesh)
+    orecs = osim.run(0.0, [case["dt"]] * 2, maxiter_list=[2, 40])[1:]
+    assert [o["converged"] for o in orecs] == [False, True] and r1["iterations"] == orecs[1]["iters"]
+    check_fields(eq, osim, [orecs[-1]])
+
+
 def test_time_steps_cavern_regular(sf):
     """BASELINE config 2: cavern_regular (14 346 cells), fully implicit, cyclic gas pressure."""
     from safeincave_b200 import cases
@@ -337,15 +369,95 @@ def test_time_steps_cavern_regular_extrapolated_guess(sf):
     check_extrapolated_guess(sf, 2)
 
 
-def test_time_step_cavern_regular_config3_desai_pressure_solution(sf):
-    """BASELINE config 3 physics on cavern_regular: Spring + Kelvin + DislocationCreep + PressureSolutionCreep +
-    ViscoplasticDesai with compute_initial_hardening after the elastic response (theta = 0.5)."""
+# State variables of a run in which Desai FLOWS (eps_ne_old / eps_ne_rate_old of every element, alpha) carry the
+# reference algorithm's own round-off: the hardening increment d_alpha = -(r + P:d_sigma)/h uses the forward-FD
+# quantities P (0.1 Pa step) and h (1e-4 alpha step) directly (MaterialProps.py:1129-1158, 1432-1500), not only inside
+# a tangent.  Measured with two faithful (< 1 ulp) exp/pow implementations inside the SAME oracle
+# (tests/test_oracle_fem.py::test_roundoff_sensitivity_of_the_staged_desai_run): staged cube -- fields <= 2e-9, state
+# <= 1.2e-8; staged cavern_regular -- u/sigma/eps <= 4e-11, Desai eps_old 7e-8, rate_old 5e-8, Kelvin rate_old 1.3e-8.
+# Fields are therefore held to north_star's 1e-8 and the state to 5e-7 in the staged tests; runs in which Desai does
+# not flow (test_time_steps_triaxial_cube_with_desai: sensitivity 1e-12) are held to 1e-8 throughout.
+DESAI_STATE_TOL = 5e-7
+
+
+def run_staged(sf, grid_name, n_eq, n_op, levels=0, cases_fn="staged_cavern_cases"):
+    """BASELINE config 3 as the reference runs it: equilibrium stage -> compute_initial_hardening on the equilibrium
+    stress -> operation stage with Desai and compute_elastic_response=False (cases.staged_cavern_cases)."""
     from safeincave_b200 import cases
-    eq, sim, hist, osim, ohist = run_both(sf, "cavern_regular", cases.cavern_case, 1, ksp_type="bicg", theta=0.5,
-                                          elements=("kelvin", "dislocation", "pressure_solution", "desai"))
-    assert hist[0]["iterations"] == ohist[1]["iters"]
-    check_fields(eq, osim, ohist, tol=1e-7)
+    grid = load_grid(sf, grid_name, levels)
+    case_eq, case_op = getattr(cases, cases_fn)(grid, n_eq=n_eq, n_op=n_op)
+    eq, sim = cases.build(case_eq, grid)
+    h_eq = sim.run()
+    u_eq = eq.X.reshape(-1).cpu().numpy().copy()
+    sim_op = cases.add_operation_stage(case_op, eq, grid)
+    alpha_0 = eq.mat.elems_ne[-1].alpha_0.numpy().copy()
+    h_op = sim_op.run()
+    return grid, case_eq, case_op, eq, h_eq, u_eq, alpha_0, h_op
+
+
+def assert_oracle_run_is_a_reference(ohist):
+    """A diverged oracle must not serve as the reference."""
+    assert all(h["converged"] for h in ohist[1:]), [(h["iters"], h["error"]) for h in ohist[1:]]
+    assert all(h["dt_used"] == ohist[1]["dt_used"] for h in ohist[1:])          # no dt-retry on the way
+    assert all(np.isfinite(h["u"]).all() and np.isfinite(h["sig"]).all() for h in ohist)
+
+
+def check_staged_config3(sf, grid_name, n_eq=2, n_op=2, golden=None, tol=1e-8, levels=0, cases_fn="staged_cavern_cases",
+                         n_elems=4, min_yielding=100):
+    """Spring + Kelvin + DislocationCreep + PressureSolutionCreep, then + ViscoplasticDesai (theta = 0.5), against the
+    oracle run the same way, or against the oracle's committed output (``golden``: oracle/gen_staged_golden.py)."""
+    grid, case_eq, case_op, eq, h_eq, u_eq, alpha_0, h_op = run_staged(sf, grid_name, n_eq, n_op, levels, cases_fn)
     eng = eq.engine
-    d_gpu, d_or = eng.elems[3].desai, osim.mat.elems[3]
-    assert relerr(eng.get1(d_gpu[0]), d_or.alpha) < 1e-9          # hardening variable
-    assert relerr(eng.get1(d_gpu[4]), d_or.Fvp) < 1e-6 or np.abs(d_or.Fvp).max() < 1e-6
+    assert all(h["converged"] and h["dt_used"] == h["dt"] for h in h_eq + h_op)
+    desai_gpu = eq.mat.elems_ne[-1]
+    assert type(desai_gpu).__name__ == "ViscoplasticDesai" and len(eng.elems) == n_elems
+    if golden is None:
+        from tests.case_oracle import oracle_staged_run
+        osim_eq, oh_eq, osim, oh_op = oracle_staged_run(case_eq, case_op, grid.tetmesh)
+        assert_oracle_run_is_a_reference(oh_eq)
+        assert_oracle_run_is_a_reference(oh_op)
+        assert [h["iterations"] for h in h_eq] == [h["iters"] for h in oh_eq[1:]]
+        assert [h["iterations"] for h in h_op] == [h["iters"] for h in oh_op[1:]]
+        assert relerr(u_eq, oh_eq[-1]["u"]) < tol
+        d_or = osim.mat.elems[-1]
+        assert relerr(alpha_0, d_or.alpha_0) < 1e-10           # hardening initialised on the equilibrium stress
+        check_fields(eq, osim, oh_op, tol=tol, tol_state=DESAI_STATE_TOL)
+        assert relerr(desai_gpu.alpha.numpy(), d_or.alpha) < tol
+        assert relerr(desai_gpu.qsi_old.numpy(), d_or.qsi_old) < 1e-6 or np.abs(d_or.qsi_old).max() < 1e-30
+        assert np.abs(desai_gpu.Fvp.numpy() - d_or.Fvp).max() < 1e-6 * max(1.0, np.abs(d_or.Fvp).max())
+        assert (d_or.Fvp > 0).sum() >= min_yielding and np.abs(d_or.rate).max() > 0     # Desai is actually flowing
+        return
+    g = np.load(os.path.join(GOLD, golden))
+    assert int(g["n_eq"]) == n_eq and int(g["n_op"]) == n_op and int(g["n_cells"]) == eng.N
+    assert [h["iterations"] for h in h_eq] == list(g["iters_eq"])
+    assert [h["iterations"] for h in h_op] == list(g["iters_op"])
+    sel = g["cell_sel"]
+    assert relerr(u_eq, g["u_eq"]) < tol
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), g["u"]) < tol
+    sig, eps = eng.get6(eng.sig), eng.get6(eng.eps)
+    assert abs(np.abs(sig).max() / float(g["sig_absmax"]) - 1) < tol and abs(np.abs(eps).max() / float(g["eps_absmax"]) - 1) < tol
+    assert np.abs(sig[sel] - g["sig_sel"]).max() / float(g["sig_absmax"]) < tol
+    assert np.abs(eps[sel] - g["eps_sel"]).max() / float(g["eps_absmax"]) < tol
+    assert abs(np.linalg.norm(sig) / float(g["sig_norm"]) - 1) < tol
+    assert relerr(alpha_0, g["alpha_0"]) < 1e-10
+    assert relerr(desai_gpu.alpha.numpy(), g["alpha"]) < tol
+    assert abs(int((desai_gpu.Fvp.numpy() > 0).sum()) - int(g["n_yielding"])) <= 2 + int(g["n_yielding"]) // 1000
+
+
+def test_staged_triaxial_cube_with_desai(sf):
+    """The two-stage workflow of Simulators.py:1089-1326 on the triaxial cube (384 cells): equilibrium with Kelvin +
+    DislocationCreep, Desai's hardening initialised on the equilibrium stress, four steps of the axial load ramp with
+    Desai flowing in every cell (alpha falls from 5.6e-3 to 1.2e-3)."""
+    check_staged_config3(sf, "cube_coarse", n_eq=2, n_op=4, levels=1, cases_fn="staged_triaxial_cases", n_elems=3)
+
+
+def test_staged_config3_cavern_regular(sf):
+    """BASELINE configs[2] physics (Desai + pressure solution) on cavern_regular through the reference's two-stage
+    workflow, live against the oracle."""
+    check_staged_config3(sf, "cavern_regular")
+
+
+def test_staged_config3_cavern_irregular_finemesh(sf):
+    """The same on the grid BASELINE configs[2] names (91 896 cells), against the oracle's committed output
+    (tests/golden/staged_cfg3_cavern_irregular_finemesh.npz; the oracle's sparse LU needs minutes on this grid)."""
+    check_staged_config3(sf, "cavern_irregular_finemesh", golden="staged_cfg3_cavern_irregular_finemesh.npz")
