@@ -9,8 +9,14 @@ post-solve phase, convergence measure -- plus the commit, excluding p/q smoothin
 
 Workload: BASELINE.json configs[1] physics (grids/cavern_regular, cyclic gas pressure, fully implicit
 theta = 0, Spring + DislocationCreep, dt = 2 h) on the cavern_regular grid red-refined `--levels`
-times (configs[4]: 14 346 * 8^L cells; L = 0 is the reference's own grid; default L = 3 = 7 345 152 cells).  Synthetic refinement,
-random nothing: loads, materials and BCs are the example's.
+times (configs[4]: 14 346 * 8^L cells; L = 0 is the reference's own grid; default L = 4 = 58 761 216 cells, ~50 GB of
+state on one B200; the SAME mesh at every --gpus N, i.e. strong scaling).  Synthetic refinement, random nothing: loads,
+materials and BCs are the example's.
+
+CPU arm (`--impl reference`, and the `cpu_baseline` of the GPU line): the oracle port of the same time step on the SAME
+mesh family at the largest level the host finishes in about a minute (L = 1, 114 768 cells), all host cores
+(oracle/cpu_step.py: chunked constitutive update + assembled CSR + block-Jacobi PCG to the GPU arm's rtol).  Its fields
+after the step are also what `parity_check` compares the GPU path with (same mesh, the TIMED solver settings).
 
 metric  cell-updates/s = n_cells * (Newton iterations executed) / (time of the steps), whole job.
 value   steps timed with CUDA events, state resident in HBM.
@@ -38,7 +44,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--levels", type=int, default=3, help="red-refinement levels of cavern_regular (14 346 * 8^L cells)")
+    ap.add_argument("--levels", type=int, default=4, help="red-refinement levels of cavern_regular (14 346 * 8^L cells)")
+    ap.add_argument("--cpu-levels", type=int, default=1, help="refinement level of the CPU arm's mesh (same mesh family)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0: every host core)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ksp", default="cg")
     ap.add_argument("--rtol", type=float, default=1e-10)
@@ -89,51 +97,99 @@ class _HostGrid:
     def get_boundary_tag(self, name):
         return self.tetmesh.names[2][name]
 
+    def get_boundary_names(self):
+        return list(self.tetmesh.names[2].keys())
 
-def cpu_reference_steps(n_steps, warmup):
-    """Time `n_steps` time steps of the CPU oracle (oracle/fem.py OracleSimulatorM: numpy constitutive
-    update + scipy CSR assembly + sparse LU) on the UNREFINED cavern_regular grid (14 346 cells), same
-    loads/materials as the GPU arm.  Returns (cell_updates_per_s, ms_per_step, newton_iterations, cores)."""
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_mesh(levels):
+    """The CPU arm's mesh: finest level of the SAME hierarchy the GPU arm refines (built on the host, so that the GPU
+    parity check and the CPU arm index cells and nodes identically)."""
     from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    return refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz")), levels)
+
+
+def cpu_reference_steps(n_steps, warmup, levels=1, threads=0, rtol=1e-10, solver="pcg", hierarchy=None):
+    """Time `n_steps` time steps of the CPU port of the path on cavern_regular x8^levels, same loads / materials / rtol
+    as the GPU arm.  solver="pcg": oracle/cpu_step.py on `threads` host threads (0: all cores); "lu": the plain oracle
+    (oracle/fem.py OracleSimulatorM: sparse LU, one core).  Returns a dict (value, ms_per_step, newton iterations, cores,
+    n_cells, Krylov iterations, final fields of the last step)."""
     from safeincave_b200 import cases
     from tests.case_oracle import oracle_simulator
-    tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
-    case = cases.cavern_case(_HostGrid(tm), n_steps=n_steps + warmup)
-    sim = oracle_simulator(case, tm)
+    threads = threads if threads > 0 else host_cores()
+    h = hierarchy if hierarchy is not None else cpu_mesh(levels)
+    tm = h.finest
+    case = cases.cavern_case(_HostGrid(tm), n_steps=n_steps + warmup, ksp_type="cg", rtol=rtol)
+    if solver == "pcg":
+        from oracle.cpu_step import threaded_simulator
+        sim = threaded_simulator(case, tm, threads, rtol=rtol)
+        commit_owner = sim.mat
+    else:
+        sim, threads = oracle_simulator(case, tm), 1
+        commit_owner = sim.mat
     marks = []
-    orig = sim.mat.commit
+    orig = commit_owner.commit
 
     def commit(*a, **k):
         orig(*a, **k)
         marks.append(time.perf_counter())
-    sim.mat.commit = commit
-    t_begin = time.perf_counter()
+    commit_owner.commit = commit
+    orig_rates = commit_owner.commit_rates
+    t_init = []
+
+    def commit_rates(*a, **k):          # end of the initial elastic response + initial rates (setup, untimed)
+        orig_rates(*a, **k)
+        t_init.append(time.perf_counter())
+    commit_owner.commit_rates = commit_rates
     hist = sim.run(0.0, [case["dt"]] * (n_steps + warmup))
-    marks = [t_begin] + marks
-    # marks[0] -> after init+step boundaries; step i spans marks[i]..marks[i+1] (init folded into step 0)
-    t0 = marks[warmup] if warmup > 0 else marks[0]
-    elapsed = marks[-1] - t0
-    iters = sum(h["iters"] for h in hist[1 + warmup:])
-    return tm.n_cells * iters / elapsed, 1e3 * elapsed / n_steps, iters, 1, tm.n_cells
+    marks = [t_init[0]] + marks
+    elapsed = marks[-1] - marks[warmup]
+    recs = hist[1 + warmup:]
+    if not all(r["converged"] and r["dt_used"] == case["dt"] for r in recs):
+        raise RuntimeError("CPU arm: a timed step did not converge")
+    iters = sum(r["iters"] for r in recs)
+    return {"value": tm.n_cells * iters / elapsed, "ms_per_step": 1e3 * elapsed / n_steps, "newton_iterations": iters,
+            "cores": threads, "n_cells": tm.n_cells, "levels": levels, "seconds": elapsed,
+            "krylov_iterations": sum(getattr(sim, "krylov_iterations", [0])[1:]), "solver": solver,
+            "u": hist[-1]["u"], "sig": hist[-1]["sig"], "n_steps_run": n_steps + warmup}
+
+
+def cpu_sample_text(r):
+    how = ("chunked numpy constitutive update + assembled CSR + block-Jacobi PCG to the GPU arm's rtol, "
+           f"{r['krylov_iterations']} Krylov iterations" if r["solver"] == "pcg" else "numpy + scipy sparse LU")
+    return (f"{r['n_steps_run']} time step(s) of the oracle port ({how}) on cavern_regular x8^{r['levels']} "
+            f"({r['n_cells']} cells), {r['newton_iterations']} Newton iterations, {r['seconds']:.1f} s on {r['cores']} thread(s)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))      # each oracle step is ~25 s of CPU work
+    steps = max(1, min(args.steps, 2))      # one step is ~1 min of work for all cores at 115k cells
     warm = 0                                # no JIT / cache to warm on the CPU port
-    v, ms, iters, cores, n_cells = cpu_reference_steps(steps, warm)
-    sample = (f"{steps} time step(s) of the oracle port (numpy + scipy sparse LU) on cavern_regular unrefined "
-              f"({n_cells} cells), {iters} Newton iterations")
+    r = cpu_reference_steps(steps, warm, levels=args.cpu_levels, threads=args.cpu_threads, rtol=args.rtol)
+    lu = cpu_reference_steps(1, 0, levels=0, solver="lu", rtol=args.rtol)       # round 1's line, kept for continuity
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(0, n_cells), "note": "CPU port of the reference path; the reference's "
-                   "own FEniCSx/PETSc stack is not installable here (SURVEY 8c)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(args.cpu_levels, r["n_cells"]), "n_cells": r["n_cells"],
+                   "same_mesh_family_as_gpu_arm": True, "gpu_arm_levels": args.levels, "rtol": args.rtol,
+                   "note": "CPU port of the reference path on every host core; the reference's own FEniCSx/PETSc stack "
+                           "is not installable here (SURVEY 8c).  cell-updates/s is size-normalised; the mesh is the "
+                           "GPU arm's refined x8^%d instead of x8^%d so that the sample ends within minutes"
+                           % (args.cpu_levels, args.levels)},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": cpu_sample_text(r)},
+        "cpu_baseline_unrefined_lu": {"value": lu["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                      "sample": cpu_sample_text(lu)},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -480,11 +536,42 @@ def run_b200(args):
     if rank != 0:
         return
     if not args.no_cpu_baseline and world == 1:
-        v, cms, citers, cores, n0 = cpu_reference_steps(1, 0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"1 time step of the oracle port (numpy + scipy sparse LU) on cavern_regular "
-                                          f"unrefined ({n0} cells), {citers} Newton iterations, {cms / 1e3:.1f} s"}
+        del sim, eq, eng
+        torch.cuda.empty_cache()
+        hc = cpu_mesh(args.cpu_levels)
+        r = cpu_reference_steps(1, 0, levels=args.cpu_levels, threads=args.cpu_threads, rtol=args.rtol, hierarchy=hc)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "same_mesh_family": True, "n_cells": r["n_cells"], "sample": cpu_sample_text(r)}
+        note(f"CPU arm: {r['seconds']:.1f} s per step on {r['cores']} threads at {r['n_cells']} cells")
+        line["parity_check"] = parity_check(args, pc, hc, r, dev)
+        note(f"parity check: {line['parity_check']}")
     print(json.dumps(line), flush=True)
+
+
+def parity_check(args, pc, hierarchy, cpu, dev):
+    """The GPU path with the TIMED solver settings (preconditioner, warm start / extrapolated guess, lagged multigrid
+    setup, rtol) against the CPU arm's fields after the same time step on the same mesh (cavern_regular x8^cpu_levels):
+    max relative difference of the displacement and of the stress."""
+    import torch
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases
+    tm = hierarchy.finest
+    grid = sf.GridHandlerGMSH.from_hierarchy(hierarchy) if pc == "mg" else sf.GridHandlerGMSH.from_mesh(tm, reorder=False)
+    case = cases.cavern_case(grid, n_steps=cpu["n_steps_run"], ksp_type=args.ksp, rtol=args.rtol)
+    eq, sim = cases.build(case, grid, device=dev)
+    sim.verbose = False
+    if pc == "mg":
+        eq.solver.getPC().setType("mg")
+    apply_solver_settings(eq.solver, args.warm_start, args.mg_lag)
+    recs = sim.run()
+    u = eq.X.reshape(-1).cpu().numpy()
+    sig = eq.engine.get6(eq.engine.sig)
+    rel = lambda a, b: float(abs(a - b).max() / abs(b).max())
+    return {"mesh": f"cavern_regular x8^{cpu['levels']} ({tm.n_cells} cells), {cpu['n_steps_run']} time step(s)",
+            "against": "CPU arm (oracle port, block-Jacobi PCG to the same rtol)", "u_max_rel": rel(u, cpu["u"]),
+            "sigma_max_rel": rel(sig, cpu["sig"]), "newton_iterations_gpu": sum(r["iterations"] for r in recs),
+            "newton_iterations_cpu": cpu["newton_iterations"], "rtol": args.rtol,
+            "solver_settings": f"pc={pc}, warm_start={args.warm_start}, mg_lag={args.mg_lag}"}
 
 
 if __name__ == "__main__":

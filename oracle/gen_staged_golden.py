@@ -46,5 +46,39 @@ def main(name="cavern_irregular_finemesh", n_eq=2, n_op=2):
           f"{int((desai.Fvp > 0).sum())}, clamped alpha_0 {desai.n_disabled}")
 
 
+def main_cfg2(levels=1, n_steps=2):
+    """BASELINE config 2 (cavern_regular, cyclic gas pressure, theta = 0, Spring + DislocationCreep, dt = 2 h) on the
+    grid red-refined `levels` times -- the bench workload at the size the oracle's sparse LU still finishes in minutes:
+
+        python oracle/gen_staged_golden.py cfg2          # writes tests/golden/cfg2_cavern_regular_L1.npz
+
+    The mesh is the finest level of multigrid.refine_hierarchy (what the multigrid tests and bench.py build)."""
+    import safeincave_b200 as sf
+    from safeincave_b200 import cases
+    from safeincave_b200.mesh import TetMesh
+    from safeincave_b200.multigrid import refine_hierarchy
+    from tests.case_oracle import oracle_simulator
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz")), levels)
+    tm = h.finest
+    grid = sf.GridHandlerGMSH.from_hierarchy(h)
+    case = cases.cavern_case(grid, n_steps=n_steps, ksp_type="cg", rtol=1e-12)
+    t0 = time.time()
+    hist = oracle_simulator(case, tm).run(0.0, [case["dt"]] * n_steps)
+    for r in hist[1:]:
+        print(r["iters"], r["error"], r["converged"], r["dt_used"])
+        assert r["converged"] and r["dt_used"] == case["dt"] and np.isfinite(r["u"]).all()
+    last = hist[-1]
+    sel = np.arange(0, tm.n_cells, 16)
+    out = os.path.join(ROOT, "tests", "golden", f"cfg2_cavern_regular_L{levels}.npz")
+    np.savez_compressed(out, levels=levels, n_steps=n_steps, n_cells=tm.n_cells, iters=np.array([r["iters"] for r in hist[1:]]),
+                        u=last["u"], cell_sel=sel, sig_sel=last["sig"][sel], eps_sel=last["eps"][sel],
+                        sig_absmax=np.abs(last["sig"]).max(), eps_absmax=np.abs(last["eps"]).max(),
+                        sig_norm=np.linalg.norm(last["sig"]), coords_checksum=float(np.abs(tm.coords).sum()))
+    print(f"wrote {out} ({os.path.getsize(out) / 1e6:.1f} MB) in {time.time() - t0:.0f} s")
+
+
 if __name__ == "__main__":
-    main(*sys.argv[1:2])
+    if sys.argv[1:2] == ["cfg2"]:
+        main_cfg2()
+    else:
+        main(*sys.argv[1:2])

@@ -61,8 +61,8 @@ def dry(monkeypatch):
     return bench
 
 
-def run(bench, capsys, *flags):
-    argv = ["bench.py", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + list(flags)
+def run(bench, capsys, *flags, cpu_baseline=False):
+    argv = ["bench.py", "--steps", "2", "--warmup", "1"] + ([] if cpu_baseline else ["--no-cpu-baseline"]) + list(flags)
     old = sys.argv
     sys.argv = argv
     try:
@@ -97,6 +97,27 @@ def test_bench_line_multigrid(dry, capsys):
     check_contract(line, "mg")
     mg = line["constitutive"]["mg"]
     assert mg["setup_lag"] == 2 and 0 < mg["setups"] < mg["solves"] and len(mg["lambda_max"]) == 3
+
+
+def test_bench_line_cpu_arm_and_parity_check(dry, capsys):
+    """The CPU leg of the GPU line (oracle/cpu_step.py on the same mesh family) and the parity check of the timed
+    solver settings against its fields."""
+    line = run(dry, capsys, "--pc", "mg", "--levels", "2", "--cpu-levels", "1", "--cpu-threads", "2", cpu_baseline=True)
+    check_contract(line, "mg")
+    cb, pc = line["cpu_baseline"], line["parity_check"]
+    assert cb["kind"] == "port" and cb["cores"] == 2 and cb["value"] > 0 and cb["n_cells"] == 384 and "PCG" in cb["sample"]
+    assert pc["u_max_rel"] < 1e-8 and pc["sigma_max_rel"] < 1e-8
+    assert pc["newton_iterations_gpu"] == pc["newton_iterations_cpu"] and "mg_lag=2" in pc["solver_settings"]
+
+
+def test_reference_arm_line(dry, capsys, monkeypatch):
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-threads", "2"])
+    dry.run_reference(dry.parse())
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "cell_updates_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["n_cells"] == 384 and line["cpu_baseline_unrefined_lu"]["cores"] == 1
 
 
 def test_bench_line_block_jacobi(dry, capsys):
