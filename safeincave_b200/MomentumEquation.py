@@ -260,7 +260,9 @@ class LinearMomentum(LinearMomentumBase):
             from .multigrid import Multigrid
             part = getattr(self.grid, "partition", None) if (self.dist is not None and self.dist.world > 1) else None
             self.mg = Multigrid(eng, self.grid.hierarchy, part=part, coarse_fixed=self._coarse_dirichlet_mask,
-                                **self.mg_options)
+                                dist=self.dist if part is not None else None,
+                                **{"dist_min_cells_per_rank": getattr(self.grid, "dist_min_cells_per_rank", 200_000),
+                                   **self.mg_options})
         lag = ksp.mg_setup_first > 0 and self.mg.setups > 0 and not self._elastic_tangent_live \
             and self._solves_in_step >= ksp.mg_setup_first and 0.0 <= self._last_newton_error <= ksp.mg_setup_error
         if not lag:

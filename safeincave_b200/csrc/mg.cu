@@ -18,12 +18,14 @@
 // The outer CG keeps its scalars on the device (as solver.cu does) and the host looks at them every
 // `check_every` iterations; every kernel of the cycle is a no-op once the `done` flag is up.
 //
-// Several GPUs (levels[top].halo != NULL): the FINEST level is partitioned by cells exactly as in solver.cu
-// (interface nodes duplicated, vectors kept consistent, operator results completed by sic_exchange over NVLink,
-// dot products with owner weights + scalar exchange); every COARSER level is replicated on every rank.  The
-// finest level carries 7/8 of the work of a cycle, the replicated part costs each rank 1/7 of one fine-level
-// sweep, and the only extra traffic is one all-reduce of the first coarse right-hand side per cycle (and of
-// the first coarse C_T per tangent).  Transfers of the finest level index the coarse level GLOBALLY.
+// Several GPUs (levels[l].halo != NULL): the levels from some level `lc` up to the finest are partitioned by cells
+// exactly as in solver.cu (interface nodes duplicated, vectors kept consistent, operator results completed by
+// sic_exchange over NVLink, dot products with owner weights + scalar exchange), NESTED: a cell lives on the rank of
+// its ancestor on level lc, so children, prolongation parents and the Galerkin coarsening of C_T are rank-local
+// between two partitioned levels, and the restriction (summed by the owners of the fine nodes) is completed by one
+// halo sum on the coarse level.  The levels below lc are replicated on every rank: the transfers of level lc index
+// level lc-1 GLOBALLY, its right-hand side is completed by one all-reduce per cycle and its C_T by one all-reduce per
+// tangent (small: the host keeps lc-1 at <= a few 100k cells).
 #include <math.h>
 #include <string.h>
 
@@ -427,13 +429,17 @@ static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_
     if (!L.fixed || !L.dinv || !L.x || !L.b || !L.r || !L.d || !L.t || !L.prob.CT)
       return sic_fail("multigrid: level with a null buffer");
     const bool part = L.halo && L.halo->n_ranks > 1;
-    if (part && l != n_levels - 1) return sic_fail("multigrid: only the finest level may be partitioned (coarser ones are replicated)");
+    if (part && l == 0) return sic_fail("multigrid: the coarsest level must be replicated (not partitioned)");
+    if (part && l + 1 < n_levels && !(lv[l + 1].halo && lv[l + 1].halo->n_ranks > 1))
+      return sic_fail("multigrid: every level above a partitioned level must be partitioned");
     if (part && (!L.halo->owner_w || !L.halo->comm)) return sic_fail("multigrid: halo without owner weights / communicator");
     if (part && n_levels < 2) return sic_fail("multigrid: a partitioned run needs at least two levels");
     if (l > 0) {
       if (!L.parent_a || !L.parent_b || !L.rst_ptr || !L.rst_idx || !L.children)
         return sic_fail("multigrid: level without transfer tables");
-      if (!part && L.prob.n_cells != 8 * lv[l - 1].prob.n_cells) return sic_fail("multigrid: levels are not nested 1:8");
+      const bool cpart = lv[l - 1].halo && lv[l - 1].halo->n_ranks > 1;
+      // nested 1:8: on one GPU, and between two partitioned levels (a cell lives on its parent's rank)
+      if ((!part || cpart) && L.prob.n_cells != 8 * lv[l - 1].prob.n_cells) return sic_fail("multigrid: levels are not nested 1:8");
     }
   }
   return 0;
@@ -568,11 +574,15 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
     if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
     k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
-    // several GPUs: every fine node is restricted by its owner only, then the (replicated) coarse right-hand side is
-    // completed by one all-reduce over NVLink
+    // several GPUs: every fine node is restricted by its owner only; the coarse right-hand side is then completed by a
+    // halo sum when the coarse level is partitioned too (nested partition: the parents of an owned fine node are
+    // local), by one all-reduce over NVLink when it is replicated
     k_mg_restrict<<<mg_blocks(C.prob.n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(
         C.prob.n_nodes, L.rst_ptr, L.rst_idx, L.r, C.b, C.fixed, h ? h->owner_w : nullptr, done);
-    if (h) if (int rc = sic_allreduce_sum(h->comm, C.b, 3 * C.prob.n_nodes, (void*)st)) return rc;
+    if (h) {
+      if (const sic_halo_t* hc = mg_halo(C)) { if (int rc = sic_exchange(hc, C.b, 3, nullptr, 0, (void*)st)) return rc; }
+      else if (int rc = sic_allreduce_sum(h->comm, C.b, 3 * C.prob.n_nodes, (void*)st)) return rc;
+    }
   }
   {
     const sic_mg_level_t& L = lv[0];
@@ -599,14 +609,16 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (o->power_its_warm < 0) return sic_fail("sic_mg_setup: power_its_warm must be >= 0");
   if (int rc = mg_host_mirror()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // 1. Galerkin coarse tangents, fine to coarse (several GPUs: every rank sums the children it holds, then one
-  //    all-reduce completes the first coarse level; the levels below are computed redundantly)
+  // 1. Galerkin coarse tangents, fine to coarse (several GPUs: rank-local between partitioned levels; into the first
+  //    replicated level every rank sums the children it holds and one all-reduce completes it; the levels below are
+  //    computed redundantly)
   for (int l = n_levels - 1; l >= 1; --l) {
     const int ncoarse = lv[l - 1].prob.n_cells;
     if (ncoarse > 0)
       k_mg_ct_coarsen<<<mg_blocks(ncoarse, 128), 128, 0, st>>>(ncoarse, lv[l].children, lv[l].prob.CT, lv[l - 1].prob.CT);
     if (int rc = sic_check_launch("k_mg_ct_coarsen")) return rc;
-    if (const sic_halo_t* h = mg_halo(lv[l])) {
+    const sic_halo_t* h = mg_halo(lv[l]);
+    if (h && !mg_halo(lv[l - 1])) {      // replicated coarse level: partial sums of the children each rank holds
       const int64_t cnt = 36 * (int64_t)lv[l - 1].prob.cell_stride;
       if (cnt > 2147483647) return sic_fail("sic_mg_setup: coarse C_T too large for one all-reduce");
       if (int rc = sic_allreduce_sum(h->comm, lv[l - 1].prob.CT, (int)cnt, stream)) return rc;

@@ -94,15 +94,23 @@ def init(device=None) -> DistContext:
     return DistContext(rank, world, device, comm)
 
 
-def partition_grid(ctx: DistContext, tetmesh, hierarchy=None):
+def partition_grid(ctx: DistContext, tetmesh, hierarchy=None, min_cells_per_rank=200_000):
     """Every rank holds the same global (Morton-ordered) mesh; returns (local grid, Partition).
-    hierarchy: the GLOBAL multigrid hierarchy whose finest level is ``tetmesh`` (kept on the local grid for PC mg:
-    the finest level is distributed, the coarser ones replicated)."""
+    hierarchy: the GLOBAL multigrid hierarchy whose finest level is ``tetmesh`` (kept on the local grid for PC mg).
+    With a nested hierarchy (multigrid.refine_hierarchy(..., nested=True)) the cells are cut by their ancestors on the
+    coarsest level that still gives every rank ``min_cells_per_rank`` cells, so that the multigrid can partition every
+    level from there up (multigrid.distributed_from); otherwise into equal chunks of the finest level's order."""
+    bounds = None
+    if hierarchy is not None and getattr(hierarchy, "nested", False) and ctx.world > 1:
+        from .multigrid import distributed_from, nested_bounds
+        lc = distributed_from(hierarchy, ctx.world, min_cells_per_rank)
+        bounds = nested_bounds(hierarchy, ctx.world, hierarchy.n_levels - 1, lc)
     part = build_partition(tetmesh.cells, tetmesh.n_nodes, ctx.rank, ctx.world,
-                           device=ctx.device if ctx.device.type == "cuda" else "cpu")
+                           device=ctx.device if ctx.device.type == "cuda" else "cpu", bounds=bounds)
     local = part.local_mesh(tetmesh)
     grid = GridHandlerGMSH.from_mesh(local, reorder=False)
     grid.partition = part
+    grid.dist_min_cells_per_rank = min_cells_per_rank
     if hierarchy is not None:
         grid.hierarchy = hierarchy
     return grid, part

@@ -265,8 +265,10 @@ def morton_keys(points: torch.Tensor) -> torch.Tensor:
     return _spread3(q[:, 0]) | (_spread3(q[:, 1]) << 1) | (_spread3(q[:, 2]) << 2)
 
 
-def morton_order(mesh: TetMesh, device="cpu") -> TetMesh:
-    """Renumber nodes and cells along a Morton curve (nodes by position, cells by centroid)."""
+def morton_order(mesh: TetMesh, device="cpu", keep_cell_order=False) -> TetMesh:
+    """Renumber nodes and cells along a Morton curve (nodes by position, cells by centroid).
+    keep_cell_order: renumber the nodes only (a red-refined mesh lists the eight children of every parent cell
+    together, in the parents' order: the NESTED order a multi-GPU multigrid hierarchy is partitioned in)."""
     dev = torch.device(device)
     coords = torch.as_tensor(mesh.coords, device=dev)
     cells = torch.as_tensor(mesh.cells, device=dev)
@@ -275,7 +277,10 @@ def morton_order(mesh: TetMesh, device="cpu") -> TetMesh:
     ninv[nperm] = torch.arange(nperm.numel(), device=dev)
     cells = ninv[cells]
     coords = coords[nperm]
-    cperm = torch.argsort(morton_keys(coords[cells].mean(dim=1)))
+    if keep_cell_order:
+        cperm = torch.arange(cells.shape[0], device=dev)
+    else:
+        cperm = torch.argsort(morton_keys(coords[cells].mean(dim=1)))
     tris = ninv[torch.as_tensor(mesh.tris, device=dev)] if mesh.tris.shape[0] else torch.as_tensor(mesh.tris)
     out = TetMesh(coords.cpu().numpy(), cells[cperm].cpu().numpy(), mesh.cell_tags[cperm.cpu().numpy()],
                   tris.cpu().numpy(), mesh.tri_tags.copy(), mesh.names)

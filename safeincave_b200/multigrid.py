@@ -64,17 +64,44 @@ def _transfer(coarse: TetMesh, fine_raw: TetMesh, edges: np.ndarray, fine: TetMe
     return Transfer(i32(pa), i32(pb), i32(ptr), i32(idx[order]), i32(children), i32(inject))
 
 
-def refine_hierarchy(base: TetMesh, levels: int, device="cpu") -> Hierarchy:
-    """``levels`` regular refinements of ``base``; returns all levels (level 0 = ``base`` in Morton order)."""
+def refine_hierarchy(base: TetMesh, levels: int, device="cpu", nested=False) -> Hierarchy:
+    """``levels`` regular refinements of ``base``; returns all levels (level 0 = ``base`` in Morton order).
+    nested: every refined level keeps the eight children of a cell together, in the order of the parents (cell 8 c + j
+    of level l is child j of cell c of level l-1) -- a hierarchical space-filling order in which an equal-chunk cell
+    partition of ANY level induces contiguous chunks on every finer level (what the multi-GPU multigrid partitions
+    by, ``nested_bounds``); nodes are Morton-ordered either way."""
     m0 = base if hasattr(base, "cell_perm") else morton_order(base, device=device)
     h = Hierarchy([m0], [None])
+    h.nested = bool(nested)
     for _ in range(levels):
         coarse = h.meshes[-1]
         raw, edges = red_refine(coarse, device=device, return_edges=True)
-        fine = morton_order(raw, device=device)
+        fine = morton_order(raw, device=device, keep_cell_order=nested)
         h.transfers.append(_transfer(coarse, raw, edges, fine))
         h.meshes.append(fine)
     return h
+
+
+def distributed_from(hierarchy: Hierarchy, n_ranks: int, min_cells_per_rank: int = 200_000) -> int:
+    """Index of the coarsest level a multi-GPU multigrid PARTITIONS (every level from it to the finest is partitioned,
+    the ones below are replicated on every rank): the coarsest level >= 1 that still gives every rank
+    ``min_cells_per_rank`` cells -- below that a level's kernels are launch-latency bound and an exchange per operator
+    application costs more than computing the level redundantly.  Without a nested hierarchy only the finest level can
+    be partitioned."""
+    top = hierarchy.n_levels - 1
+    if n_ranks <= 1 or not getattr(hierarchy, "nested", False):
+        return top
+    lc = top
+    while lc - 1 >= 1 and hierarchy.meshes[lc - 1].n_cells >= min_cells_per_rank * n_ranks:
+        lc -= 1
+    return lc
+
+
+def nested_bounds(hierarchy: Hierarchy, n_ranks: int, level: int, lc: int):
+    """Cell ranges of the ranks on ``level`` >= lc: level lc is cut into equal chunks of its (Morton) order and every
+    finer cell belongs to the rank of its ancestor on level lc (offsets scale by 8 per level)."""
+    from .partition import chunk_bounds
+    return [b * 8 ** (level - lc) for b in chunk_bounds(hierarchy.meshes[lc].n_cells, n_ranks)]
 
 
 def _localise(t: Transfer, part, n_coarse_nodes: int) -> Transfer:
@@ -93,6 +120,33 @@ def _localise(t: Transfer, part, n_coarse_nodes: int) -> Transfer:
     ch = np.where((ch >= c0) & (ch < c1), ch - c0, -1)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
     return Transfer(i32(pa), i32(pb), i32(ptr), i32(idx[order]), i32(ch), t.inject)
+
+
+def _localise_pair(t: Transfer, part_f, part_c, n_coarse_nodes: int) -> Transfer:
+    """Transfer tables between TWO partitioned levels of a nested partition, in the rank's local numbering on both
+    sides: the parents of every local fine node are vertices of a local coarse cell, and the eight children of a local
+    coarse cell are local fine cells."""
+    ln_f, ln_c = part_f.local_nodes.cpu().numpy(), part_c.local_nodes.cpu().numpy()
+    lut = np.full(n_coarse_nodes, -1, dtype=np.int64)
+    lut[ln_c] = np.arange(ln_c.size)
+    pa, pb = lut[t.parent_a[ln_f].astype(np.int64)], lut[t.parent_b[ln_f].astype(np.int64)]
+    if (pa < 0).any() or (pb < 0).any():
+        raise ValueError("the partitions of two multigrid levels are not nested (a fine node's parent is not local)")
+    m, mc = ln_f.size, ln_c.size
+    rows = np.concatenate([pa, pb])
+    idx = np.concatenate([np.arange(m), np.arange(m)])
+    order = np.argsort(rows, kind="stable")
+    ptr = np.zeros(mc + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum(np.bincount(rows, minlength=mc))
+    (f0, f1), (c0, c1) = part_f.cell_range, part_c.cell_range
+    ch = t.children[:, c0:c1].astype(np.int64) - f0
+    if ch.size and (ch.min() < 0 or ch.max() >= f1 - f0):
+        raise ValueError("the partitions of two multigrid levels are not nested (a child cell is not local)")
+    lut_f = np.full(t.parent_a.shape[0], -1, dtype=np.int64)
+    lut_f[ln_f] = np.arange(m)
+    inj = lut_f[t.inject[ln_c].astype(np.int64)]
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return Transfer(i32(pa), i32(pb), i32(ptr), i32(idx[order]), i32(ch), i32(inj))
 
 
 def prolongation_matrix(t: Transfer, n_coarse_nodes: int):
@@ -114,11 +168,14 @@ class Multigrid:
     the coarse levels are operator-only engines whose C_T ``setup()`` fills by Galerkin coarsening."""
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01,
-                 safety=1.15, power_its=32, power_its_warm=4, part=None, coarse_fixed=None):
-        """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one):
-        the finest level is distributed, the coarser ones are replicated on every rank (csrc/mg.cu).
-        coarse_fixed: callable(level index, TetMesh) -> uint8 (3 M,) Dirichlet mask of a coarse level; needed when the
-        finest level is partitioned (a rank cannot inject a mask it only holds a part of)."""
+                 safety=1.15, power_its=32, power_its_warm=4, part=None, coarse_fixed=None, dist=None,
+                 dist_min_cells_per_rank=200_000):
+        """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one).
+        With a NESTED hierarchy (refine_hierarchy(..., nested=True)) and ``dist`` (the DistContext, for the levels'
+        own exchange mailboxes) every level down to ``distributed_from(...)`` is partitioned by the rank's ancestors'
+        cells; the levels below are replicated on every rank (csrc/mg.cu).  Otherwise only the finest level is.
+        coarse_fixed: callable(level index, TetMesh) -> uint8 (3 M,) Dirichlet mask of a coarse level (global
+        numbering); needed when the finest level is partitioned (a rank cannot inject a mask it holds a part of)."""
         import ctypes
 
         import torch
@@ -144,11 +201,34 @@ class Multigrid:
         self.coarse_fixed = coarse_fixed
         self.h, self.fine = hierarchy, fine_engine
         self.lib, dev = fine_engine.lib, fine_engine.device
-        self.engines = [type(fine_engine)(m.coords, m.cells, device=dev, operator_only=True)
-                        for m in hierarchy.meshes[:-1]] + [fine_engine]
+        n = hierarchy.n_levels
+        # per-level partitions of a nested multi-GPU hierarchy: parts[l] is None for a replicated level
+        self.parts = [None] * n
+        self.lc = n - 1
+        if self.part is not None:
+            self.parts[-1] = self.part
+            lc = distributed_from(hierarchy, self.part.n_ranks, dist_min_cells_per_rank) if dist is not None else n - 1
+            if lc < n - 1 and list(self.part.bounds) != nested_bounds(hierarchy, self.part.n_ranks, n - 1, lc):
+                lc = n - 1            # the finest level was not partitioned by ancestors: replicate everything below it
+            self.lc = lc
+            from .partition import build_partition
+            for l in range(lc, n - 1):
+                m = hierarchy.meshes[l]
+                self.parts[l] = build_partition(m.cells, m.n_nodes, self.part.rank, self.part.n_ranks, device=dev,
+                                                bounds=nested_bounds(hierarchy, self.part.n_ranks, l, lc))
+        self.engines = []
+        for l, m in enumerate(hierarchy.meshes[:-1]):
+            pl = self.parts[l]
+            if pl is None:
+                eng = type(fine_engine)(m.coords, m.cells, device=dev, operator_only=True)
+            else:
+                eng = type(fine_engine)(m.coords[pl.local_nodes.cpu().numpy()], pl.cells_local.cpu().numpy(), device=dev,
+                                        operator_only=True)
+                eng.set_partition(pl, dist.comm, dist.make_p2p(pl))
+            self.engines.append(eng)
+        self.engines.append(fine_engine)
         self.opts = L.SicMgOpts(int(nu), int(coarse_its), float(smooth_lo), float(coarse_lo), float(safety), int(power_its),
                                 int(power_its_warm))
-        n = hierarchy.n_levels
         self.levels = (L.SicMgLevel * n)()
         self._keep = []
         zeros = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype, device=dev)
@@ -162,8 +242,10 @@ class Multigrid:
             lv.lambda_max = 0.0
             if l > 0:
                 t = hierarchy.transfers[l]
-                if self.part is not None and l == n - 1:
-                    t = _localise(t, self.part, hierarchy.meshes[l - 1].n_nodes)
+                if self.parts[l] is not None and self.parts[l - 1] is not None:
+                    t = _localise_pair(t, self.parts[l], self.parts[l - 1], hierarchy.meshes[l - 1].n_nodes)
+                elif self.parts[l] is not None:
+                    t = _localise(t, self.parts[l], hierarchy.meshes[l - 1].n_nodes)
                 tabs = {k: dt(getattr(t, k)) for k in ("parent_a", "parent_b", "rst_ptr", "rst_idx", "children", "inject")}
                 self._keep.append(tabs)
                 lv.parent_a, lv.parent_b = _ptr(tabs["parent_a"]), _ptr(tabs["parent_b"])
@@ -191,8 +273,9 @@ class Multigrid:
             lv = self.levels[l]
             lv.prob = eng.problem()
             lv.fixed, lv.dinv = _ptr(self.fixed[l]), _ptr(self.dinv[l])
-        if self.part is not None:
-            self.levels[n - 1].halo = self._ct.cast(self._ct.pointer(self.fine.halo), self._ct.c_void_p)
+        for l, eng in enumerate(self.engines):
+            if self.parts[l] is not None:
+                self.levels[l].halo = self._ct.cast(self._ct.pointer(eng.halo), self._ct.c_void_p)
 
     def setup(self, fixed_fine, dinv_fine):
         """Once per tangent: inject the Dirichlet mask down the hierarchy, then sic_mg_setup (Galerkin C_T,
@@ -203,10 +286,18 @@ class Multigrid:
             for l in range(len(self.engines) - 1, 0, -1):
                 inj = self._keep[l]["inject"].long()
                 self.fixed[l - 1].view(-1, 3).copy_(self.fixed[l].view(-1, 3)[inj])
-        else:       # replicated coarse levels: every rank builds their masks from the boundary data of the coarse meshes
-            for l in range(len(self.engines) - 1):
-                m = self._to.as_tensor(self.coarse_fixed(l, self.h.meshes[l])).to(self.fixed[l].device, dtype=self._to.uint8)
-                self.fixed[l].copy_(m.reshape(-1))
+        else:       # every rank builds the coarse masks from the boundary data of the (global) coarse meshes, once per
+            # set of Dirichlet boundaries; a partitioned coarse level keeps the rows of its local nodes
+            bc = getattr(getattr(self.coarse_fixed, "__self__", None), "bc", None)
+            key = tuple((b.boundary_name, int(b.component)) for b in bc.dirichlet_boundaries) if bc is not None else None
+            if key is None or key != getattr(self, "_mask_key", ()):
+                for l in range(len(self.engines) - 1):
+                    m = np.asarray(self.coarse_fixed(l, self.h.meshes[l])).reshape(-1, 3)
+                    if self.parts[l] is not None:
+                        m = m[self.parts[l].local_nodes.cpu().numpy()]
+                    self.fixed[l].copy_(self._to.as_tensor(np.ascontiguousarray(m)).to(self.fixed[l].device,
+                                                                                   dtype=self._to.uint8).reshape(-1))
+                self._mask_key = key
         st = self.fine._stream()
         L.check(self.lib.sic_mg_setup(self.levels, len(self.engines), self._ct.byref(self.opts), self._ptr(self.work), st),
                 "sic_mg_setup")

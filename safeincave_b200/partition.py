@@ -33,6 +33,7 @@ class Partition:
     n_global_cells: int = 0
     n_global_nodes: int = 0
     touch: torch.Tensor = None         # (M_global,) bitmask of the ranks touching each global node
+    bounds: list = None                # cell ranges of ALL ranks: rank r holds [bounds[r], bounds[r+1])
 
     @property
     def n_interface(self):
@@ -71,13 +72,18 @@ def chunk_bounds(n_cells, n_ranks):
     return [(n_cells * r) // n_ranks for r in range(n_ranks + 1)]
 
 
-def build_partition(cells, n_nodes, rank, n_ranks, device="cpu") -> Partition:
+def build_partition(cells, n_nodes, rank, n_ranks, device="cpu", bounds=None) -> Partition:
     """cells: (N,4) global connectivity (Morton ordered).  Deterministic: every rank computes the same
-    sharing pattern from the same global mesh, so no communication is needed to agree on the plan."""
+    sharing pattern from the same global mesh, so no communication is needed to agree on the plan.
+    bounds: the ranks' cell ranges (n_ranks + 1 ascending offsets) when they are not the equal chunks of the order --
+    the nested partition of a multigrid hierarchy cuts a COARSE level into equal chunks and gives every finer cell
+    to the rank of its ancestor (multigrid.nested_bounds)."""
     dev = torch.device(device)
     cells = torch.as_tensor(cells, device=dev).long()
     N = int(cells.shape[0])
-    b = chunk_bounds(N, n_ranks)
+    b = chunk_bounds(N, n_ranks) if bounds is None else [int(x) for x in bounds]
+    if len(b) != n_ranks + 1 or b[0] != 0 or b[-1] != N or any(b[i] > b[i + 1] for i in range(n_ranks)):
+        raise ValueError("bounds must be n_ranks + 1 ascending offsets from 0 to the number of cells")
     # bitmask of ranks touching each node (n_ranks <= 62)
     touch = torch.zeros(n_nodes, dtype=torch.int64, device=dev)
     for r in range(n_ranks):
@@ -99,7 +105,7 @@ def build_partition(cells, n_nodes, rank, n_ranks, device="cpu") -> Partition:
         if sel.numel():
             peers.append(r)
             shared.append(sel)
-    return Partition(rank, n_ranks, (c0, c1), local_nodes, cells_local, owner_w, peers, shared, N, n_nodes, touch)
+    return Partition(rank, n_ranks, (c0, c1), local_nodes, cells_local, owner_w, peers, shared, N, n_nodes, touch, b)
 
 
 def halo_sum_reference(part: Partition, vec: torch.Tensor, group=None):

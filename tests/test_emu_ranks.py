@@ -20,12 +20,13 @@ def sf():
     sf.LinearMomentum.engine_cls = old
 
 
-def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None, multigrid=False):
+def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None, multigrid=False, nested=False,
+                          min_cells_per_rank=200_000):
     from safeincave_b200 import cases, distributed
     from safeincave_b200.mesh import TetMesh
     from safeincave_b200.multigrid import refine_hierarchy
     from tests.hostemu.ranks import run_ranks
-    h = refine_hierarchy(TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz")), levels)
+    h = refine_hierarchy(TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz")), levels, nested=nested)
     tm = h.finest
     gg = sf.GridHandlerGMSH.from_hierarchy(h)
     case = cases.triaxial_case(gg, n_steps=n_steps, ksp_override=ksp)
@@ -38,7 +39,8 @@ def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None, 
     hist1 = sim1.run()
 
     def body(ctx):
-        grid, part = distributed.partition_grid(ctx, tm, hierarchy=h if multigrid else None)
+        grid, part = distributed.partition_grid(ctx, tm, hierarchy=h if multigrid else None,
+                                                min_cells_per_rank=min_cells_per_rank)
         eq, sim = cases.build(case, grid, part=part, ctx=ctx)
         if setup:
             setup(eq, grid, part)
@@ -50,7 +52,8 @@ def partitioned_vs_single(sf, world, ksp="cg", levels=1, n_steps=2, setup=None, 
         return dict(e_u=rel(eq.X, eq1.X[ln]), e_s=rel(eq.engine.sig[:, :eq.engine.N], eq1.engine.sig[:, c0:c1]),
                     e_c=rel(eq.engine.elems[1].eps_old[:, :eq.engine.N], eq1.engine.elems[1].eps_old[:, c0:c1]),
                     newton=[h["iterations"] for h in hist], ksp=[h["ksp_iterations"] for h in hist],
-                    peers=part.peers, n=eq.engine.N)
+                    peers=part.peers, n=eq.engine.N, lc=eq.mg.lc if eq.mg is not None else None,
+                    level_cells=[e.N for e in eq.mg.engines] if eq.mg is not None else None)
 
     res = run_ranks(world, body)
     for r in res:
@@ -77,6 +80,19 @@ def test_partitioned_multigrid_matches_single_rank(sf, world):
     for r in res:
         assert all(abs(a - b) <= 2 for a, b in zip(r["ksp"], r["ksp1"])), (r["ksp"], r["ksp1"])
         assert max(r["ksp"]) < 250
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_nested_partition_distributes_the_coarse_levels(sf, world):
+    """A nested hierarchy (children listed with their parent) partitioned by the ancestors on level 1: levels 1 and 2 are
+    distributed (rank-local transfers and C_T coarsening, restriction completed by a halo sum on the coarse level),
+    level 0 is replicated.  Same fields, Newton history and Krylov counts as the single-rank run."""
+    res, hist1 = partitioned_vs_single(sf, world, "cg", levels=2, n_steps=2, multigrid=True, nested=True,
+                                       min_cells_per_rank=100)
+    for r in res:
+        assert r["lc"] == 1 and r["level_cells"][0] == 48 and r["level_cells"][2] == 8 * r["level_cells"][1]
+        assert all(abs(a - b) <= 2 for a, b in zip(r["ksp"], r["ksp1"])), (r["ksp"], r["ksp1"])
+    assert sum(r["level_cells"][1] for r in res) == 384
 
 
 def test_bench_multigrid_probe_on_emulated_ranks(sf):
