@@ -66,6 +66,12 @@ def parse():
     ap.add_argument("--mg-lag", type=int, default=2,
                     help="PC mg: rebuild the preconditioner on the first MG_LAG Newton iterations of a time step and "
                          "afterwards only while the Newton error is above 1e-3 (KSP.mg_setup_first); 0: for every tangent")
+    ap.add_argument("--nested", type=int, default=1,
+                    help="1: hierarchical cell order (the eight children of a cell listed together, in the parents' order), "
+                         "which lets several GPUs partition the coarse multigrid levels too; 0: every level in its own "
+                         "Morton order (several GPUs: only the finest level is partitioned)")
+    ap.add_argument("--min-cells-per-rank", type=int, default=100_000,
+                    help="several GPUs, PC mg: levels with fewer cells per rank than this are replicated on every rank")
     ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-fallback", action="store_true",
                     help="N = 1: do not retry with the configurations measured earlier when the run fails its own checks")
@@ -282,7 +288,7 @@ def probe_mg(levels=2, device="cuda:0", warm_start=2, mg_lag=2):
     return 0 if ok else 1
 
 
-def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None, warm_start=2, mg_lag=2):
+def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None, warm_start=2, mg_lag=2, min_cells_per_rank=2000):
     """The same comparison as probe_mg for a run on several GPUs, IN PROCESS and collectively: one time step of the
     cavern case on cavern_regular x8^levels, partitioned over the ranks, with block-Jacobi CG and with the multigrid
     CG (finest level distributed, coarser levels replicated).  Every rank compares its own part; the verdict is the
@@ -294,12 +300,14 @@ def probe_mg_ranks(ctx, levels=1, mesh="cavern_regular", case_fn=None, warm_star
     from safeincave_b200.multigrid import refine_hierarchy
     dev, ok, msg = ctx.device, 1, ""
     try:
-        h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", f"mesh_{mesh}.npz")), levels, device=dev)
+        h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", f"mesh_{mesh}.npz")), levels, device=dev,
+                             nested=True)
         gg = sf.GridHandlerGMSH.from_hierarchy(h)
         case = case_fn(gg) if case_fn else cases.cavern_case(gg, n_steps=1, ksp_type="cg", rtol=1e-10)
         out = {}
         for pc in ("jacobi", "mg"):
-            grid, part = distributed.partition_grid(ctx, h.finest, hierarchy=h if pc == "mg" else None)
+            grid, part = distributed.partition_grid(ctx, h.finest, hierarchy=h if pc == "mg" else None,
+                                                    min_cells_per_rank=min_cells_per_rank)
             eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
             if pc == "mg":
                 eq.solver.getPC().setType("mg")
@@ -370,7 +378,9 @@ def run_b200(args):
     tm = TetMesh.load_npz(os.path.join(ROOT, "tests", "golden", "mesh_cavern_regular.npz"))
     if pc == "mg":
         from safeincave_b200.multigrid import refine_hierarchy
-        hierarchy = refine_hierarchy(tm, args.levels, device=dev)      # every level kept, each in Morton order
+        # every level kept; nested order (children listed with their parent) so that several GPUs can partition the
+        # coarse levels too (multigrid.distributed_from), the SAME numbering at every N
+        hierarchy = refine_hierarchy(tm, args.levels, device=dev, nested=bool(args.nested))
         tm = hierarchy.finest
         grid_global = sf.GridHandlerGMSH.from_hierarchy(hierarchy)
     else:
@@ -382,7 +392,8 @@ def run_b200(args):
     n_total = args.warmup + args.steps * (1 if args.no_e2e else 2)
     case = cases.cavern_case(grid_global, n_steps=n_total, ksp_type=args.ksp, rtol=args.rtol)
     if world > 1:            # strong scaling: the SAME mesh, cells partitioned along the Morton curve
-        grid, part = distributed.partition_grid(ctx, tm, hierarchy=hierarchy if pc == "mg" else None)
+        grid, part = distributed.partition_grid(ctx, tm, hierarchy=hierarchy if pc == "mg" else None,
+                                                min_cells_per_rank=args.min_cells_per_rank)
         eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
     else:
         grid, part = grid_global, None
@@ -519,9 +530,10 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.levels, N), "n_cells": N, "n_nodes": M,
                    "cells_per_gpu": N_loc, "partition": ("single GPU" if world == 1 else (
-                       "Morton-curve cell chunks, interface nodes duplicated, P2P halo sum + scalar sums over NVLink in one kernel"
-                       + ("; multigrid: finest level distributed, coarser levels replicated, one all-reduce of the coarse "
-                          "right-hand side per cycle" if pc == "mg" else ""))),
+                       "contiguous cell chunks of the (hierarchical) Morton order, interface nodes duplicated, P2P halo sum + scalar sums over NVLink in one kernel"
+                       + (("; multigrid: levels %d..%d partitioned by the cells' ancestors (rank-local transfers, halo sums), "
+                           "levels below replicated (one all-reduce of the first replicated right-hand side per cycle)"
+                           % (eq.mg.lc, args.levels)) if pc == "mg" and eq.mg is not None else ""))),
                    "newton_iterations": iters, "krylov_iterations": ksp_its, "ksp": args.ksp + ("/chronopoulos-gear" if args.cgcg and args.ksp == "cg" else ""), "rtol": args.rtol,
                    "preconditioner": ("geometric multigrid V(2,2), Chebyshev/block-Jacobi smoother, Galerkin coarse tangents, "
                                       f"{args.levels + 1} levels") if pc == "mg" else "nodal 3x3 block Jacobi",

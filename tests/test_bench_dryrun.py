@@ -169,7 +169,7 @@ def test_bench_line_two_emulated_ranks(dry, capsys, monkeypatch):
     assert line["n_gpus"] == 2 and line["scaling"] == "strong" and "cpu_baseline" not in line
     assert line["config"]["cells_per_gpu"] * 2 == line["config"]["n_cells"]
     assert "MG_PROBE_OK" in line["config"]["pc_choice"] and "multigrid" in line["config"]["preconditioner"]
-    assert "finest level distributed" in line["config"]["partition"]
+    assert "partitioned by the cells. ancestors" in line["config"]["partition"].replace("'", ".")
 
 
 def test_single_gpu_multigrid_probe(dry, capsys):
