@@ -72,6 +72,10 @@ def parse():
                          "Morton order (several GPUs: only the finest level is partitioned)")
     ap.add_argument("--min-cells-per-rank", type=int, default=100_000,
                     help="several GPUs, PC mg: levels with fewer cells per rank than this are replicated on every rank")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="PC mg: replay every Krylov iteration from one captured CUDA graph (sic_ksp_t.use_graph)")
+    ap.add_argument("--fused-coarse", type=int, default=1,
+                    help="PC mg: the coarsest level's Chebyshev sweep as one cooperative launch (sic_mg_opts_t.fused_coarse)")
     ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-fallback", action="store_true",
                     help="N = 1: do not retry with the configurations measured earlier when the run fails its own checks")
@@ -401,6 +405,7 @@ def run_b200(args):
     sim.verbose = False
     if pc == "mg":
         eq.solver.getPC().setType("mg")
+        eq.mg_options = dict(eq.mg_options, use_graph=bool(args.graph), fused_coarse=bool(args.fused_coarse))
     apply_solver_settings(eq.solver, args.warm_start, args.mg_lag)
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
@@ -427,7 +432,8 @@ def run_b200(args):
     eng.profile = True
     eng.profile_summary()
     eng.op_ms, eng.op_samples, eng.op_launches = 0.0, 0, 0
-    launches0 = eng.launches
+    launches0, nodes0 = eng.launches, getattr(eng, "graph_kernel_nodes", 0)
+    graphs0 = eq.mg.graph_launches if eq.mg is not None else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
@@ -439,6 +445,8 @@ def run_b200(args):
     clk = clocks.stop()
     note(f"timed steps done: {ms / args.steps:.1f} ms/step")
     launches = eng.launches - launches0
+    graph_launches = (eq.mg.graph_launches if eq.mg is not None else 0) - graphs0
+    graph_nodes = getattr(eng, "graph_kernel_nodes", 0) - nodes0
     # a bench line is only printed for a run that did what it claims: every step converged (no dt-retry), every
     # Krylov solve of the timed steps reached its tolerance, no NaN
     n_solves = sum(r["iterations"] for r in recs)
@@ -540,7 +548,13 @@ def run_b200(args):
                    "pc_choice": pc_why, "warm_start": {0: "zero guess", 1: "previous Newton iterate"}.get(
                        args.warm_start, "extrapolated from the step's Newton iterates (sic_guess_extrapolate)"),
                    "l2": "inputs larger than L2 (C_T alone is %.0f MB)" % (36 * 8 * N / 1e6)},
-        "clocks": clk, "gpu_launches": launches, "roofline": roofline, "constitutive": constitutive,
+        "clocks": clk, "gpu_launches": launches,
+        # gpu_launches = host-side launches of this library's kernels and graphs in the timed region; of these
+        # `graph_launches` are CUDA graphs of one Krylov iteration each, holding `kernels_inside_graphs` kernel nodes
+        "launch_breakdown": {"graph_launches": graph_launches, "kernels_inside_graphs": graph_nodes,
+                             "kernels_executed": launches - graph_launches + graph_nodes,
+                             "host_launches_per_step": launches / args.steps},
+        "roofline": roofline, "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,
     }
     if e2e:

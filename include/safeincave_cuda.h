@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SIC_ABI_VERSION 12
+#define SIC_ABI_VERSION 13
 #define SIC_MAX_ELEMS 8   /* non-elastic elements per material */
 #define SIC_MAX_THERMO 4
 
@@ -253,7 +253,10 @@ typedef struct {
   double rtol;            /* on ||r||_2 / ||r0||_2, r0 = b - K x0 restricted to free dofs */
   double atol;
   int32_t check_every;    /* host looks at the residual every this many iterations */
-  int32_t use_graph;      /* capture check_every iterations into one CUDA graph */
+  int32_t use_graph;      /* sic_mg_solve: replay every Krylov iteration (operator, scalar recurrences, the whole V-cycle,
+                             exchanges) from ONE captured CUDA graph instead of ~110-170 kernel launches; re-captured
+                             whenever a set-up changed the baked-in Chebyshev coefficients.  sic_ksp_solve: the same for
+                             one CG / BiCGStab iteration */
   int32_t guess_nonzero;  /* x holds an initial guess on the free dofs; rtol is then relative to the residual of the
                              ZERO guess (PETSc's default ||r|| < rtol ||b||), so a warm start saves iterations */
   /* results */
@@ -265,6 +268,10 @@ typedef struct {
   int32_t time_operator;
   int32_t op_samples;
   double op_ms;
+  /* host-side launch accounting of the Krylov loop: iterations replayed as one graph launch each, iterations
+   * launched kernel by kernel (all of them without use_graph; with it, the timed iteration of each batch) */
+  int32_t graph_launches;
+  int32_t direct_iterations;
 } sic_ksp_t;
 
 /* Workspace: sic_ksp_workspace_doubles(n_nodes, method) doubles, caller-allocated. */
@@ -316,9 +323,12 @@ typedef struct {
   /* work vectors, [3 n_nodes] each */
   double *x, *b, *r, *d, *t;
   double* pv;              /* [3 n_nodes] or NULL: power-iteration vector kept BETWEEN calls of sic_mg_setup (warm start) */
-  const sic_halo_t* halo;  /* FINEST level only, several GPUs: its cells are partitioned exactly as for sic_ksp_solve; all
-                              coarser levels are replicated on every rank.  The finest level's parent_a/b, rst_* then index
-                              the coarse level globally and `children` holds -1 for cells of other ranks.  NULL: one GPU */
+  const sic_halo_t* halo;  /* several GPUs: this level's cells are partitioned exactly as for sic_ksp_solve.  Partitioned
+                              levels are the finest one and any run of levels below it (never level 0), NESTED: a cell
+                              lives on the rank of its ancestor, so the transfer tables between two partitioned levels are
+                              rank-local.  The lowest partitioned level's parent_a/b, rst_* index the (replicated) level
+                              below it globally and its `children` holds -1 for cells of other ranks.  NULL: replicated /
+                              one GPU */
 } sic_mg_level_t;
 
 typedef struct {
@@ -329,6 +339,9 @@ typedef struct {
   double safety;           /* lambda_max is the power-iteration estimate times this (1.15) */
   int32_t power_its;       /* power iterations per level in sic_mg_setup (>= 2, default 16); 0: keep lambda_max as it is */
   int32_t power_its_warm;  /* passes when restarting from pv of the previous setup (4); 0: always start cold */
+  int32_t fused_coarse;    /* != 0: the coarsest level's Chebyshev sweep runs as ONE cooperative launch (k_mg_coarse_fused)
+                              instead of two launches per step, whenever its grid fits the device co-resident */
+  int32_t reserved;
 } sic_mg_opts_t;
 
 /* Once per tangent: restrict C_T down the hierarchy (mean of the 8 children), build the block-Jacobi blocks of
@@ -340,10 +353,11 @@ int sic_mg_setup(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts
 int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, sic_ksp_t* ksp,
                  const double* b_ext, double* x, double* work, void* stream);
 
-/* Opt-in (environment SIC_MG_FUSED_COARSE=1, one GPU): the coarsest level's Chebyshev sweep runs as ONE cooperative launch
- * (k_mg_coarse_fused) instead of two launches per step.  How many such launches this process has made (0: the switch is
- * off or the cooperative launch was refused and the launch-per-step sweep is used). */
+/* How many cooperative coarsest-level launches (opts->fused_coarse) this process has made (0: switched off, or the
+ * cooperative launch was refused and the launch-per-step sweep is used), and how many times an MG-CG iteration has been
+ * captured into a CUDA graph (ksp->use_graph). */
 long long sic_mg_fused_coarse_launches(void);
+long long sic_mg_graph_captures(void);
 
 /* z = V-cycle(r) alone (tests, and users who bring their own Krylov method): reads levels[top].b, writes .x */
 int sic_mg_vcycle(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
 
-SIC_ABI_VERSION = 12
+SIC_ABI_VERSION = 13
 SIC_MAX_ELEMS = 8
 SIC_MAX_THERMO = 4
 SIC_MAX_PEERS = 16
@@ -35,6 +35,7 @@ EXPORTS = (
     "sic_ksp_solve", "sic_guess_workspace_doubles", "sic_guess_extrapolate", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
     "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle", "sic_mg_fused_coarse_launches",
+    "sic_mg_graph_captures",
     "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean", "sic_node_volumes", "sic_pq_fields",
 )
 
@@ -63,7 +64,8 @@ class SicKsp(ctypes.Structure):
                 ("check_every", c_int32), ("use_graph", c_int32), ("guess_nonzero", c_int32),
                 ("iterations", c_int32), ("reason", c_int32),
                 ("rnorm", c_double), ("rnorm0", c_double),
-                ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double)]
+                ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double),
+                ("graph_launches", c_int32), ("direct_iterations", c_int32)]
 
 
 class SicMgLevel(ctypes.Structure):
@@ -76,7 +78,8 @@ class SicMgLevel(ctypes.Structure):
 
 class SicMgOpts(ctypes.Structure):
     _fields_ = [("nu", c_int32), ("coarse_its", c_int32), ("smooth_lo", c_double), ("coarse_lo", c_double),
-                ("safety", c_double), ("power_its", c_int32), ("power_its_warm", c_int32)]
+                ("safety", c_double), ("power_its", c_int32), ("power_its_warm", c_int32), ("fused_coarse", c_int32),
+                ("reserved", c_int32)]
 
 
 SIC_MG_MAX_LEVELS = 8
@@ -129,6 +132,7 @@ def declare(lib, single_gpu_only=False):
     lib.sic_mg_workspace_doubles.argtypes = [c_int, c_int]
     lib.sic_mg_workspace_doubles.restype = c_int64
     lib.sic_mg_fused_coarse_launches.restype = c_int64
+    lib.sic_mg_graph_captures.restype = c_int64
     lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]

@@ -154,9 +154,12 @@ struct P2P {
   unsigned* counters;                     // [n_ranks] blocks-done counters (device)
   unsigned long long* gbar;               // device: halo blocks that have finished READING vec, over all exchanges
   int* error;                             // device flag: a wait timed out
-  unsigned long long epoch;               // nodal (halo) exchanges issued so far (identical on every rank)
-  unsigned long long epoch_s;             // scalar exchanges issued so far; own counter so that two consecutive
-                                          // scalar exchanges always alternate the mailbox parity
+  unsigned long long* epochs;             // DEVICE counters (so that a launch can be replayed from a CUDA graph):
+                                          // [0] nodal (halo) exchanges done so far (identical on every rank),
+                                          // [1] scalar exchanges done so far (own counter so that two consecutive scalar
+                                          //     exchanges always alternate the mailbox parity),
+                                          // [2] blocks of the running launch that have finished (the last one advances
+                                          //     [0] / [1] for the next launch)
 };
 
 __device__ __forceinline__ double* p2p_slot(double* mailbox, size_t slot_doubles, int src, int parity) {
@@ -168,9 +171,25 @@ __device__ __forceinline__ double* p2p_slot(double* mailbox, size_t slot_doubles
 //   scalar block     : thread r sends this rank's n_scal partial sums to rank r (EVERY rank, neighbour or not),
 //                      waits for rank r's, then the sums are formed in rank order (identical on all ranks).
 // Slot layout per (source rank, parity): [9*cap nodal values | NSCAL scalars | halo flag | scalar flag].
+// every block has read the epochs before it takes its ticket, so the last block of the launch may advance them
+__device__ __forceinline__ void p2p_block_done(const P2P& ctx, int ncomp, int n_scal, unsigned long long epoch,
+                                               unsigned long long epoch_s) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ctx.epochs + 2, 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      ctx.epochs[2] = 0ull;
+      if (ncomp > 0) ctx.epochs[0] = epoch + 1ull;
+      if (n_scal > 0) ctx.epochs[1] = epoch_s + 1ull;
+      __threadfence();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, P2P ctx, double* __restrict__ vec, int ncomp,
-                                                                 double* __restrict__ scal, int n_scal,
-                                                                 unsigned long long epoch, unsigned long long epoch_s) {
+                                                                 double* __restrict__ scal, int n_scal) {
+  const unsigned long long epoch = ((volatile unsigned long long*)ctx.epochs)[0];
+  const unsigned long long epoch_s = ((volatile unsigned long long*)ctx.epochs)[1];
   const int parity = (int)(epoch & 1ull);
   const size_t scal_off = 9 * (size_t)ctx.cap;
   const int n_halo_blocks = (ncomp > 0) ? H.n_peers * SIC_P2P_BPP : 0;
@@ -179,6 +198,7 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
   if ((int)blockIdx.x >= n_halo_blocks) {
     // ---------------- scalar block -----------------------------------------------------------------
     const int r = threadIdx.x;
+    const unsigned long long epoch_h = epoch;
     const int parity = (int)(epoch_s & 1ull);          // shadows the halo parity
     const unsigned long long epoch = epoch_s;          // and the halo epoch
     if (r < n_scal) mine[r] = scal[r];
@@ -203,6 +223,7 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
         acc += (q == ctx.rank) ? mine[r] : __ldcv(p2p_slot(ctx.local, ctx.slot_doubles, q, parity) + scal_off + r);
       scal[r] = acc;
     }
+    p2p_block_done(ctx, ncomp, n_scal, epoch_h, epoch_s);
     return;
   }
   // ---------------- halo block ---------------------------------------------------------------------
@@ -248,11 +269,13 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     ok = good;
   }
   __syncthreads();
-  if (!ok) return;
-  for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
-    const int k = t / ncomp, c = t - k * ncomp;
-    atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, __ldcv(in + t));
+  if (ok) {
+    for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
+      const int k = t / ncomp, c = t - k * ncomp;
+      atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, __ldcv(in + t));
+    }
   }
+  p2p_block_done(ctx, ncomp, n_scal, epoch, epoch_s);
 }
 }  // namespace sic
 
@@ -260,17 +283,17 @@ extern "C" int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, 
   if (!p2p || !handle64) return sic_fail("sic_p2p_create: null");
   if (n_ranks < 2 || n_ranks > SIC_P2P_MAX_RANKS) return sic_fail("sic_p2p_create: 2..16 ranks");
   sic::P2P* c = new sic::P2P();
-  c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1; c->epoch = 0; c->epoch_s = 0;
+  c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1;
   c->slot_doubles = 9 * (size_t)c->cap + SIC_P2P_NSCAL + 2;   // + halo flag + scalar flag
   const size_t bytes = sizeof(double) * c->slot_doubles * 2 * n_ranks;
   if (int rc = sic_check_cuda(cudaMalloc((void**)&c->local, bytes), "cudaMalloc mailbox")) return rc;
   if (int rc = sic_check_cuda(cudaMemset(c->local, 0, bytes), "memset mailbox")) return rc;
-  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->counters, sizeof(unsigned) * SIC_P2P_MAX_RANKS + 2 * sizeof(unsigned long long)),
-                              "cudaMalloc"))
-    return rc;
-  cudaMemset(c->counters, 0, sizeof(unsigned) * SIC_P2P_MAX_RANKS + 2 * sizeof(unsigned long long));
+  const size_t cbytes = sizeof(unsigned) * SIC_P2P_MAX_RANKS + 5 * sizeof(unsigned long long);
+  if (int rc = sic_check_cuda(cudaMalloc((void**)&c->counters, cbytes), "cudaMalloc")) return rc;
+  cudaMemset(c->counters, 0, cbytes);
   c->gbar = (unsigned long long*)(c->counters + SIC_P2P_MAX_RANKS);
   c->error = (int*)(c->gbar + 1);
+  c->epochs = c->gbar + 2;
   cudaIpcMemHandle_t h;
   if (int rc = sic_check_cuda(cudaIpcGetMemHandle(&h, c->local), "cudaIpcGetMemHandle")) return rc;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
@@ -336,11 +359,9 @@ extern "C" int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double*
   if (h->n_ranks > SIC_P2P_THREADS) return sic_fail("sic_exchange: too many ranks");
   const int blocks = (ncomp > 0 ? h->n_peers * SIC_P2P_BPP : 0) + (n_scal > 0 ? 1 : 0);
   // every rank takes this path for every call (nodal data to the neighbours, scalars to everybody), so the
-  // epoch counters of all ranks advance in lock step
-  const unsigned long long epoch = c->epoch, epoch_s = c->epoch_s;
-  if (ncomp > 0) c->epoch++;
-  if (n_scal > 0) c->epoch_s++;
+  // (device-resident) epoch counters of all ranks advance in lock step; a rank without neighbours on this halo plan
+  // launches nothing for a nodal-only exchange and its nodal epoch is then never looked at by anybody
   if (blocks == 0) return 0;
-  sic::k_p2p_exchange<<<blocks, SIC_P2P_THREADS, 0, st>>>(*h, *c, vec, ncomp, scal, n_scal, epoch, epoch_s);
+  sic::k_p2p_exchange<<<blocks, SIC_P2P_THREADS, 0, st>>>(*h, *c, vec, ncomp, scal, n_scal);
   return sic_check_launch("k_p2p_exchange");
 }

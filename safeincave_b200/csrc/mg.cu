@@ -32,6 +32,7 @@
 #include "fem.cuh"
 #ifndef SIC_HOSTEMU
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include <stdlib.h>
 #endif
 
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, d
 }
 
 #ifndef SIC_HOSTEMU
-// ---- coarsest level in ONE launch (opt-in: SIC_MG_FUSED_COARSE=1) -----------------------------------------
+// ---- coarsest level in ONE launch (sic_mg_opts_t.fused_coarse) ---------------------------------------------
 // The coarsest level (the gmsh grid: 14 346 cells = 113 CTAs, < one wave of a B200) runs `coarse_its` Chebyshev steps per
 // V-cycle; as separate launches every step is an operator kernel (~10 us) plus a vector kernel (~6 us), both pure
 // latency: ~0.5 ms per cycle, 10-15 % of a Krylov iteration at 7.35 M cells and the largest part of one on 8 GPUs.
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, d
 // the operator and the vector phase); the phases are the SAME device functions as the kernels above
 // (ebe_tile_scatter, mg_cheb_first_node, mg_cheb_step_node).  Vectors written in one phase and gathered in the next
 // (d, t) are read through the coherent path (XCOH / plain loads): the read-only cache is not covered by grid.sync().
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): off unless SIC_MG_FUSED_COARSE=1.
+// Verified on a B200 against the oracle's V-cycle (tests/test_gpu_mg.py); the host emulation has no cooperative launch
+// and always runs the launch-per-step sweep.
 #define SIC_MG_MAX_COARSE_ITS 64
 struct MgCoarseCoef { double a[SIC_MG_MAX_COARSE_ITS], c[SIC_MG_MAX_COARSE_ITS]; double inv_theta; int its; };
 
@@ -508,14 +510,14 @@ static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, doubl
 static long long g_fused_coarse_launches = 0;
 extern "C" long long sic_mg_fused_coarse_launches(void) { return g_fused_coarse_launches; }
 
-static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, double lo, const int* done, cudaStream_t st) {
+static int g_fused_refused = 0;        // the cooperative launch failed once: launch-per-step sweep from then on
+static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, double lo, const int* done, cudaStream_t st,
+                            int wanted) {
 #ifdef SIC_HOSTEMU
-  (void)L; (void)b; (void)its; (void)lo; (void)done; (void)st;
+  (void)L; (void)b; (void)its; (void)lo; (void)done; (void)st; (void)wanted;
   return false;
 #else
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("SIC_MG_FUSED_COARSE"); enabled = (e && e[0] == '1') ? 1 : 0; }
-  if (!enabled || mg_halo(L) || its < 2 || its > SIC_MG_MAX_COARSE_ITS || L.prob.n_cells <= 0) return false;
+  if (!wanted || g_fused_refused || mg_halo(L) || its < 2 || its > SIC_MG_MAX_COARSE_ITS || L.prob.n_cells <= 0) return false;
   const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
   static int max_blocks = -1;
   if (max_blocks < 0) {
@@ -549,7 +551,7 @@ static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, d
   void* args[] = {&P, &bb, &r, &d, &x, &t, &dinv, &fixed, &cf, &dn};
   if (cudaLaunchCooperativeKernel((const void*)k_mg_coarse_fused, dim3(cb), dim3(SIC_TILE_CELLS), args, 0, st) != cudaSuccess) {
     cudaGetLastError();      // clear; fall back to the launch-per-step sweep for good
-    enabled = 0;
+    g_fused_refused = 1;
     return false;
   }
   g_fused_coarse_launches += 1;
@@ -587,7 +589,7 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
   {
     const sic_mg_level_t& L = lv[0];
     const double* b = (top == 0) ? b_top : L.b;
-    if (!mg_coarse_fused(L, b, o->coarse_its, o->coarse_lo, done, st))
+    if (!mg_coarse_fused(L, b, o->coarse_its, o->coarse_lo, done, st, o->fused_coarse))
       if (int rc = mg_chebyshev(L, b, o->coarse_its, o->coarse_lo, 1, done, st)) return rc;
   }
   for (int l = 1; l <= top; ++l) {
@@ -688,6 +690,86 @@ extern "C" int sic_mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts
   return mg_vcycle(lv, n_levels, o, lv[n_levels - 1].b, &W.S->done, st, nullptr);
 }
 
+static long long g_mg_graph_captures = 0;      // stays 0 in the host emulation (no graphs there)
+extern "C" long long sic_mg_graph_captures(void) { return g_mg_graph_captures; }
+
+#ifndef SIC_HOSTEMU
+// ---- CUDA graph of one MG-CG iteration -----------------------------------------------------------------------
+// One iteration is ~110 launches on a 5-level hierarchy (170 with the launch-per-step coarsest sweep), most of them
+// 5-10 us kernels of the coarse levels: launched one by one they are bound by the launch rate of the host thread.
+// The iteration is captured ONCE per (hierarchy, tangent set-up, solve arguments) and replayed with one
+// cudaGraphLaunch per iteration.  Everything that changes between replays lives in device memory (CG scalars, the
+// `done` flag, the epochs of the P2P exchange); what is baked into the nodes -- pointers, sizes, the Chebyshev
+// coefficients that follow lambda_max -- is the cache key, so a new set-up re-captures (about a millisecond).
+struct MgGraphKey {
+  sic_mg_level_t lv[SIC_MG_MAX_LEVELS];
+  sic_mg_opts_t o;
+  const double* b_ext; double* x; double* work;
+  double rtol, atol;
+  double lam[SIC_MG_MAX_LEVELS];      // the levels' lambda_max (kept out of lv: a new set-up changes only these)
+  int n_levels, guess, fused_refused;
+  cudaStream_t st;
+};
+struct MgGraphEntry { MgGraphKey key; cudaGraphExec_t exec; unsigned long long used; };
+#define SIC_MG_GRAPH_SLOTS 4
+static MgGraphEntry g_mg_graphs[SIC_MG_GRAPH_SLOTS];
+static unsigned long long g_mg_graph_clock = 0;
+static int g_mg_graph_broken = 0;      // a capture failed once: launch kernel by kernel from then on
+
+template <class Body>
+static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, const double* b_ext,
+                                          double* x, double* work, double rtol, double atol, int guess, cudaStream_t st,
+                                          Body& body) {
+  if (g_mg_graph_broken) return nullptr;
+  MgGraphKey key;
+  memset(&key, 0, sizeof(key));
+  memcpy(key.lv, lv, sizeof(sic_mg_level_t) * n_levels);
+  memcpy(&key.o, o, sizeof(sic_mg_opts_t));
+  key.b_ext = b_ext; key.x = x; key.work = work; key.rtol = rtol; key.atol = atol;
+  key.n_levels = n_levels; key.guess = guess; key.fused_refused = g_fused_refused; key.st = st;
+  for (int l = 0; l < n_levels; ++l) { key.lam[l] = lv[l].lambda_max; key.lv[l].lambda_max = 0.0; }
+  MgGraphEntry* slot = nullptr;
+  MgGraphEntry* lru = &g_mg_graphs[0];
+  for (int i = 0; i < SIC_MG_GRAPH_SLOTS; ++i) {
+    MgGraphEntry& e = g_mg_graphs[i];
+    if (e.exec && memcmp(&e.key, &key, sizeof(key)) == 0) { e.used = ++g_mg_graph_clock; return e.exec; }
+    if (e.exec && memcmp(e.key.lv, key.lv, sizeof(key.lv)) == 0 && e.key.x == key.x && e.key.work == key.work)
+      slot = &e;                             // same hierarchy and vectors: its graph has the same topology
+    if (e.used < lru->used) lru = &e;        // least recently used (empty slots have used == 0)
+  }
+  if (!slot) slot = lru;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); g_mg_graph_broken = 1; return nullptr; }
+  const int rc = body(nullptr);
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g_mg_graph_broken = 1;
+    fprintf(stderr, "safeincave_cuda: CUDA graph capture of the MG-CG iteration failed (%s); launching kernel by kernel\n",
+            ce != cudaSuccess ? cudaGetErrorString(ce) : sic_last_error());
+    return nullptr;
+  }
+  cudaGraphExec_t exec = nullptr;
+  // same hierarchy as the slot's previous graph (a new tangent set-up changed only kernel arguments): update in place
+  if (slot->exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(slot->exec, graph, &info) == cudaSuccess) exec = slot->exec;
+    else { cudaGetLastError(); cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+  }
+  if (!exec && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    g_mg_graph_broken = 1;
+    return nullptr;
+  }
+  cudaGraphDestroy(graph);
+  slot->key = key; slot->exec = exec; slot->used = ++g_mg_graph_clock;
+  g_mg_graph_captures += 1;
+  return exec;
+}
+#endif
+
 extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, sic_ksp_t* ksp,
                             const double* b_ext, double* x, double* work, void* stream) {
   if (int rc = mg_check_levels(lv, n_levels, o)) return rc;
@@ -751,28 +833,57 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (int rc = reduce(MG_OP_INIT_RZ, nullptr, 1)) return rc;
   k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);   // p = z ; q = 0
 
+  // one CG iteration: q = K p with p.Kp summed per cell (cells are partitioned: no owner weights needed); several
+  // GPUs: the halo sum of q and the sum of p.Kp over the ranks travel in ONE exchange.  Every argument is either a
+  // device pointer or a value fixed until the next setup, so the iteration can be replayed from a CUDA graph.
+  auto iteration = [&](cudaEvent_t* time_ev) -> int {
+    if (cb > 0) k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
+    k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
+    if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
+    k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
+    if (int rc = reduce(MG_OP_RR, nullptr, 1)) return rc;
+    if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, time_ev)) return rc;
+    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
+    if (int rc = reduce(MG_OP_RZ, nullptr, 1)) return rc;
+    k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
+    return 0;
+  };
+  ksp->graph_launches = 0;
+  ksp->direct_iterations = 0;
+#ifndef SIC_HOSTEMU
+  cudaGraphExec_t gexec = nullptr;
+  if (ksp->use_graph) gexec = mg_iteration_graph(lv, n_levels, o, b_ext, x, work, rtol, atol, guess, st, iteration);
+#endif
+
   int launched = 0;
+  bool timed_batch = false;
   while (true) {
     cudaMemcpyAsync(g_mg_host, S, sizeof(MgScal), cudaMemcpyDeviceToHost, st);
     if (int rc = sic_check_cuda(cudaStreamSynchronize(st), "mg sync")) return rc;
-    if (ev && launched > 0) {
+    if (timed_batch) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { ksp->op_ms += ms; ksp->op_samples += 1; }
+      timed_batch = false;
     }
     if (g_mg_host->done || launched >= ksp->max_it) break;
     const int batch = ksp->max_it - launched < check ? ksp->max_it - launched : check;
     for (int k = 0; k < batch; ++k) {
-      // q = K p with p.Kp summed per cell (cells are partitioned: no owner weights needed); several GPUs: the halo
-      // sum of q and the sum of p.Kp over the ranks travel in ONE exchange
-      if (cb > 0) k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
-      k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
-      if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
-      k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
-      if (int rc = reduce(MG_OP_RR, nullptr, 1)) return rc;
-      if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, (k == 0) ? ev : nullptr)) return rc;
-      k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
-      if (int rc = reduce(MG_OP_RZ, nullptr, 1)) return rc;
-      k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
+#ifndef SIC_HOSTEMU
+      // the timed iteration is launched kernel by kernel (its events bracket one operator launch)
+      const bool timed = ev && k == 0 && (launched == 0 || !gexec);
+      if (timed) timed_batch = true;
+      if (gexec && !timed) {
+        if (int rc = sic_check_cuda(cudaGraphLaunch(gexec, st), "cudaGraphLaunch (mg-cg iteration)")) return rc;
+        ksp->graph_launches += 1;
+        continue;
+      }
+#endif
+#ifdef SIC_HOSTEMU
+      const bool timed = ev && k == 0;
+      if (timed) timed_batch = true;
+#endif
+      if (int rc = iteration(timed ? ev : nullptr)) return rc;
+      ksp->direct_iterations += 1;
     }
     launched += batch;
     if (int rc = sic_check_launch("mg-cg batch")) return rc;

@@ -169,13 +169,16 @@ class Multigrid:
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01,
                  safety=1.15, power_its=32, power_its_warm=4, part=None, coarse_fixed=None, dist=None,
-                 dist_min_cells_per_rank=200_000):
+                 dist_min_cells_per_rank=200_000, fused_coarse=True, use_graph=True):
         """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one).
         With a NESTED hierarchy (refine_hierarchy(..., nested=True)) and ``dist`` (the DistContext, for the levels'
         own exchange mailboxes) every level down to ``distributed_from(...)`` is partitioned by the rank's ancestors'
         cells; the levels below are replicated on every rank (csrc/mg.cu).  Otherwise only the finest level is.
         coarse_fixed: callable(level index, TetMesh) -> uint8 (3 M,) Dirichlet mask of a coarse level (global
-        numbering); needed when the finest level is partitioned (a rank cannot inject a mask it holds a part of)."""
+        numbering); needed when the finest level is partitioned (a rank cannot inject a mask it holds a part of).
+        fused_coarse: the coarsest level's sweep as one cooperative launch; use_graph: replay every Krylov iteration of
+        ``solve`` from one captured CUDA graph (both: csrc/mg.cu; the graph is not used while the operator is being timed
+        launch by launch)."""
         import ctypes
 
         import torch
@@ -228,7 +231,9 @@ class Multigrid:
             self.engines.append(eng)
         self.engines.append(fine_engine)
         self.opts = L.SicMgOpts(int(nu), int(coarse_its), float(smooth_lo), float(coarse_lo), float(safety), int(power_its),
-                                int(power_its_warm))
+                                int(power_its_warm), 1 if fused_coarse else 0, 0)
+        self.use_graph = bool(use_graph)
+        self.graph_launches = 0
         self.levels = (L.SicMgLevel * n)()
         self._keep = []
         zeros = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype, device=dev)
@@ -259,6 +264,7 @@ class Multigrid:
         # kernels per V-cycle (bench.py's gpu_launches): per level 2 nu operator + 2 nu smoother + residual, restriction,
         # prolongation; coarsest level 2 coarse_its - 1
         self.launches_per_cycle = (n - 1) * (4 * nu + 3) + 2 * coarse_its - 1
+        self._coarse_launches = 2 * coarse_its - 1
         self.setups = 0
 
     def _refresh(self, fixed_fine=None, dinv_fine=None):
@@ -322,13 +328,22 @@ class Multigrid:
         self._refresh()
         ksp = L.SicKsp()
         ksp.method, ksp.max_it, ksp.rtol, ksp.atol = 0, int(max_it), float(rtol), float(atol)
-        ksp.check_every, ksp.use_graph = int(check_every), 0
+        ksp.check_every, ksp.use_graph = int(check_every), 1 if self.use_graph else 0
         ksp.guess_nonzero = 1 if guess_nonzero else 0
         ksp.time_operator = 1 if time_operator else 0
+        fused0 = int(self.lib.sic_mg_fused_coarse_launches())
         L.check(self.lib.sic_mg_solve(self.levels, len(self.engines), ct.byref(self.opts), ct.byref(ksp), self._ptr(b_ext),
                                       self._ptr(x), self._ptr(self.work), self.fine._stream()), "sic_mg_solve")
         eng = self.fine
-        eng.launches += 6 + (self.launches_per_cycle + 5) * (int(ksp.iterations) + 1)
+        if int(self.lib.sic_mg_fused_coarse_launches()) > fused0 and self._coarse_launches > 1:
+            self.launches_per_cycle -= self._coarse_launches - 1       # the coarsest sweep is ONE cooperative launch
+            self._coarse_launches = 1
+        # host-side launches: the prologue (incl. the first V-cycle) and the iterations launched kernel by kernel, plus
+        # ONE graph launch per replayed iteration (graph_kernel_nodes: the kernels inside those graphs)
+        per_it = self.launches_per_cycle + 5
+        eng.launches += 6 + per_it * (int(ksp.direct_iterations) + 1) + int(ksp.graph_launches)
+        eng.graph_kernel_nodes = getattr(eng, "graph_kernel_nodes", 0) + per_it * int(ksp.graph_launches)
+        self.graph_launches += int(ksp.graph_launches)
         eng.op_ms += float(ksp.op_ms)
         eng.op_samples += int(ksp.op_samples)
         nu, n = self.opts.nu, len(self.engines)

@@ -64,6 +64,7 @@ def main():
     eq._elastic_tangent_live = False
     if a.what == "step":
         eq.mg.setup(eq.fixed, eq.dinv)
+        eq.mg.use_graph = False                  # kernel by kernel: the profiler sees ordinary launches
         torch.cuda.synchronize()
         rt.cudaProfilerStart()
         res = eq.mg.solve(eq.b_ext, eq.X.reshape(-1), rtol=1e-10, max_it=1, check_every=1, guess_nonzero=True)

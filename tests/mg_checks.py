@@ -40,7 +40,7 @@ def random_tangent(n, seed, nonsym=0.0):
     return CT
 
 
-def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True):
+def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True, mg_kwargs=None):
     """sic_mg_setup (Galerkin C_T, masks, blocks, lambda_max), one V-cycle and the full solve against the
     assembled-matrix oracle and the sparse direct solve."""
     from safeincave_b200 import cases
@@ -54,7 +54,7 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=
     eng.put6(eng.eps_rhs, eps_rhs)
     eq.bc.update_dirichlet(0.0)
     eq.bc.update_neumann(0.0)
-    mg = Multigrid(eng, h)
+    mg = Multigrid(eng, h, **(mg_kwargs or {}))
     mg.setup(eq.fixed, eq.dinv)
     fixed = eq.fixed.cpu().numpy().astype(bool)
     om = OracleMG(h.meshes, h.transfers, CT, fixed)

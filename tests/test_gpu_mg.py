@@ -44,20 +44,41 @@ def test_lagged_multigrid_setup(sf):
     C.check_lagged_setup(sf)
 
 
-@pytest.mark.xfail(reason="opt-in path (SIC_MG_FUSED_COARSE=1) whose first run on a GPU is this test", strict=False)
-def test_fused_coarse_level_sweep_matches_the_oracle():
-    """k_mg_coarse_fused: the coarsest level's Chebyshev sweep as ONE cooperative launch.  Run in a child process (the
-    switch is read once per process; a hang would be cut off by the timeout without taking the suite along): the
-    V-cycle must still agree vector for vector with the oracle's, and the solves with the direct solve."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import safeincave_b200 as sf; from tests import mg_checks as C; "
-            "its = C.check_setup_vcycle_solve(sf, 'cube_coarse', levels=2); "
-            "its2 = C.check_setup_vcycle_solve(sf, 'cavern_regular', levels=1, nonsym=0.01, full=False); "
-            "from safeincave_b200 import _lib; n = _lib.load().sic_mg_fused_coarse_launches(); "
-            "assert n > 0, 'the cooperative launch was refused: nothing was tested'; print('FUSED_OK', its, its2, n)")
-    env = dict(os.environ, SIC_MG_FUSED_COARSE="1")
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+def test_fused_coarse_level_sweep_matches_the_oracle(sf):
+    """k_mg_coarse_fused (the default): the coarsest level's Chebyshev sweep as ONE cooperative launch.  The V-cycle must
+    agree vector for vector with the oracle's, the solves with the direct solve -- and the cooperative launch must really
+    have been used (a refused launch falls back to the launch-per-step sweep silently)."""
+    from safeincave_b200 import _lib
+    lib = _lib.load()
+    n0 = lib.sic_mg_fused_coarse_launches()
+    C.check_setup_vcycle_solve(sf, "cube_coarse", levels=2)
+    C.check_setup_vcycle_solve(sf, "cavern_regular", levels=1, nonsym=0.01, full=False)
+    assert lib.sic_mg_fused_coarse_launches() > n0, "the cooperative launch was refused: nothing was tested"
+
+
+def test_launch_per_step_coarse_sweep_still_matches(sf):
+    """fused_coarse=False: the 2 * coarse_its - 1 launches the fused kernel replaces (the path of the host emulation)."""
+    C.check_setup_vcycle_solve(sf, "cube_coarse", levels=2, mg_kwargs=dict(fused_coarse=False))
+
+
+def test_graph_replayed_iterations_equal_launched_ones(sf):
+    """sic_ksp_t.use_graph: the Krylov iterations of a solve replayed from one captured CUDA graph give the same
+    iteration counts and fields as the same kernels launched one by one, over two time steps with several set-ups
+    (each re-captures: the Chebyshev coefficients are baked into the nodes)."""
+    from safeincave_b200 import _lib, cases
+    lib = _lib.load()
+    out = {}
+    for graph in (False, True):
+        h, grid, case, eq, sim = C.make(sf, "cavern_regular", 1, cases.cavern_case, n_steps=2, ksp_type="cg", rtol=1e-10)
+        eq.mg_options = dict(use_graph=graph)
+        eq.solver.initial_guess_nonzero = True
+        sim.verbose = False
+        c0 = lib.sic_mg_graph_captures()
+        hist = sim.run()
+        out[graph] = (eq.X.clone(), [k[0] for k in eq.ksp_log], [r["iterations"] for r in hist], eq.mg.graph_launches,
+                      lib.sic_mg_graph_captures() - c0, eq.mg.setups)
+    (x0, its0, newton0, g0, cap0, _), (x1, its1, newton1, g1, cap1, setups) = out[False], out[True]
+    assert g0 == 0 and cap0 == 0
+    assert g1 > 0 and 1 <= cap1 <= setups + 1, (g1, cap1, setups)
+    assert newton0 == newton1 and all(abs(a - b) <= 1 for a, b in zip(its0, its1)), (its0, its1)
+    assert float((x0 - x1).abs().max() / x0.abs().max()) < 1e-9
