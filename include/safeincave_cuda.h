@@ -379,6 +379,8 @@ typedef struct {
   const double* tri_h;     /* [n_tri] Robin coefficient h of the facet's BC (0: none) */
   const double* tri_q;     /* [n_tri] Neumann flux + h * T_inf of the facet's BCs at the current time */
   const uint8_t* fixed;    /* [n_nodes] Dirichlet mask */
+  const sic_halo_t* halo;  /* several GPUs: cells and boundary triangles partitioned as for the momentum equation (the
+                              reference's heat solve is MPI-parallel, HeatEquation.py:344-364); NULL: one GPU */
 } sic_heat_t;
 
 int64_t sic_heat_workspace_doubles(int n_nodes);

@@ -61,8 +61,13 @@ class BcHandler:
             eq = self.eq
             tm, dev = eq.grid.tetmesh, eq.engine.device
             sel = lambda bc: to.as_tensor(np.nonzero(tm.tri_tags == eq.grid.get_boundary_tag(bc.boundary_name))[0], device=dev)
-            nodes = lambda bc: to.as_tensor(np.unique(tm.tris[tm.tri_tags == eq.grid.get_boundary_tag(bc.boundary_name)]),
-                                            dtype=to.int64, device=dev)
+            def nodes(bc):
+                tag = eq.grid.get_boundary_tag(bc.boundary_name)
+                if getattr(tm, "boundary_nodes", None) is not None:   # partitioned mesh: node sets from the GLOBAL mesh
+                    n = np.asarray(tm.boundary_nodes.get(int(tag), np.zeros(0, dtype=np.int64)))
+                else:
+                    n = np.unique(tm.tris[tm.tri_tags == tag])
+                return to.as_tensor(n, dtype=to.int64, device=dev)
             self._cache = ([nodes(bc) for bc in self.dirichlet_boundaries], [sel(bc) for bc in self.neumann_boundaries],
                            [sel(bc) for bc in self.robin_boundaries])
         return self._cache

@@ -27,11 +27,17 @@ class HeatDiffusion:
     def __init__(self, grid, device="cuda"):
         self.grid = grid
         tm = grid.tetmesh
-        if getattr(grid, "partition", None) is not None and grid.partition.n_ranks > 1:
-            raise NotImplementedError("HeatDiffusion runs on one GPU in this version (the heat solve is ~1 % of a "
-                                      "thermo-mechanical step); build it on the unpartitioned grid")
         self.engine = self.engine_cls(tm.coords, tm.cells, device=device, geometry_only=True)
         eng = self.engine
+        # several GPUs (the reference's heat solve is MPI-parallel, HeatEquation.py:344-364): the grid of
+        # distributed.partition_grid carries its cell partition and the process group; the heat equation gets its own
+        # halo plan / exchange mailbox on the same partition (csrc/heat.cu)
+        part = getattr(grid, "partition", None)
+        self.dist = getattr(grid, "dist", None)
+        if part is not None and part.n_ranks > 1:
+            if self.dist is None:
+                raise ValueError("a partitioned grid needs its DistContext (grid.dist, set by distributed.partition_grid)")
+            eng.set_partition(part, self.dist.comm, self.dist.make_p2p(part))
         dev = eng.device
         self.n_elems, self.n_nodes = eng.N, eng.M
         z = lambda n, dt=to.float64: to.zeros(max(n, 1), dtype=dt, device=dev)
@@ -96,6 +102,7 @@ class HeatDiffusion:
         H.rho_cp, H.k = _ptr(self.rho_cp), _ptr(self.k_dev)
         H.tri, H.tri_area, H.tri_h, H.tri_q = _ptr(self.tri), _ptr(self.tri_area), _ptr(self.tri_h), _ptr(self.tri_q)
         H.fixed = _ptr(self.fixed)
+        H.halo = ctypes.cast(ctypes.pointer(eng.halo), ctypes.c_void_p) if eng.halo is not None else None
         return H
 
     def get_T_elems(self):
@@ -122,7 +129,7 @@ class HeatDiffusion:
         H = self._problem()
         L.check(eng.lib.sic_heat_step(ctypes.byref(H), float(dt), _ptr(self.T_old_dev), _ptr(T), ctypes.byref(res),
                                       _ptr(self.work), eng._stream()), "sic_heat_step")
-        eng.launches += 12 + 5 * int(res.iterations)
+        eng.launches += (12 + 5 * int(res.iterations)) if eng.halo is None else (22 + 10 * int(res.iterations))
         ksp.record(res)
         self.ksp_log.append((int(res.iterations), int(res.reason), float(res.rnorm)))
         if res.reason < 0:

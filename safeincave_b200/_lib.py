@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("SIC_LIB_PATH", os.path.join(HERE, "libsafeincave_cuda.so"))   # override: A/B experiments only
+LIB_PATH = os.path.join(HERE, "libsafeincave_cuda.so")       # the one library of the product: no override, no stand-in
 
 SIC_ABI_VERSION = 13
 SIC_MAX_ELEMS = 8
@@ -88,7 +88,8 @@ SIC_MG_MAX_LEVELS = 8
 class SicHeat(ctypes.Structure):
     _fields_ = [("n_cells", c_int32), ("cell_stride", c_int32), ("n_nodes", c_int32), ("n_tri", c_int32),
                 ("conn", c_void_p), ("grad", c_void_p), ("vol", c_void_p), ("rho_cp", c_void_p), ("k", c_void_p),
-                ("tri", c_void_p), ("tri_area", c_void_p), ("tri_h", c_void_p), ("tri_q", c_void_p), ("fixed", c_void_p)]
+                ("tri", c_void_p), ("tri_area", c_void_p), ("tri_h", c_void_p), ("tri_q", c_void_p), ("fixed", c_void_p),
+                ("halo", c_void_p)]
 
 
 class SicHalo(ctypes.Structure):

@@ -339,9 +339,11 @@ extern "C" int sic_p2p_destroy(void* p2p) {
 
 extern "C" int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double* scal, int n_scal, void* stream) {
   if (!h || h->n_ranks <= 1) return 0;
-  static int dbg_skip = -1;   // SIC_DBG_NOXCHG=1: timing experiment only (results are wrong)
+#ifdef SIC_DEBUG_SWITCHES      // never defined by build.py: timing experiment only (results are wrong)
+  static int dbg_skip = -1;
   if (dbg_skip < 0) { const char* e = getenv("SIC_DBG_NOXCHG"); dbg_skip = (e && e[0] == '1') ? 1 : 0; }
   if (dbg_skip) return 0;
+#endif
   if (n_scal < 0 || n_scal > SIC_P2P_NSCAL) return sic_fail("sic_exchange: n_scal must be 0..8");
   if (!h->p2p) {   // NCCL path
     if (ncomp > 0) { if (int rc = sic_halo_sum(h, vec, ncomp, stream)) return rc; }

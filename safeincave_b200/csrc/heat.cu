@@ -9,6 +9,12 @@
 // block, a `done` flag turns the remaining launches of a batch into no-ops).  The system is mass-dominated at
 // the reference's time steps (rho cp h^2 / (k dt) >> 1), so a handful of iterations suffice; this path is
 // ~1 % of a thermo-mechanical step and is kept simple (one thread per cell, one FP64 atomic per cell node).
+//
+// Several GPUs (sic_heat_t.halo, the reference's heat solve is MPI-parallel: HeatEquation.py:344-364 ghostUpdate /
+// scatter_forward): cells and boundary triangles are partitioned exactly as for the momentum equation, nodal vectors
+// are kept consistent on the interface nodes, every cell / facet sum (operator result, right-hand side, diagonal) is
+// completed by the halo sum of sic_exchange (one component), dot products use the owner weights and their partial
+// sums travel through the same exchange kernel; the scalar recurrence then runs in a one-thread kernel.
 #include <math.h>
 
 #include "fem.cuh"
@@ -17,6 +23,7 @@ namespace sic {
 
 struct HeatScal {
   double rz, pq, rr, rr0, rr_ref, alpha, beta, tol2;
+  double sum[2];        // several GPUs: this rank's partial sums of the running reduction
   int done, iters, nanflag, reason;
 };
 static_assert(sizeof(HeatScal) <= 64 * sizeof(double), "HeatScal must fit the reserved workspace header");
@@ -26,8 +33,13 @@ static_assert(sizeof(HeatScal) <= 64 * sizeof(double), "HeatScal must fit the re
 enum { HT_REF = 0, HT_INIT, HT_PQ, HT_UPDATE };
 
 struct HeatFin {
-  HeatScal* S; int op; double rtol, atol;
+  HeatScal* S; int op; double rtol, atol; int multi;
+  // one GPU: run the scalar recurrence at once; several: park the partial sums, k_heat_scal runs it after the exchange
   __device__ __forceinline__ void run(const double* tot) const {
+    if (multi) { S->sum[0] = tot[0]; S->sum[1] = tot[1]; return; }
+    step(tot);
+  }
+  __device__ __forceinline__ void step(const double* tot) const {
     switch (op) {
       case HT_REF: S->rr_ref = tot[0]; break;
       case HT_INIT: {   // tot = {r.z, r.r}
@@ -48,6 +60,11 @@ struct HeatFin {
     }
   }
 };
+
+__global__ void k_heat_scal(HeatFin fin, int skip_if_done) {
+  if (skip_if_done && fin.S->done) return;
+  fin.step(fin.S->sum);
+}
 
 // y += cm * M x + ck * K x over the cells (one thread per cell)
 __global__ void __launch_bounds__(SIC_EBE_THREADS) k_heat_cells(sic_heat_t H, double cm, double ck,
@@ -136,17 +153,19 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_diag_tris(sic_heat_t H
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_init(int n, const double* __restrict__ b, const double* __restrict__ t,
                                                               const double* __restrict__ diag, const uint8_t* __restrict__ fixed,
                                                               double* __restrict__ r, double* __restrict__ p,
-                                                              double* __restrict__ q, HeatFin fin, int only_norm,
+                                                              double* __restrict__ q, const double* __restrict__ w,
+                                                              HeatFin fin, int only_norm,
                                                               double* __restrict__ partials, unsigned* counter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
   if (i < n) {
+    const double wn = w ? w[i] : 1.0;       // several GPUs: every node is counted by its owner only
     const double rn = fixed[i] ? 0.0 : b[i] - t[i];
-    if (only_norm) { v[0] = rn * rn; }
+    if (only_norm) { v[0] = wn * rn * rn; }
     else {
       const double zn = fixed[i] ? 0.0 : rn / diag[i];
       r[i] = rn; p[i] = zn; q[i] = 0.0;
-      v[0] = rn * zn; v[1] = rn * rn;
+      v[0] = wn * rn * zn; v[1] = wn * rn * rn;
     }
   }
   grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot); });
@@ -154,12 +173,12 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_init(int n, const doub
 
 // p.q over the free nodes
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_pq(int n, const double* __restrict__ p, const double* __restrict__ q,
-                                                            const uint8_t* __restrict__ fixed, HeatFin fin,
-                                                            double* __restrict__ partials, unsigned* counter) {
+                                                            const uint8_t* __restrict__ fixed, const double* __restrict__ w,
+                                                            HeatFin fin, double* __restrict__ partials, unsigned* counter) {
   if (fin.S->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
-  if (i < n && !fixed[i]) v[0] = p[i] * q[i];
+  if (i < n && !fixed[i]) v[0] = (w ? w[i] : 1.0) * p[i] * q[i];
   grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot); });
 }
 
@@ -167,13 +186,14 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_pq(int n, const double
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_update(int n, double* __restrict__ x, double* __restrict__ r,
                                                                 double* __restrict__ z, const double* __restrict__ p,
                                                                 const double* __restrict__ q, const double* __restrict__ diag,
-                                                                const uint8_t* __restrict__ fixed, HeatFin fin,
-                                                                double* __restrict__ partials, unsigned* counter) {
+                                                                const uint8_t* __restrict__ fixed, const double* __restrict__ w,
+                                                                HeatFin fin, double* __restrict__ partials, unsigned* counter) {
   if (fin.S->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double alpha = fin.S->alpha;
   double v[2] = {0.0, 0.0};
   if (i < n) {
+    const double wn = w ? w[i] : 1.0;
     double rn = 0.0, zn = 0.0;
     if (!fixed[i]) {
       x[i] += alpha * p[i];
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_heat_update(int n, double* 
       zn = rn / diag[i];
     }
     r[i] = rn; z[i] = zn;
-    v[0] = rn * zn; v[1] = rn * rn;
+    v[0] = wn * rn * zn; v[1] = wn * rn * rn;
   }
   grid_reduce<2, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot); });
 }
@@ -233,13 +253,17 @@ static int heat_check(const sic_heat_t* h) {
   return 0;
 }
 
-// y = A x = (M/dt + K + R) x   (y zeroed here)
+static inline const sic_halo_t* heat_halo(const sic_heat_t* h) { return (h->halo && h->halo->n_ranks > 1) ? h->halo : nullptr; }
+
+// y = A x = (M/dt + K + R) x   (y zeroed here; several GPUs: completed on the interface nodes by the halo sum)
 static int heat_apply(const sic_heat_t* h, double inv_dt, const double* x, double* y, const int* done, cudaStream_t st) {
   if (int rc = sic_check_cuda(cudaMemsetAsync(y, 0, sizeof(double) * h->n_nodes, st), "heat memset")) return rc;
   if (h->n_cells > 0)
     k_heat_cells<<<ht_blocks(h->n_cells, SIC_EBE_THREADS), SIC_EBE_THREADS, 0, st>>>(*h, inv_dt, 1.0, x, y, done);
   if (h->n_tri > 0) k_heat_tris<<<ht_blocks(h->n_tri, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(*h, 1, 0, x, y, done);
-  return sic_check_launch("heat apply");
+  if (int rc = sic_check_launch("heat apply")) return rc;
+  if (const sic_halo_t* halo = heat_halo(h)) return sic_exchange(halo, y, 1, nullptr, 0, (void*)st);
+  return 0;
 }
 
 extern "C" int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old, double* T, sic_ksp_t* ksp, double* work,
@@ -264,7 +288,18 @@ extern "C" int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old
   const int nb = ht_blocks(n, SIC_VEC_THREADS), cb = ht_blocks(h->n_cells, SIC_EBE_THREADS),
             tb = ht_blocks(h->n_tri, SIC_VEC_THREADS);
   const double rtol = ksp->rtol, atol = ksp->atol;
-  auto fin = [&](int op) { return HeatFin{S, op, rtol, atol}; };
+  const sic_halo_t* halo = heat_halo(h);
+  const int multi = halo ? 1 : 0;
+  const double* ow = halo ? halo->owner_w : nullptr;
+  if (halo && !ow) return sic_fail("sic_heat_step: halo without owner weights");
+  auto fin = [&](int op) { return HeatFin{S, op, rtol, atol, multi}; };
+  // several GPUs: add the partial sums of the last reducing kernel over the ranks, then run the scalar recurrence
+  auto reduce = [&](int op, int skip_if_done) -> int {
+    if (!multi) return 0;
+    if (int rc = sic_exchange(halo, nullptr, 0, S->sum, 2, stream)) return rc;
+    k_heat_scal<<<1, 1, 0, st>>>(fin(op), skip_if_done);
+    return sic_check_launch("k_heat_scal");
+  };
   // b = (M/dt) T_old + q ; diag of A
   if (h->n_cells > 0) {
     k_heat_cells<<<cb, SIC_EBE_THREADS, 0, st>>>(*h, inv_dt, 0.0, T_old, b, nullptr);
@@ -275,13 +310,19 @@ extern "C" int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old
     k_heat_diag_tris<<<tb, SIC_VEC_THREADS, 0, st>>>(*h, diag);
   }
   if (int rc = sic_check_launch("heat rhs")) return rc;
+  if (multi) {
+    if (int rc = sic_exchange(halo, b, 1, nullptr, 0, stream)) return rc;
+    if (int rc = sic_exchange(halo, diag, 1, nullptr, 0, stream)) return rc;
+  }
   // reference norm of rtol: the residual of the zero guess (prescribed values only), PETSc's ||b|| after lifting
   k_heat_zero_free<<<nb, SIC_VEC_THREADS, 0, st>>>(n, tmp, T, h->fixed);
   if (int rc = heat_apply(h, inv_dt, tmp, q, nullptr, st)) return rc;
-  k_heat_init<<<nb, SIC_VEC_THREADS, 0, st>>>(n, b, q, diag, h->fixed, r, p, z, fin(HT_REF), 1, partials, counter);
+  k_heat_init<<<nb, SIC_VEC_THREADS, 0, st>>>(n, b, q, diag, h->fixed, r, p, z, ow, fin(HT_REF), 1, partials, counter);
+  if (int rc = reduce(HT_REF, 0)) return rc;
   // r0 = b - A T(guess) on the free nodes
   if (int rc = heat_apply(h, inv_dt, T, tmp, nullptr, st)) return rc;
-  k_heat_init<<<nb, SIC_VEC_THREADS, 0, st>>>(n, b, tmp, diag, h->fixed, r, p, q, fin(HT_INIT), 0, partials, counter);
+  k_heat_init<<<nb, SIC_VEC_THREADS, 0, st>>>(n, b, tmp, diag, h->fixed, r, p, q, ow, fin(HT_INIT), 0, partials, counter);
+  if (int rc = reduce(HT_INIT, 0)) return rc;
   const int check = ksp->check_every > 0 ? ksp->check_every : 10;
   int launched = 0;
   while (true) {
@@ -293,13 +334,17 @@ extern "C" int sic_heat_step(const sic_heat_t* h, double dt, const double* T_old
       // q = A p (q is zero on entry: k_heat_init / k_heat_p leave it so)
       if (h->n_cells > 0) k_heat_cells<<<cb, SIC_EBE_THREADS, 0, st>>>(*h, inv_dt, 1.0, p, q, &S->done);
       if (h->n_tri > 0) k_heat_tris<<<tb, SIC_VEC_THREADS, 0, st>>>(*h, 1, 0, p, q, &S->done);
-      k_heat_pq<<<nb, SIC_VEC_THREADS, 0, st>>>(n, p, q, h->fixed, fin(HT_PQ), partials, counter);
-      k_heat_update<<<nb, SIC_VEC_THREADS, 0, st>>>(n, T, r, z, p, q, diag, h->fixed, fin(HT_UPDATE), partials, counter);
+      if (multi) if (int rc = sic_exchange(halo, q, 1, nullptr, 0, stream)) return rc;
+      k_heat_pq<<<nb, SIC_VEC_THREADS, 0, st>>>(n, p, q, h->fixed, ow, fin(HT_PQ), partials, counter);
+      if (int rc = reduce(HT_PQ, 1)) return rc;
+      k_heat_update<<<nb, SIC_VEC_THREADS, 0, st>>>(n, T, r, z, p, q, diag, h->fixed, ow, fin(HT_UPDATE), partials, counter);
+      if (int rc = reduce(HT_UPDATE, 1)) return rc;
       k_heat_p<<<nb, SIC_VEC_THREADS, 0, st>>>(n, p, z, q, S);
     }
     launched += batch;
     if (int rc = sic_check_launch("heat cg batch")) return rc;
   }
+  if (multi && halo->p2p && sic_p2p_error(halo->p2p)) return sic_fail("P2P exchange timed out waiting for a peer");
   ksp->iterations = g_heat_host->iters;
   ksp->rnorm = sqrt(g_heat_host->rr);
   ksp->rnorm0 = sqrt(g_heat_host->rr0);

@@ -110,6 +110,7 @@ def partition_grid(ctx: DistContext, tetmesh, hierarchy=None, min_cells_per_rank
     local = part.local_mesh(tetmesh)
     grid = GridHandlerGMSH.from_mesh(local, reorder=False)
     grid.partition = part
+    grid.dist = ctx
     grid.dist_min_cells_per_rank = min_cells_per_rank
     if hierarchy is not None:
         grid.hierarchy = hierarchy

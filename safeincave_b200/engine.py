@@ -110,6 +110,7 @@ class Engine:
         self.vol = torch.zeros(ns, dtype=torch.float64, device=dev)
         self.vol[:self.N] = vol
         self.launches = 0
+        self.halo, self._halo_keep = None, None
         if geometry_only:
             self.operator_only = True
             return

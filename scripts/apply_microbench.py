@@ -29,4 +29,4 @@ for _ in range(n):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 byt = eng.N * 408 + eng.M * 72
-print(f"{os.environ.get('SIC_LIB_PATH','default'):60s} cells {eng.N} apply {ms*1e3:.1f} us  {byt/ms/1e6:.0f} GB/s")
+print(f"{'libsafeincave_cuda.so':60s} cells {eng.N} apply {ms*1e3:.1f} us  {byt/ms/1e6:.0f} GB/s")

@@ -3,7 +3,9 @@ Runs the cavern case partitioned over N GPUs and (on every rank, on its own GPU)
 compares displacement / stress / creep strain on the rank's local nodes and cells.
 
 --pc mg: multigrid CG with the bench's solver settings (extrapolated guess, lagged setup) on a NESTED hierarchy: every
-level with at least --min-cells-per-rank cells per rank is partitioned (csrc/mg.cu), the ones below are replicated."""
+level with at least --min-cells-per-rank cells per rank is partitioned (csrc/mg.cu), the ones below are replicated.
+--heat: Simulator_TM instead of Simulator_M (HeatDiffusion on the partitioned grid, csrc/heat.cu; thermal strain and
+thermally activated creep in the momentum equation): temperatures compared as well."""
 import argparse
 import os
 import sys
@@ -25,6 +27,7 @@ ap.add_argument("--min-cells-per-rank", type=int, default=200_000)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--rtol", type=float, default=1e-12)
 ap.add_argument("--tol", type=float, default=1e-8)
+ap.add_argument("--heat", action="store_true")
 a = ap.parse_args()
 
 ctx = distributed.init()
@@ -45,10 +48,28 @@ def settings(eq):
         eq.solver.mg_setup_first = 2
 
 
+heat = heat1 = None
+if a.heat:
+    from tests import heat_checks as H
+    hc = H.heat_case(gg, "cavern_regular")
+    case["dt"], case["t_final_run"], case["thermo_alpha"] = 20 * H.DAY, a.steps * 20 * H.DAY, 44e-6
+
+
+def thermo(eq, sim_m, grid, part):
+    """Simulator_TM around the momentum equation of `sim_m` (examples/thermomechanics/2_cavern/main.py's set-up)."""
+    hcl = dict(hc, T0=hc["T0"][part.local_nodes.cpu().numpy()] if part is not None else hc["T0"])
+    ht = H.build_heat(sf, grid, hcl)
+    eq.mat.add_to_thermoelastic(sf.Thermoelastic(case["thermo_alpha"] * torch.ones(grid.n_elems, dtype=torch.float64)))
+    eq.set_material(eq.mat)
+    return ht, sf.Simulator_TM(eq, ht, sim_m.t_control, [], compute_elastic_response=True, verbose=False)
+
+
 grid, part = distributed.partition_grid(ctx, tm, hierarchy=h if a.pc == "mg" else None,
                                         min_cells_per_rank=a.min_cells_per_rank)
 eq, sim = cases.build(case, grid, device=dev, part=part, ctx=ctx)
 settings(eq)
+if a.heat:
+    heat, sim = thermo(eq, sim, grid, part)
 sim.verbose = False
 hist = sim.run()
 lc = eq.mg.lc if eq.mg is not None else None
@@ -56,6 +77,8 @@ level_cells = [e.N for e in eq.mg.engines] if eq.mg is not None else None
 # single-domain run of the same case on this rank's GPU
 eq1, sim1 = cases.build(case, gg, device=dev)
 settings(eq1)
+if a.heat:
+    heat1, sim1 = thermo(eq1, sim1, gg, None)
 sim1.verbose = False
 hist1 = sim1.run()
 ln = part.local_nodes.to(dev)
@@ -70,6 +93,12 @@ print(f"rank {ctx.rank}/{ctx.world}: cells {eq.engine.N} nodes {eq.engine.M} pee
       f"| u err {e_u:.2e} sig err {e_s:.2e} eps_cr err {e_c:.2e} | newton {its} ksp {[r['ksp_iterations'] for r in hist]} "
       f"vs {[r['ksp_iterations'] for r in hist1]}", flush=True)
 assert e_u < a.tol and e_s < a.tol and e_c < a.tol and its[0] == its[1]
+if a.heat:
+    T0 = torch.as_tensor(hc["T0"], device=dev)
+    e_T = rel(heat.T_dev[:heat.n_nodes] - T0[ln], heat1.T_dev[ln] - T0[ln])
+    print(f"rank {ctx.rank}: temperature change err {e_T:.2e}, max |dT| {float((heat1.T_dev - T0).abs().max()):.2f} K, "
+          f"heat iterations {[k[0] for k in heat.ksp_log]} vs {[k[0] for k in heat1.ksp_log]}", flush=True)
+    assert e_T < a.tol
 ctx.barrier()
 if ctx.rank == 0:
     print("DIST CHECK OK")

@@ -142,3 +142,56 @@ def test_guess_extrapolation_same_coefficients_on_every_rank(sf, world):
 
     res = run_ranks(world, body)
     assert all(r == res[0] for r in res)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_heat_and_thermomechanics_match_single_rank(sf, world):
+    """HeatDiffusion on a partitioned grid (the reference's heat solve is MPI-parallel, HeatEquation.py:344-364): halo sums
+    of the operator / right-hand side / diagonal, owner-weighted dot products, Dirichlet node sets from the global mesh;
+    then Simulator_TM on the same partition.  Temperatures and the coupled displacement equal the single-rank run."""
+    from safeincave_b200 import cases, distributed
+    from safeincave_b200.mesh import TetMesh, red_refine
+    from tests import heat_checks as H
+    from tests.hostemu import EmuEngine
+    from tests.hostemu.ranks import run_ranks
+    import torch as to
+    old = sf.HeatDiffusion.engine_cls
+    sf.HeatDiffusion.engine_cls = EmuEngine
+    try:
+        tm = red_refine(TetMesh.load_npz(os.path.join(GOLD, "mesh_cube_coarse.npz")))
+        gg = sf.GridHandlerGMSH.from_mesh(tm)
+        tm = gg.tetmesh
+        hc = H.heat_case(gg, "cube_coarse")
+        n_steps, dt = 3, 0.5 * H.DAY
+
+        def run(grid, part=None, ctx=None):
+            hcl = dict(hc, T0=hc["T0"][part.local_nodes.cpu().numpy()] if part is not None else hc["T0"])
+            heat = H.build_heat(sf, grid, hcl)
+            case = cases.triaxial_case(gg, n_steps=n_steps)
+            case["dt"], case["t_final_run"], case["thermo_alpha"] = dt, n_steps * dt, 44e-6
+            eq, sim_m = cases.build(case, grid, part=part, ctx=ctx)
+            eq.mat.add_to_thermoelastic(sf.Thermoelastic(case["thermo_alpha"] * to.ones(grid.n_elems, dtype=to.float64)))
+            eq.set_material(eq.mat)
+            sim = sf.Simulator_TM(eq, heat, sim_m.t_control, [], compute_elastic_response=True, verbose=False)
+            hist = sim.run()
+            return heat, eq, hist
+
+        heat1, eq1, hist1 = run(gg)
+
+        def body(ctx):
+            grid, part = distributed.partition_grid(ctx, tm)
+            heat, eq, hist = run(grid, part, ctx)
+            ln = part.local_nodes
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+            return dict(e_T=rel(heat.T_dev[:heat.n_nodes], heat1.T_dev[ln]),
+                        e_dT=rel(heat.T_dev[:heat.n_nodes] - to.as_tensor(hc["T0"])[ln], heat1.T_dev[ln] - to.as_tensor(hc["T0"])[ln]),
+                        e_u=rel(eq.X, eq1.X[ln]), newton=[h["iterations"] for h in hist],
+                        heat_its=[k[0] for k in heat.ksp_log])
+
+        res = run_ranks(world, body)
+        for r in res:
+            assert r["e_T"] < 1e-11 and r["e_dT"] < 1e-8 and r["e_u"] < 1e-8, r
+            assert r["newton"] == [h["iterations"] for h in hist1]
+            assert all(abs(a - b) <= 1 for a, b in zip(r["heat_its"], [k[0] for k in heat1.ksp_log]))
+    finally:
+        sf.HeatDiffusion.engine_cls = old

@@ -38,3 +38,8 @@ def test_two_ranks_multigrid_bench_settings_nested_partition():
     partitioned by the cells' ancestors, level 0 replicated; fields equal to the single-GPU run of the same settings."""
     out = _torchrun(2, "--levels", "2", "--pc", "mg", "--min-cells-per-rank", "20000", "--rtol", "1e-10")
     assert "distributed from level 1" in out
+
+
+def test_two_ranks_thermomechanical_steps():
+    """Simulator_TM with HeatDiffusion on the partitioned grid (BASELINE config 4's physics on cavern_regular x8)."""
+    _torchrun(2, "--levels", "1", "--pc", "jacobi", "--heat", "--rtol", "1e-12")
