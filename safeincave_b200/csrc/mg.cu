@@ -511,6 +511,7 @@ static long long g_fused_coarse_launches = 0;
 extern "C" long long sic_mg_fused_coarse_launches(void) { return g_fused_coarse_launches; }
 
 static int g_fused_refused = 0;        // the cooperative launch failed once: launch-per-step sweep from then on
+static int g_fused_not_in_capture = 0;
 static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, double lo, const int* done, cudaStream_t st,
                             int wanted) {
 #ifdef SIC_HOSTEMU
@@ -518,6 +519,11 @@ static bool mg_coarse_fused(const sic_mg_level_t& L, const double* b, int its, d
   return false;
 #else
   if (!wanted || g_fused_refused || mg_halo(L) || its < 2 || its > SIC_MG_MAX_COARSE_ITS || L.prob.n_cells <= 0) return false;
+  if (g_fused_not_in_capture) {       // a capture with the cooperative launch in it failed once: keep it out of graphs
+    cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cst) != cudaSuccess) cudaGetLastError();
+    if (cst != cudaStreamCaptureStatusNone) return false;
+  }
   const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
   static int max_blocks = -1;
   if (max_blocks < 0) {
@@ -716,6 +722,12 @@ static MgGraphEntry g_mg_graphs[SIC_MG_GRAPH_SLOTS];
 static unsigned long long g_mg_graph_clock = 0;
 static int g_mg_graph_broken = 0;      // a capture failed once: launch kernel by kernel from then on
 
+static cudaStream_t mg_capture_stream() {
+  static cudaStream_t cs = nullptr;
+  if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); cs = nullptr; }
+  return cs;
+}
+
 template <class Body>
 static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, const double* b_ext,
                                           double* x, double* work, double rtol, double atol, int guess, cudaStream_t st,
@@ -726,7 +738,7 @@ static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels
   memcpy(key.lv, lv, sizeof(sic_mg_level_t) * n_levels);
   memcpy(&key.o, o, sizeof(sic_mg_opts_t));
   key.b_ext = b_ext; key.x = x; key.work = work; key.rtol = rtol; key.atol = atol;
-  key.n_levels = n_levels; key.guess = guess; key.fused_refused = g_fused_refused; key.st = st;
+  key.n_levels = n_levels; key.guess = guess; key.fused_refused = g_fused_refused | (g_fused_not_in_capture << 1); key.st = st;
   for (int l = 0; l < n_levels; ++l) { key.lam[l] = lv[l].lambda_max; key.lv[l].lambda_max = 0.0; }
   MgGraphEntry* slot = nullptr;
   MgGraphEntry* lru = &g_mg_graphs[0];
@@ -739,12 +751,23 @@ static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels
   }
   if (!slot) slot = lru;
   cudaGraph_t graph = nullptr;
-  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); g_mg_graph_broken = 1; return nullptr; }
-  const int rc = body(nullptr);
-  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-  if (rc != 0 || ce != cudaSuccess || !graph) {
+  for (int attempt = 0; attempt < 2 && !graph; ++attempt) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      fprintf(stderr, "safeincave_cuda: cudaStreamBeginCapture failed (%s); launching kernel by kernel\n",
+              cudaGetErrorString(cudaGetLastError()));
+      g_mg_graph_broken = 1;
+      return nullptr;
+    }
+    const int rc = body(nullptr);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc == 0 && ce == cudaSuccess && graph) break;
     cudaGetLastError();
-    if (graph) cudaGraphDestroy(graph);
+    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+    if (attempt == 0 && o->fused_coarse && !g_fused_not_in_capture) {   // retry without the cooperative launch
+      g_fused_not_in_capture = 1;
+      key.fused_refused = g_fused_refused | (g_fused_not_in_capture << 1);
+      continue;
+    }
     g_mg_graph_broken = 1;
     fprintf(stderr, "safeincave_cuda: CUDA graph capture of the MG-CG iteration failed (%s); launching kernel by kernel\n",
             ce != cudaSuccess ? cudaGetErrorString(ce) : sic_last_error());
@@ -851,8 +874,17 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   ksp->graph_launches = 0;
   ksp->direct_iterations = 0;
 #ifndef SIC_HOSTEMU
+  // Captured on a stream of the library's own (the caller's is normally the legacy default stream, which cannot be
+  // captured) and replayed on the caller's stream.  The lambdas above launch on `st` / `stream`, whatever they hold.
   cudaGraphExec_t gexec = nullptr;
-  if (ksp->use_graph) gexec = mg_iteration_graph(lv, n_levels, o, b_ext, x, work, rtol, atol, guess, st, iteration);
+  if (ksp->use_graph) {
+    if (cudaStream_t cs = mg_capture_stream()) {
+      void* const user = stream;
+      st = cs; stream = (void*)cs;
+      gexec = mg_iteration_graph(lv, n_levels, o, b_ext, x, work, rtol, atol, guess, cs, iteration);
+      st = (cudaStream_t)user; stream = user;
+    }
+  }
 #endif
 
   int launched = 0;
