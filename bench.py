@@ -76,6 +76,9 @@ def parse():
                     help="PC mg: replay every Krylov iteration from one captured CUDA graph (sic_ksp_t.use_graph)")
     ap.add_argument("--fused-coarse", type=int, default=1,
                     help="PC mg: the coarsest level's Chebyshev sweep as one cooperative launch (sic_mg_opts_t.fused_coarse)")
+    ap.add_argument("--compressed", type=int, default=1,
+                    help="PC mg: operator applications inside the V-cycle read float(sym(C_T)) + float geometry "
+                         "(152 B per cell instead of 408); the Krylov operator stays exact FP64")
     ap.add_argument("--probe-mg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-fallback", action="store_true",
                     help="N = 1: do not retry with the configurations measured earlier when the run fails its own checks")
@@ -405,7 +408,8 @@ def run_b200(args):
     sim.verbose = False
     if pc == "mg":
         eq.solver.getPC().setType("mg")
-        eq.mg_options = dict(eq.mg_options, use_graph=bool(args.graph), fused_coarse=bool(args.fused_coarse))
+        eq.mg_options = dict(eq.mg_options, use_graph=bool(args.graph), fused_coarse=bool(args.fused_coarse),
+                             compressed=bool(args.compressed))
     apply_solver_settings(eq.solver, args.warm_start, args.mg_lag)
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
@@ -432,6 +436,7 @@ def run_b200(args):
     eng.profile = True
     eng.profile_summary()
     eng.op_ms, eng.op_samples, eng.op_launches = 0.0, 0, 0
+    eng.op_dot_ms, eng.op_dot_samples, eng.op_dot_launches = 0.0, 0, 0
     launches0, nodes0 = eng.launches, getattr(eng, "graph_kernel_nodes", 0)
     graphs0 = eq.mg.graph_launches if eq.mg is not None else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -519,18 +524,42 @@ def run_b200(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bytes_per_launch = N_loc * (36 * 8 + 12 * 8 + 8 + 16) + M_loc * (24 + 48)      # this rank's launch
-    achieved = bytes_per_launch / (op_ms * 1e-3) / 1e9 if op_ms > 0 else None
-    traffic = None
+    # Two operator kernels run on the finest level: the exact FP64 one of the Krylov iteration (k_mg_ebe_dot, or
+    # k_ebe_dot without multigrid: 408 B per cell) and, inside the V-cycle, 2 nu applications of the preconditioner's
+    # (k_mg_ebe_pc on float(sym(C_T)) + float geometry, 152 B per cell; k_mg_ebe when --compressed 0).  `roofline` is the
+    # one with the larger share of the step, `roofline_other` the other.  Both add 72 B per node (x read, y read-modify-write).
+    traffic_ref = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.isfile(tpath):        # ncu --set full capture at 918 144 cells; DRAM traffic scales with the cell count
-        ref = json.load(open(tpath))
-        traffic = int(ref["918144"] * N_loc / 918144)
-    roofline = {"bound": "hbm", "kernel": "k_mg_ebe (finest level)" if pc == "mg" else ("k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain"),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "avg_launch_ms": op_ms, "launches_sampled": eng.op_samples, "launches_in_timed_region": op_launches,
-                "share_of_step_time": op_ms * op_launches / ms if ms > 0 else None}
+    if os.path.isfile(tpath):
+        traffic_ref = json.load(open(tpath))
+
+    def roof(kernel, ms_launch, samples, n_launches, bytes_per_cell):
+        if not (ms_launch > 0):
+            return None
+        nbytes = N_loc * bytes_per_cell + M_loc * (24 + 48)          # this rank's launch
+        ach = nbytes / (ms_launch * 1e-3) / 1e9
+        ref = traffic_ref.get(kernel.split(" ")[0])                  # ncu --set full of THIS kernel (profiles/README.md)
+        traffic, src = None, None
+        if ref:
+            traffic = int(ref["dram_bytes"] * N_loc / ref["n_cells"])
+            src = (f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of {kernel.split(' ')[0]} at {ref['n_cells']} cells "
+                   f"({ref['file']})" + ("" if ref["n_cells"] == N_loc else f", scaled to {N_loc} cells"))
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_source": src, "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes,
+                "algorithmic_bytes_per_cell": bytes_per_cell, "avg_launch_ms": ms_launch, "launches_sampled": samples,
+                "launches_in_timed_region": n_launches, "share_of_step_time": ms_launch * n_launches / ms if ms > 0 else None}
+    if pc == "mg":
+        pc_on = bool(eq.mg is not None and eq.mg.compressed)
+        dot_ms = eng.op_dot_ms / max(eng.op_dot_samples, 1)
+        r_cycle = roof("k_mg_ebe_pc (finest level, inside the V-cycle)" if pc_on else "k_mg_ebe (finest level, inside the V-cycle)",
+                       op_ms, eng.op_samples, op_launches, 152 if pc_on else 408)
+        r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, eng.op_dot_samples, eng.op_dot_launches, 408)
+        both = [r for r in (r_cycle, r_dot) if r]
+        both.sort(key=lambda r: -r["share_of_step_time"])
+        roofline, roofline_other = (both + [None, None])[:2]
+    else:
+        roofline = roof("k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain", op_ms, eng.op_samples, op_launches, 408)
+        roofline_other = None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -554,7 +583,7 @@ def run_b200(args):
         "launch_breakdown": {"graph_launches": graph_launches, "kernels_inside_graphs": graph_nodes,
                              "kernels_executed": launches - graph_launches + graph_nodes,
                              "host_launches_per_step": launches / args.steps},
-        "roofline": roofline, "constitutive": constitutive,
+        "roofline": roofline, "roofline_other": roofline_other, "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,
     }
     if e2e:

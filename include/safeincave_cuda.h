@@ -272,6 +272,11 @@ typedef struct {
    * launched kernel by kernel (all of them without use_graph; with it, the timed iteration of each batch) */
   int32_t graph_launches;
   int32_t direct_iterations;
+  /* sic_mg_solve with time_operator: op_ms / op_samples time the finest-level operator INSIDE the V-cycle (the
+   * compressed one when the levels carry pc_ct), op_dot_ms / op_dot_samples the exact Krylov operator (k_mg_ebe_dot) */
+  int32_t op_dot_samples;
+  int32_t reserved;
+  double op_dot_ms;
 } sic_ksp_t;
 
 /* Workspace: sic_ksp_workspace_doubles(n_nodes, method) doubles, caller-allocated. */
@@ -323,6 +328,11 @@ typedef struct {
   /* work vectors, [3 n_nodes] each */
   double *x, *b, *r, *d, *t;
   double* pv;              /* [3 n_nodes] or NULL: power-iteration vector kept BETWEEN calls of sic_mg_setup (warm start) */
+  /* compressed operator of the preconditioner, or both NULL: every operator application INSIDE the V-cycle (smoother,
+   * residual, power iteration) then reads the symmetric part of C_T as 21 floats per cell and the gradients + volume
+   * as 13 floats -- 152 B per cell instead of 408 -- with FP64 arithmetic; the Krylov operator stays exact */
+  float* pc_ct;            /* [cell_stride/128][21][128] filled by sic_mg_setup from prob.CT */
+  const float* pc_geom;    /* [13][cell_stride] rows 0-11 = prob.grad, row 12 = prob.vol (filled by the caller) */
   const sic_halo_t* halo;  /* several GPUs: this level's cells are partitioned exactly as for sic_ksp_solve.  Partitioned
                               levels are the finest one and any run of levels below it (never level 0), NESTED: a cell
                               lives on the rank of its ancestor, so the transfer tables between two partitioned levels are

@@ -129,6 +129,19 @@ class GridHandlerGMSH:
         grid.hierarchy = hierarchy
         return grid
 
+    def refine(self, levels: int, nested=True, device="cpu"):
+        """A NEW grid on this grid's mesh regularly (red / Bey) refined ``levels`` times, with this mesh as the coarsest
+        level of the attached hierarchy: PC type ``mg`` (the stand-in for the reference's ``gamg``,
+        nobian/Simulation/run_interlayer.py:2114-2116) then works for ANY mesh loaded from a .msh file, not only for the
+        bench's synthetic ones.  Region / boundary tags are inherited by the children; per-cell material tensors must be
+        built for the refined grid (``refined.get_parameter`` / ``region_indices`` follow the new numbering)."""
+        from .multigrid import refine_hierarchy
+        if levels < 1:
+            raise ValueError("refine: levels must be >= 1")
+        grid = type(self).from_hierarchy(refine_hierarchy(self.tetmesh, int(levels), device=device, nested=nested))
+        grid.grid_folder, grid.geometry_name = self.grid_folder, self.geometry_name
+        return grid
+
     # --- tag queries (Grid.py:392-494)
     def get_boundaries(self):
         return _MeshTags(2, np.arange(self.tetmesh.tris.shape[0]), self.tetmesh.tri_tags)

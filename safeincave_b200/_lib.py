@@ -65,7 +65,8 @@ class SicKsp(ctypes.Structure):
                 ("iterations", c_int32), ("reason", c_int32),
                 ("rnorm", c_double), ("rnorm0", c_double),
                 ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double),
-                ("graph_launches", c_int32), ("direct_iterations", c_int32)]
+                ("graph_launches", c_int32), ("direct_iterations", c_int32),
+                ("op_dot_samples", c_int32), ("reserved", c_int32), ("op_dot_ms", c_double)]
 
 
 class SicMgLevel(ctypes.Structure):
@@ -73,7 +74,7 @@ class SicMgLevel(ctypes.Structure):
                 ("parent_a", c_void_p), ("parent_b", c_void_p), ("rst_ptr", c_void_p), ("rst_idx", c_void_p),
                 ("children", c_void_p),
                 ("x", c_void_p), ("b", c_void_p), ("r", c_void_p), ("d", c_void_p), ("t", c_void_p), ("pv", c_void_p),
-                ("halo", c_void_p)]
+                ("pc_ct", c_void_p), ("pc_geom", c_void_p), ("halo", c_void_p)]
 
 
 class SicMgOpts(ctypes.Structure):

@@ -87,6 +87,11 @@ __device__ __forceinline__ double ldcg_f64(const double* p) {
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float ldg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ int ldg_s32(const int* p) {
   int v;
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -172,11 +177,25 @@ struct TileScratch {                      // shared memory of one operator CTA (
   int eoff[4 * SIC_TILE_CELLS + 1];       // per unique node: offset into ent
 };
 
+// Compressed operator of the multigrid PRECONDITIONER (PC = true): the symmetric part of C_T as 21 floats per cell
+// (tiled like C_T: [tile][21][128]) and the gradients + volume as 13 floats ([13][cell_stride]): 152 B per cell
+// instead of 408.  The arithmetic stays FP64 (the vectors are).  A preconditioner only has to approximate K: the
+// non-symmetry of the finite-difference tangent is round-off (1e-6 relative) and float storage perturbs the entries by
+// 6e-8, neither of which moves the Krylov iteration count; the OUTER operator of the solve is always the exact one.
+#define SIC_PC_CT_ROWS 21
+#define SIC_PC_GEOM_ROWS 13
+#define SIC_PC_CT_INDEX(e, i) (((size_t)((i) / SIC_TILE_CELLS) * SIC_PC_CT_ROWS + (e)) * SIC_TILE_CELLS + ((i) % SIC_TILE_CELLS))
+__host__ __device__ constexpr int sic_sym_index(int r, int k) {      // upper triangle, row-major
+  return (r <= k) ? (r * 6 - (r * (r - 1)) / 2 + (k - r)) : (k * 6 - (k * (k - 1)) / 2 + (r - k));
+}
+
 // XCOH: gather x through the coherent path (x was written earlier in the SAME launch, k_mg_coarse_fused).
-template <int MODE, bool XCOH = false>
+template <int MODE, bool XCOH = false, bool PC = false>
 __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const double* __restrict__ x,
                                                    double* __restrict__ y, TileScratch& sc,
-                                                   const int* done_flag = nullptr) {
+                                                   const int* done_flag = nullptr, const float* __restrict__ pc_ct = nullptr,
+                                                   const float* __restrict__ pc_geom = nullptr) {
+  static_assert(!(PC && MODE != 0), "the compressed operator only applies K");
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int i = tile * SIC_TILE_CELLS + tid;
   const size_t ns = (size_t)P.cell_stride;
@@ -190,24 +209,44 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
   asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(ent_lo), "=r"(ent_hi)
                : "l"(P.ent + (size_t)tile * 4 * SIC_TILE_CELLS + 4 * tid));
   int node[4];
-  double g[12], CT[36], er[6], ua[12];
+  double g[12], CT[PC ? SIC_PC_CT_ROWS : 36], er[6], ua[12], vol;
 #pragma unroll
   for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
+  if constexpr (PC) {
+    float gf[SIC_PC_GEOM_ROWS], cf[SIC_PC_CT_ROWS];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
-  const double vol = ldg_f64(P.vol + i);
-  const double* ct = P.CT + SIC_CT_INDEX(0, i);
+    for (int k = 0; k < SIC_PC_GEOM_ROWS; ++k) gf[k] = ldg_f32(pc_geom + k * ns + i);
+    const float* ct = pc_ct + SIC_PC_CT_INDEX(0, i);
 #pragma unroll
-  for (int k = 0; k < 36; ++k) CT[k] = ldg_f64(ct + k * SIC_TILE_CELLS);
-  if (MODE == 1) {
+    for (int k = 0; k < SIC_PC_CT_ROWS; ++k) cf[k] = ldg_f32(ct + k * SIC_TILE_CELLS);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
-  }
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
+      for (int j = 0; j < 3; ++j)
+        ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
+    }
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
+    for (int k = 0; k < 12; ++k) g[k] = (double)gf[k];
+    vol = (double)gf[12];
+#pragma unroll
+    for (int k = 0; k < SIC_PC_CT_ROWS; ++k) CT[k] = (double)cf[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
+    vol = ldg_f64(P.vol + i);
+    const double* ct = P.CT + SIC_CT_INDEX(0, i);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) CT[k] = ldg_f64(ct + k * SIC_TILE_CELLS);
+    if (MODE == 1) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
+    }
   }
   // scatter plan of the tile -> shared memory (depends only on q0, requested first)
   const int nq = q1 - q0, ebase = tile * 4 * SIC_TILE_CELLS;
@@ -239,7 +278,7 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
   for (int r = 0; r < 6; ++r) {
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc += CT[r * 6 + k] * eps[k];
+    for (int k = 0; k < 6; ++k) acc += CT[PC ? sic_sym_index(r, k) : r * 6 + k] * eps[k];
     s[r] = acc;
   }
 #pragma unroll

@@ -97,6 +97,29 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, c
   ebe_tile_scatter<0>(P, x, y, sc, done);
 }
 
+// the compressed operator of the preconditioner (fem.cuh, PC = true): symmetric float C_T, float geometry
+__global__ void __launch_bounds__(SIC_TILE_CELLS, 4) k_mg_ebe_pc(sic_problem_t P, const float* __restrict__ pc_ct,
+                                                               const float* __restrict__ pc_geom, const double* __restrict__ x,
+                                                               double* __restrict__ y, const int* done) {
+  __shared__ TileScratch sc;
+  ebe_tile_scatter<0, false, true>(P, x, y, sc, done, pc_ct, pc_geom);
+}
+
+// pc_ct = float(sym(C_T)) of one level (once per set-up; both tiled by 128 cells)
+__global__ void __launch_bounds__(128) k_mg_ct_compress(int n_cells, const double* __restrict__ CT, float* __restrict__ pc_ct) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+#pragma unroll
+    for (int k = r; k < 6; ++k) {
+      const double v = (r == k) ? __ldg(CT + SIC_CT_INDEX(r * 6 + k, i))
+                                : 0.5 * (__ldg(CT + SIC_CT_INDEX(r * 6 + k, i)) + __ldg(CT + SIC_CT_INDEX(k * 6 + r, i)));
+      pc_ct[SIC_PC_CT_INDEX(sic_sym_index(r, k), i)] = (float)v;
+    }
+  }
+}
+
 // q = K p with the per-cell energies p.Kp summed per block (finished by k_mg_sum_pq)
 __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe_dot(sic_problem_t P, const double* __restrict__ x,
                                                                 double* __restrict__ y, double* __restrict__ partials,
@@ -430,6 +453,7 @@ static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_
     if (L.prob.abi_version != SIC_ABI_VERSION) return sic_fail("multigrid: sic_problem_t.abi_version mismatch");
     if (!L.fixed || !L.dinv || !L.x || !L.b || !L.r || !L.d || !L.t || !L.prob.CT)
       return sic_fail("multigrid: level with a null buffer");
+    if ((L.pc_ct != nullptr) != (L.pc_geom != nullptr)) return sic_fail("multigrid: pc_ct and pc_geom go together");
     const bool part = L.halo && L.halo->n_ranks > 1;
     if (part && l == 0) return sic_fail("multigrid: the coarsest level must be replicated (not partitioned)");
     if (part && l + 1 < n_levels && !(lv[l + 1].halo && lv[l + 1].halo->n_ranks > 1))
@@ -452,7 +476,10 @@ static inline const sic_halo_t* mg_halo(const sic_mg_level_t& L) { return (L.hal
 // t = K x on level L (t must be zero on entry); several GPUs: completed on the interface nodes by the halo sum
 static int mg_apply(const sic_mg_level_t& L, const double* x, double* t, const int* done, cudaStream_t st) {
   const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
-  if (cb > 0) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, x, t, done);
+  if (cb > 0) {
+    if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, x, t, done);
+    else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, x, t, done);
+  }
   if (const sic_halo_t* h = mg_halo(L)) return sic_exchange(h, t, 3, nullptr, 0, (void*)st);
   return 0;
 }
@@ -473,7 +500,7 @@ extern "C" int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes) {
 }
 
 static MgScal* g_mg_host = nullptr;   // pinned mirror of the device scalars
-static cudaEvent_t g_mg_ev[2] = {nullptr, nullptr};
+static cudaEvent_t g_mg_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] V-cycle operator, [2,3] Krylov operator
 
 static int mg_host_mirror() {
   if (g_mg_host) return 0;
@@ -578,7 +605,10 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     const int nn = L.prob.n_nodes, nd = 3 * nn, cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
     const sic_halo_t* h = mg_halo(L);
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[0], st);
-    if (cb > 0) k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    if (cb > 0) {
+      if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.d, L.t, done);
+      else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    }
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
     if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
     k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
@@ -632,6 +662,11 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
       if (int rc = sic_allreduce_sum(h->comm, lv[l - 1].prob.CT, (int)cnt, stream)) return rc;
     }
   }
+  for (int l = 0; l < n_levels; ++l) {     // compressed copies for the operator applications inside the V-cycle
+    const int nc = lv[l].prob.n_cells;
+    if (lv[l].pc_ct && nc > 0) k_mg_ct_compress<<<mg_blocks(nc, 128), 128, 0, st>>>(nc, lv[l].prob.CT, lv[l].pc_ct);
+  }
+  if (int rc = sic_check_launch("k_mg_ct_compress")) return rc;
   MgWork W = mg_work(work);
   // 2. block-Jacobi blocks and 3. lambda_max(Dinv K) by power iteration, level by level (x: v, d: w, t: K v)
   for (int l = 0; l < n_levels; ++l) {
@@ -836,9 +871,11 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   };
   ksp->op_samples = 0;
   ksp->op_ms = 0.0;
+  ksp->op_dot_samples = 0;
+  ksp->op_dot_ms = 0.0;
   cudaEvent_t* ev = nullptr;
   if (ksp->time_operator) {
-    if (!g_mg_ev[0]) { cudaEventCreate(&g_mg_ev[0]); cudaEventCreate(&g_mg_ev[1]); }
+    if (!g_mg_ev[0]) for (int k = 0; k < 4; ++k) cudaEventCreate(&g_mg_ev[k]);
     ev = g_mg_ev;
   }
 
@@ -860,7 +897,9 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   // GPUs: the halo sum of q and the sum of p.Kp over the ranks travel in ONE exchange.  Every argument is either a
   // device pointer or a value fixed until the next setup, so the iteration can be replayed from a CUDA graph.
   auto iteration = [&](cudaEvent_t* time_ev) -> int {
+    if (time_ev) cudaEventRecord(time_ev[2], st);
     if (cb > 0) k_mg_ebe_dot<<<cb, SIC_TILE_CELLS, 0, st>>>(*p, pp, q, W.partials, &S->done);
+    if (time_ev) cudaEventRecord(time_ev[3], st);
     k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
     if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
     k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
@@ -895,6 +934,7 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     if (timed_batch) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { ksp->op_ms += ms; ksp->op_samples += 1; }
+      if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) { ksp->op_dot_ms += ms; ksp->op_dot_samples += 1; }
       timed_batch = false;
     }
     if (g_mg_host->done || launched >= ksp->max_it) break;

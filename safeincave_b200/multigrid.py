@@ -169,7 +169,7 @@ class Multigrid:
 
     def __init__(self, fine_engine, hierarchy: Hierarchy, nu=2, coarse_its=30, smooth_lo=0.1, coarse_lo=0.01,
                  safety=1.15, power_its=32, power_its_warm=4, part=None, coarse_fixed=None, dist=None,
-                 dist_min_cells_per_rank=200_000, fused_coarse=True, use_graph=True):
+                 dist_min_cells_per_rank=200_000, fused_coarse=True, use_graph=True, compressed=True):
         """part: the fine engine holds only this rank's cells (partition.Partition; ``hierarchy`` is the GLOBAL one).
         With a NESTED hierarchy (refine_hierarchy(..., nested=True)) and ``dist`` (the DistContext, for the levels'
         own exchange mailboxes) every level down to ``distributed_from(...)`` is partitioned by the rank's ancestors'
@@ -178,7 +178,9 @@ class Multigrid:
         numbering); needed when the finest level is partitioned (a rank cannot inject a mask it holds a part of).
         fused_coarse: the coarsest level's sweep as one cooperative launch; use_graph: replay every Krylov iteration of
         ``solve`` from one captured CUDA graph (both: csrc/mg.cu; the graph is not used while the operator is being timed
-        launch by launch)."""
+        launch by launch).
+        compressed: the operator applications INSIDE the V-cycle read a float copy of the symmetric part of C_T and of the
+        geometry (152 B per cell instead of 408; sic_mg_level_t.pc_ct / pc_geom); the Krylov operator stays exact."""
         import ctypes
 
         import torch
@@ -259,6 +261,12 @@ class Multigrid:
                 self._keep.append(None)
             for k in ("x", "b", "r", "d", "t", "pv"):
                 setattr(lv, k, _ptr(self.vec[l][k]))
+            if compressed:
+                pc_geom = torch.cat([eng.grad.to(torch.float32), eng.vol.to(torch.float32).reshape(1, -1)]).contiguous()
+                pc_ct = torch.zeros((eng.ns // 128, 21, 128), dtype=torch.float32, device=dev)
+                self.vec[l]["pc_geom"], self.vec[l]["pc_ct"] = pc_geom, pc_ct
+                lv.pc_ct, lv.pc_geom = _ptr(pc_ct), _ptr(pc_geom)
+        self.compressed = bool(compressed)
         need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
         self.work = zeros(need)
         # kernels per V-cycle (bench.py's gpu_launches): per level 2 nu operator + 2 nu smoother + residual, restriction,
@@ -347,5 +355,10 @@ class Multigrid:
         eng.op_ms += float(ksp.op_ms)
         eng.op_samples += int(ksp.op_samples)
         nu, n = self.opts.nu, len(self.engines)
-        eng.op_launches += (1 + (2 * nu if n > 1 else self.opts.coarse_its)) * int(ksp.iterations)   # fine-level applies
+        # finest-level operator launches: 2 nu per V-cycle (one cycle per iteration + the first), timed by op_ms -- the
+        # compressed kernel when the levels carry pc_ct --, and the exact Krylov operator once per iteration (op_dot_ms)
+        eng.op_launches += (2 * nu if n > 1 else self.opts.coarse_its) * (int(ksp.iterations) + 1)
+        eng.op_dot_ms = getattr(eng, "op_dot_ms", 0.0) + float(ksp.op_dot_ms)
+        eng.op_dot_samples = getattr(eng, "op_dot_samples", 0) + int(ksp.op_dot_samples)
+        eng.op_dot_launches = getattr(eng, "op_dot_launches", 0) + int(ksp.iterations)
         return ksp

@@ -4,7 +4,7 @@ Rewrites the two CUDA constructs g++ cannot parse, and nothing else, so that the
 files compile UNMODIFIED IN MEANING as C++ against tests/hostemu/cuda_emu.h:
 
   kernel<<<grid, block, smem, stream>>>(args);   ->  SIC_EMU_LAUNCH(kernel, grid, block, smem, stream, args);
-  asm volatile("ld.global[.nc|.cg].{f64,s32} %0, [%1];" : "=d|r"(dst) : "l"(ptr));   ->  dst = *(ptr);
+  asm volatile("ld.global[.nc|.cg].{f64,s32,f32} %0, [%1];" : "=d|r|f"(dst) : "l"(ptr));   ->  dst = *(ptr);
   asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(ptr));  ->  two 32-bit loads
   #include "ebe_tma.cuh"   ->  #include "fem.cuh"   (the TMA/mbarrier variant is compiled out: SIC_EBE_IMPL == 3)
   static T* g_xxx ...      ->  static thread_local T* g_xxx   (host-side singletons: one per emulated rank = host thread)
@@ -86,7 +86,7 @@ def translate_launches(s):
         pos = a1
 
 
-_LD1 = re.compile(r'asm volatile\("ld\.global(?:\.nc|\.cg)?\.(?:f64|s32) %0, \[%1\];"\s*:\s*"=[dr]"\((\w+)\)\s*:\s*"l"\((.+?)\)\);',
+_LD1 = re.compile(r'asm volatile\("ld\.global(?:\.nc|\.cg)?\.(?:f64|s32|f32) %0, \[%1\];"\s*:\s*"=[drf]"\((\w+)\)\s*:\s*"l"\((.+?)\)\);',
                   re.S)
 _LD2 = re.compile(r'asm volatile\("ld\.global\.nc\.v2\.u32 \{%0, %1\}, \[%2\];"\s*:\s*"=r"\((\w+)\),\s*"=r"\((\w+)\)\s*:\s*'
                   r'"l"\((.+?)\)\);', re.S)

@@ -40,7 +40,7 @@ def random_tangent(n, seed, nonsym=0.0):
     return CT
 
 
-def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True, mg_kwargs=None):
+def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True, mg_kwargs=None, cycle_tol=None):
     """sic_mg_setup (Galerkin C_T, masks, blocks, lambda_max), one V-cycle and the full solve against the
     assembled-matrix oracle and the sparse direct solve."""
     from safeincave_b200 import cases
@@ -54,7 +54,12 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=
     eng.put6(eng.eps_rhs, eps_rhs)
     eq.bc.update_dirichlet(0.0)
     eq.bc.update_neumann(0.0)
-    mg = Multigrid(eng, h, **(mg_kwargs or {}))
+    # compressed=False: the preconditioner applies the exact FP64 operator, so the cycle can be compared vector for vector
+    # at round-off level; with the float copy of sym(C_T) (the default of the product) the cycle agrees to ~1e-6
+    mg_kwargs = {"compressed": False, **(mg_kwargs or {})}
+    cycle_tol = cycle_tol if cycle_tol is not None else (1e-5 if mg_kwargs["compressed"] else 1e-10)
+    eq.mg_options = dict(mg_kwargs)
+    mg = Multigrid(eng, h, **mg_kwargs)
     mg.setup(eq.fixed, eq.dinv)
     fixed = eq.fixed.cpu().numpy().astype(bool)
     om = OracleMG(h.meshes, h.transfers, CT, fixed)
@@ -88,7 +93,7 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=
     r = rng.standard_normal(3 * M) * (~fixed)
     z = mg.vcycle(torch.as_tensor(r).to(eng.device)).cpu().numpy()
     z_ref = om.vcycle(h.n_levels - 1, r)
-    assert relerr(z, z_ref) < 1e-10
+    assert relerr(z, z_ref) < cycle_tol
     # a second cycle on the same data gives the same answer (no state leaks between cycles)
     z2 = mg.vcycle(torch.as_tensor(r).to(eng.device)).cpu().numpy()
     assert relerr(z2, z) < 1e-14

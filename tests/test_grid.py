@@ -66,3 +66,21 @@ def test_mesh_views(grid):
     assert grid.mesh.comm.rank == 0 and grid.mesh.comm.size == 1
     assert (grid.Lx, grid.Ly, grid.Lz) == pytest.approx((1.0, 1.0, 1.0))
     assert grid.volumes.sum() == pytest.approx(grid.Lx * grid.Ly * grid.Lz)
+
+
+def test_refine_builds_a_multigrid_hierarchy_on_a_loaded_mesh():
+    """GridHandlerGMSH.refine: the loaded gmsh mesh becomes the coarsest level of a nested hierarchy (PC mg for any .msh);
+    tags are inherited, volumes add up, the children of a cell are listed together."""
+    import os
+    import numpy as np
+    import safeincave_b200 as sf
+    from safeincave_b200.mesh import TetMesh
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g0 = sf.GridHandlerGMSH.from_mesh(TetMesh.load_npz(os.path.join(gold, "mesh_cube_coarse.npz")))
+    g1 = g0.refine(1)
+    assert g1.hierarchy is not None and g1.hierarchy.n_levels == 2 and g1.n_elems == 8 * g0.n_elems
+    assert g1.get_boundary_names() == g0.get_boundary_names() and g1.get_subdomain_names() == g0.get_subdomain_names()
+    assert np.isclose(np.asarray(g1.volumes).sum(), np.asarray(g0.volumes).sum(), rtol=1e-12)
+    ch = g1.hierarchy.transfers[1].children           # (8, n_coarse): child j of coarse cell c is fine cell 8 c + j
+    assert (ch == 8 * np.arange(g0.n_elems)[None, :] + np.arange(8)[:, None]).all()
+    assert (g1.tetmesh.cell_tags.reshape(-1, 8) == g1.hierarchy.meshes[0].cell_tags[:, None]).all()
