@@ -255,8 +255,8 @@ typedef struct {
   int32_t check_every;    /* host looks at the residual every this many iterations */
   int32_t use_graph;      /* sic_mg_solve: replay every Krylov iteration (operator, scalar recurrences, the whole V-cycle,
                              exchanges) from ONE captured CUDA graph instead of ~110-170 kernel launches; re-captured
-                             whenever a set-up changed the baked-in Chebyshev coefficients.  sic_ksp_solve: the same for
-                             one CG / BiCGStab iteration */
+                             whenever a set-up changed the baked-in Chebyshev coefficients.  Ignored by sic_ksp_solve and
+                             sic_heat_step (3-5 launches per iteration, dominated by one large operator kernel) */
   int32_t guess_nonzero;  /* x holds an initial guess on the free dofs; rtol is then relative to the residual of the
                              ZERO guess (PETSc's default ||r|| < rtol ||b||), so a warm start saves iterations */
   /* results */

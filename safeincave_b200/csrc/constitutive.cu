@@ -85,7 +85,7 @@ __device__ __forceinline__ void desai_linearise(const double sig_k[6], const dou
     double rp[6];
     rate_desai(s, alpha, alpha_0, dp, rp, fv);
     double r_p = desai_residue(rp, alpha, qsi_old, alpha_0, dt, dp, qsi);
-    double Pk = (r_p - L.r) / SIC_DESAI_EPS_STRESS;
+    double Pk = SIC_DIV_CONST(r_p - L.r, SIC_DESAI_EPS_STRESS);
 #pragma unroll
     for (int c = 0; c < 6; ++c) L.P[c] = (c == k) ? Pk : L.P[c];
 #pragma unroll
@@ -135,7 +135,7 @@ __device__ __forceinline__ void md_linearise(const double sig_k[6], double T, do
 #pragma unroll
     for (int c = 0; c < 6; ++c) s[c] = (c == k) ? s[c] + SIC_MD_EPS_STRESS : s[c];
     const double r_sig = md_residue(s, T, zeta, zeta_old, dt, mp);
-    const double Pk = (r_sig - L.r) / SIC_MD_EPS_STRESS;
+    const double Pk = SIC_DIV_CONST(r_sig - L.r, SIC_MD_EPS_STRESS);
 #pragma unroll
     for (int c = 0; c < 6; ++c) L.P[c] = (c == k) ? Pk : L.P[c];
 #pragma unroll
@@ -675,8 +675,8 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_desai_init(sic_problem_t P
   double sig[6];
   load6(P.sig, ns, i, sig);
   const double c13 = 1.0 / 3.0;
-  double sxx = (-sig[0]) / SIC_MPA, syy = (-sig[1]) / SIC_MPA, szz = (-sig[2]) / SIC_MPA;
-  double sxy = (-sig[3]) / SIC_MPA, sxz = (-sig[4]) / SIC_MPA, syz = (-sig[5]) / SIC_MPA;
+  double sxx = SIC_DIV_CONST(-sig[0], SIC_MPA), syy = SIC_DIV_CONST(-sig[1], SIC_MPA), szz = SIC_DIV_CONST(-sig[2], SIC_MPA);
+  double sxy = SIC_DIV_CONST(-sig[3], SIC_MPA), sxz = SIC_DIV_CONST(-sig[4], SIC_MPA), syz = SIC_DIV_CONST(-sig[5], SIC_MPA);
   double I1 = (sxx + syy) + szz;
   double I2 = ((((sxx * syy + syy * szz) + sxx * szz) - sxy * sxy) - syz * syz) - sxz * sxz;
   double I3 = (((((sxx * syy) * szz + ((2.0 * sxy) * syz) * sxz) - szz * (sxy * sxy)) - sxx * (syz * syz)) -

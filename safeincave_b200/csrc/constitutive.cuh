@@ -15,6 +15,17 @@
 #define SIC_MPA 1.0e6                     /* Utils.py:35 */
 #define SIC_SQRT27 5.196152422706632      /* np.sqrt(27) == 27**0.5 */
 #define SIC_FD_EPS 1.0e-2                 /* MaterialProps.py:661 */
+
+// a / C for a compile-time constant C, CORRECTLY ROUNDED without the ~15-instruction division sequence: with y = RN(1/C)
+// (folded by the compiler), q = RN(a y) is a faithful quotient, r = a - C q is exact in one fma, and RN(q + r y) = RN(a / C)
+// (Markstein's theorem; holds for every C whose significand is not all ones and every finite a with a normal quotient).
+// Bit-identical to the oracle's true divisions; k_tangent spends 48 of these per cell and creep element.
+#define SIC_DIV_CONST(a, C) sic_div_const((a), (C), 1.0 / (C))
+__host__ __device__ __forceinline__ double sic_div_const(double a, double c, double rc) {
+  const double q = a * rc;
+  const double r = fma(-c, q, a);
+  return fma(r, rc, q);
+}
 #define SIC_DESAI_EPS_STRESS 1.0e-1       /* MaterialProps.py:1460 */
 
 namespace sic {
@@ -44,7 +55,7 @@ __device__ __forceinline__ void ddot_iso(double c11, double c12, double c44, con
 // ---- DislocationCreep.compute_eps_ne_rate, MaterialProps.py:921-961 ------------------------
 struct DislocationP { double A, Q, n; };
 __device__ __forceinline__ void rate_dislocation(const double s[6], double T, const DislocationP& p, double out[6]) {
-  double mean = ((s[0] + s[1]) + s[2]) / 3.0;
+  double mean = SIC_DIV_CONST((s[0] + s[1]) + s[2], 3.0);
   double a = s[0] - s[1], b = s[0] - s[2], c = s[1] - s[2];
   double q = sqrt(0.5 * (((a * a + b * b) + c * c) + 6.0 * ((s[3] * s[3] + s[4] * s[4]) + s[5] * s[5])));
   double A_bar = (p.A * sic_exp(((-p.Q) / SIC_R_GAS) / T)) * sic_pow(q, p.n - 1.0);
@@ -59,7 +70,7 @@ __device__ __forceinline__ void rate_dislocation(const double s[6], double T, co
 // ---- PressureSolutionCreep.compute_eps_ne_rate, MaterialProps.py:995-1034 ------------------
 struct PressureSolP { double A, d, Q; };
 __device__ __forceinline__ void rate_pressure_solution(const double s[6], double T, const PressureSolP& p, double out[6]) {
-  double mean = ((s[0] + s[1]) + s[2]) / 3.0;
+  double mean = SIC_DIV_CONST((s[0] + s[1]) + s[2], 3.0);
   double A_bar = ((p.A / ((p.d * p.d) * p.d)) / T) * sic_exp(((-p.Q) / SIC_R_GAS) / T);
   out[0] = A_bar * (s[0] - mean);
   out[1] = A_bar * (s[1] - mean);
@@ -102,8 +113,8 @@ struct DesaiP { double mu_1, N_1, a_1, eta, n, beta_1, beta, m, gamma, sigma_t; 
 __device__ __forceinline__ void rate_desai(const double sig[6], double alpha, double alpha_0, const DesaiP& p,
                                            double rate[6], double& Fvp_out) {
   const double c13 = 1.0 / 3.0;
-  double sxx = (-sig[0]) / SIC_MPA, syy = (-sig[1]) / SIC_MPA, szz = (-sig[2]) / SIC_MPA;
-  double sxy = (-sig[3]) / SIC_MPA, sxz = (-sig[4]) / SIC_MPA, syz = (-sig[5]) / SIC_MPA;
+  double sxx = SIC_DIV_CONST(-sig[0], SIC_MPA), syy = SIC_DIV_CONST(-sig[1], SIC_MPA), szz = SIC_DIV_CONST(-sig[2], SIC_MPA);
+  double sxy = SIC_DIV_CONST(-sig[3], SIC_MPA), sxz = SIC_DIV_CONST(-sig[4], SIC_MPA), syz = SIC_DIV_CONST(-sig[5], SIC_MPA);
   double I1 = (sxx + syy) + szz;
   double I2 = ((((sxx * syy + syy * szz) + sxx * szz) - sxy * sxy) - syz * syz) - sxz * sxz;
   double I3 = (((((sxx * syy) * szz + ((2.0 * sxy) * syz) * sxz) - szz * (sxy * sxy)) - sxx * (syz * syz)) -
@@ -189,7 +200,7 @@ __device__ __forceinline__ double clamp_min(double x, double lo) { return (x < l
 // transient limit eps_t*, transient function F
 __device__ __forceinline__ void md_fields(const double s[6], double T, double zeta, const MunsonDawsonP& p,
                                           double dev[6], double& sigma_safe, double& epsdot_ss, double& ets, double& F) {
-  const double mean = ((s[0] + s[1]) + s[2]) / 3.0;
+  const double mean = SIC_DIV_CONST((s[0] + s[1]) + s[2], 3.0);
   dev[0] = s[0] - mean; dev[1] = s[1] - mean; dev[2] = s[2] - mean;
   dev[3] = s[3]; dev[4] = s[4]; dev[5] = s[5];
   const double a = s[0] - s[1], b = s[0] - s[2], c = s[1] - s[2];
@@ -254,12 +265,12 @@ __device__ __forceinline__ void rate_mohr_coulomb(const double sig[6], const Moh
                                                   double& Fvp_out) {
   double c[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) c[k] = (-sig[k]) / SIC_MPA;
+  for (int k = 0; k < 6; ++k) c[k] = SIC_DIV_CONST(-sig[k], SIC_MPA);
   const double I1 = (c[0] + c[1]) + c[2];
   const double I2 = ((((c[0] * c[1] + c[1] * c[2]) + c[0] * c[2]) - c[3] * c[3]) - c[5] * c[5]) - c[4] * c[4];
   const double J2 = clamp_min((1.0 / 3.0) * (I1 * I1) - I2, 1.0e-20);
   const double F_shear = (sqrt(J2) - p.alpha_F * I1) - p.k_F;
-  const double F_tension = (-I1) / 3.0 - p.sigma_t;
+  const double F_tension = SIC_DIV_CONST(-I1, 3.0) - p.sigma_t;
   const double Fvp = (F_shear > F_tension || F_shear != F_shear) ? F_shear : F_tension;   // torch.maximum: NaN wins
   Fvp_out = (F_tension != F_tension) ? F_tension : Fvp;
   double lam = 0.0;
@@ -306,17 +317,17 @@ __device__ __forceinline__ void rate_matsuoka_nakai(const double sig[6], const M
                                                     double& Fvp_out) {
   double c[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) c[k] = (-sig[k]) / SIC_MPA;
+  for (int k = 0; k < 6; ++k) c[k] = SIC_DIV_CONST(-sig[k], SIC_MPA);
   double sig3, sig2, sig1;
   eigvals_sym3(c, sig3, sig2, sig1);
   const double s1 = sig1 + p.shift, s2 = sig2 + p.shift, s3 = sig3 + p.shift;
   const double d12 = clamp_min(s1 + s2, 1.0e-20), d23 = clamp_min(s2 + s3, 1.0e-20), d31 = clamp_min(s3 + s1, 1.0e-20);
   const double q12 = (s1 - s2) / d12, q23 = (s2 - s3) / d23, q31 = (s3 - s1) / d31;
   const double f_nfc = sqrt(((q12 * q12 + q23 * q23) + q31 * q31) + 1.0e-30) - p.k_nfc;
-  const double p_mean = clamp_min(((s1 + s2) + s3) / 3.0, 1.0e-20);
+  const double p_mean = clamp_min(SIC_DIV_CONST((s1 + s2) + s3, 3.0), 1.0e-20);
   const double F_shear = f_nfc * p_mean;
   const double I1 = (c[0] + c[1]) + c[2];
-  const double F_tension = (-I1) / 3.0 - p.sigma_t;
+  const double F_tension = SIC_DIV_CONST(-I1, 3.0) - p.sigma_t;
   const double Fvp = (F_shear > F_tension || F_shear != F_shear) ? F_shear : F_tension;
   Fvp_out = (F_tension != F_tension) ? F_tension : Fvp;
   double lam = 0.0;
@@ -347,7 +358,7 @@ __device__ __forceinline__ void fd_columns(RateFn rate_fn, const double sig[6], 
     for (int c = 0; c < 6; ++c) s[c] = (c == k) ? s[c] + SIC_FD_EPS : s[c];
     const double phi = (k < 3) ? 1.0 : 2.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) col[i] = (phi * (ra[i] - rb[i])) / (2.0 * SIC_FD_EPS);
+    for (int i = 0; i < 6; ++i) col[i] = SIC_DIV_CONST(phi * (ra[i] - rb[i]), 2.0 * SIC_FD_EPS);
     consume(k, col);
   }
 }

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--elements", default="dislocation")
     ap.add_argument("--theta", type=float, default=0.0)
     ap.add_argument("--what", default="step", choices=["step", "constitutive"])
+    ap.add_argument("--compressed", type=int, default=1)
     ap.add_argument("--staged", action="store_true", help="BASELINE config 3 through the two-stage workflow "
                     "(cases.staged_cavern_cases; block-Jacobi BiCGStab); implies --what constitutive")
     a = ap.parse_args()
@@ -46,6 +47,7 @@ def main():
         case["desai_initial_hardening"] = False
         eq, sim = cases.build(case, grid, device=dev)
         eq.solver.getPC().setType("mg")
+        eq.mg_options = dict(eq.mg_options, compressed=bool(a.compressed))
         eq.solver.setGuessExtrapolation(True)
     sim.verbose = False
     sim.initialize()
