@@ -554,6 +554,8 @@ def run_b200(args):
         r_cycle = roof("k_mg_ebe_pc (finest level, inside the V-cycle)" if pc_on else "k_mg_ebe (finest level, inside the V-cycle)",
                        op_ms, eng.op_samples, op_launches, 152 if pc_on else 408)
         r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, eng.op_dot_samples, eng.op_dot_launches, 408)
+        note(f"OPERATOR finest level: V-cycle kernel {op_ms:.3f} ms/launch x {op_launches}, Krylov kernel {dot_ms:.3f} ms/launch "
+             f"x {eng.op_dot_launches}; Krylov iterations {ksp_its}")
         both = [r for r in (r_cycle, r_dot) if r]
         both.sort(key=lambda r: -r["share_of_step_time"])
         roofline, roofline_other = (both + [None, None])[:2]

@@ -47,6 +47,32 @@ __device__ __forceinline__ MatsuokaNakaiP load_mn(const Row& row, int off) {
   return MatsuokaNakaiP{row[off], row[off + 1], row[off + 2], row[off + 3], row[off + 4], row[off + 5]};
 }
 
+// Build variants of k_tangent (scripts/build_variants.py times them against each other on the GPU):
+//   SIC_TAN_SMEM_G    1: the accumulated 6x6 G lives in shared memory while the elements' finite-difference columns are
+//                        formed (dynamic column index for free, 72 registers fewer during the rate evaluations); it is
+//                        pulled into registers only for the inverse.  0: in registers, columns added by predication.
+//   SIC_TAN_UNROLL    1: the six FD columns of DislocationCreep / PressureSolutionCreep as six inlined copies (SET 0).
+//   SIC_TAN_MINBLOCKS resident CTAs per SM the SET-0 instantiation is compiled for (register cap 65536 / 128 / that).
+#ifndef SIC_TAN_SMEM_G
+#define SIC_TAN_SMEM_G 1
+#endif
+#ifndef SIC_TAN_UNROLL
+#define SIC_TAN_UNROLL 0
+#endif
+#ifndef SIC_TAN_MINBLOCKS
+#define SIC_TAN_MINBLOCKS 4
+#endif
+
+// the 6x6 in shared memory, one column of the array per thread: entry j of this thread at base[j * SIC_CELL_THREADS]
+struct SmemMat {
+  double* base;
+  __device__ __forceinline__ double& operator[](int j) const { return base[j * SIC_CELL_THREADS]; }
+};
+__device__ __forceinline__ void add_col(const SmemMat& G, int k, const double col[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) G[i * 6 + k] = G[i * 6 + k] + col[i];
+}
+
 // accumulate column k of a 6x6 held in registers without dynamic indexing
 __device__ __forceinline__ void add_col(double G[36], int k, const double col[6]) {
 #pragma unroll
@@ -153,10 +179,12 @@ __device__ __forceinline__ void md_linearise(const double sig_k[6], double T, do
 // SET (sic_element_set): 0 = Kelvin / DislocationCreep / PressureSolutionCreep, 1 = + ViscoplasticDesai (together the
 // elements of BASELINE configs 1-4), 2 = + the SURVEY 8f elements; the host picks the instantiation from the material.
 // =============================================================================================
-// SET 0: 168 registers (3 resident CTAs per SM) at the price of 72 bytes of spills; the larger sets need all 255.
 template <int SET>
-__global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(sic_problem_t P, double dt, double theta) {
+__global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? SIC_TAN_MINBLOCKS : 1) k_tangent(sic_problem_t P, double dt, double theta) {
   constexpr bool DESAI = SET >= 1, EXT = SET >= 2;   // element set of the instantiation (see sic_element_set)
+#if SIC_TAN_SMEM_G
+  __shared__ double g_sm[36 * SIC_CELL_THREADS];       // 36 KB: no barrier anywhere, every thread owns its column
+#endif
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
   const int ns = P.cell_stride;
@@ -168,7 +196,11 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(
   double sk[6];
   load6(P.sig_k, ns, i, sk);
 
+#if SIC_TAN_SMEM_G
+  const SmemMat G{g_sm + threadIdx.x};
+#else
   double G[36];
+#endif
 #pragma unroll
   for (int j = 0; j < 36; ++j) G[j] = 0.0;
   double B[6] = {0, 0, 0, 0, 0, 0};
@@ -198,12 +230,12 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(
       G[21] += g44; G[28] += g44; G[35] += g44;
     } else if (el.kind == SIC_ELEM_DISLOCATION) {
       DislocationP dp{row[off], row[off + 1], row[off + 2]};
-      fd_columns([&](const double* s, double* r) { rate_dislocation(s, T, dp, r); }, sk,
-                 [&](int k, const double* col) { add_col(G, k, col); });
+      fd_columns<SET == 0 && SIC_TAN_UNROLL>([&](const double* s, double* r) { rate_dislocation(s, T, dp, r); }, sk,
+                           [&](int k, const double* col) { add_col(G, k, col); });
     } else if (el.kind == SIC_ELEM_PRESSURE_SOL) {
       PressureSolP pp{row[off], row[off + 1], row[off + 2]};
-      fd_columns([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk,
-                 [&](int k, const double* col) { add_col(G, k, col); });
+      fd_columns<SET == 0 && SIC_TAN_UNROLL>([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk,
+                           [&](int k, const double* col) { add_col(G, k, col); });
     } else if (DESAI && el.kind == SIC_ELEM_DESAI) {
       DesaiP dp = load_desai(row, off);
       double* ds = el.desai;
@@ -284,8 +316,11 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(
   }
 
   // eps_rhs = eps_ne_k + eps_th - phi2 (B + G:sigma_k)   (MomentumEquation.py:889)
+  double A[36];                 // G in registers from here on (the inverse indexes it statically)
+#pragma unroll
+  for (int j = 0; j < 36; ++j) A[j] = G[j];
   double Gs[6], er[6];
-  ddot66(G, sk, Gs);
+  ddot66(A, sk, Gs);
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     double th = (c < 3) ? eps_th : 0.0;
@@ -303,10 +338,10 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(
       double ci = 0.0;
       if (r == c) ci = (r < 3) ? ci11 : ci44;
       else if (r < 3 && c < 3) ci = ci12;
-      G[r * 6 + c] = ci + phi2 * G[r * 6 + c];
+      A[r * 6 + c] = ci + phi2 * A[r * 6 + c];
     }
   }
-  bool ok = inverse6(G);
+  bool ok = inverse6(A);
   if (!ok) {  // singular -> elastic tangent for this cell (MaterialProps.py:296-309)
     const double c11 = row[so], c12 = row[so + 1], c44 = row[so + 2];
 #pragma unroll
@@ -316,13 +351,13 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS, SET == 0 ? 3 : 1) k_tangent(
         double v = 0.0;
         if (r == c) v = (r < 3) ? c11 : c44;
         else if (r < 3 && c < 3) v = c12;
-        G[r * 6 + c] = v;
+        A[r * 6 + c] = v;
       }
     }
     if (P.n_singular) atomicAdd(P.n_singular, 1);
   }
 #pragma unroll
-  for (int j = 0; j < 36; ++j) P.CT[SIC_CT_INDEX(j, i)] = G[j];
+  for (int j = 0; j < 36; ++j) P.CT[SIC_CT_INDEX(j, i)] = A[j];
 }
 
 // CT <- C, eps_rhs <- 0 (operator of solve_elastic_response, MomentumEquation.py:892-923)
@@ -570,10 +605,10 @@ __global__ void __launch_bounds__(SIC_CELL_THREADS) k_commit(sic_problem_t P, do
       ddot_iso(g11, g12, g44, dsig, Gd);
     } else if (el.kind == SIC_ELEM_DISLOCATION) {
       DislocationP dp{row[off], row[off + 1], row[off + 2]};
-      fd_columns([&](const double* s, double* r) { rate_dislocation(s, T, dp, r); }, sk, acc);
+      fd_columns<SET == 0 && SIC_TAN_UNROLL>([&](const double* s, double* r) { rate_dislocation(s, T, dp, r); }, sk, acc);
     } else if (el.kind == SIC_ELEM_PRESSURE_SOL) {
       PressureSolP pp{row[off], row[off + 1], row[off + 2]};
-      fd_columns([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk, acc);
+      fd_columns<SET == 0 && SIC_TAN_UNROLL>([&](const double* s, double* r) { rate_pressure_solution(s, T, pp, r); }, sk, acc);
     } else if (DESAI && el.kind == SIC_ELEM_DESAI) {
       DesaiP dp = load_desai(row, off);
       double* ds = el.desai;

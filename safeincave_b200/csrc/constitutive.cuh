@@ -340,13 +340,12 @@ __device__ __forceinline__ void rate_matsuoka_nakai(const double sig[6], const M
 // shear columns doubled (T3).  consume(k, col) receives column k of E.  The k loop is kept
 // rolled (two inlined rate evaluations per trip); the perturbed component is selected by
 // predication so that s[] keeps static register indices.
-template <class RateFn, class ColFn>
+template <bool UNROLL = false, class RateFn, class ColFn>
 __device__ __forceinline__ void fd_columns(RateFn rate_fn, const double sig[6], ColFn consume) {
   double s[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) s[c] = sig[c];
-#pragma unroll 1
-  for (int k = 0; k < 6; ++k) {
+  auto column = [&](int k) {
     double ra[6], rb[6], col[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) s[c] = (c == k) ? s[c] + SIC_FD_EPS : s[c];
@@ -360,6 +359,15 @@ __device__ __forceinline__ void fd_columns(RateFn rate_fn, const double sig[6], 
 #pragma unroll
     for (int i = 0; i < 6; ++i) col[i] = SIC_DIV_CONST(phi * (ra[i] - rb[i]), 2.0 * SIC_FD_EPS);
     consume(k, col);
+  };
+  // UNROLL (cheap rate laws in the creep-only kernels): six inlined copies, k is a compile-time constant in each, so
+  // the selects that keep s[] and the consumer's 6x6 in registers under a runtime k (108 per column) disappear
+  if constexpr (UNROLL) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) column(k);
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) column(k);
   }
 }
 

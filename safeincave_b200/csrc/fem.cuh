@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/safeincave_cuda.h"
 #include "common.cuh"
 
@@ -177,7 +179,8 @@ struct TileScratch {                      // shared memory of one operator CTA (
   int eoff[4 * SIC_TILE_CELLS + 1];       // per unique node: offset into ent
 };
 
-// Compressed operator of the multigrid PRECONDITIONER (PC = true): the symmetric part of C_T as 21 floats per cell
+// Compressed operator of the multigrid PRECONDITIONER (PC = true): S = sym(W C_T), W = diag(1,1,1,2,2,2) (the form in
+// which the tangent of tensorial strains is symmetric, see k_mg_ct_compress), as 21 floats per cell
 // (tiled like C_T: [tile][21][128]) and the gradients + volume as 13 floats ([13][cell_stride]): 152 B per cell
 // instead of 408.  The arithmetic stays FP64 (the vectors are).  A preconditioner only has to approximate K: the
 // non-symmetry of the finite-difference tangent is round-off (1e-6 relative) and float storage perturbs the entries by
@@ -208,28 +211,20 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
   unsigned ent_lo, ent_hi;   // this thread's 4 of the tile's 512 scatter references (8 bytes)
   asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(ent_lo), "=r"(ent_hi)
                : "l"(P.ent + (size_t)tile * 4 * SIC_TILE_CELLS + 4 * tid));
+  // PC: the float operands stay floats in registers and are widened where they enter the FP64 arithmetic
+  using store_t = typename std::conditional<PC, float, double>::type;
   int node[4];
-  double g[12], CT[PC ? SIC_PC_CT_ROWS : 36], er[6], ua[12], vol;
+  store_t g[12], CT[PC ? SIC_PC_CT_ROWS : 36], vol;
+  double er[6], ua[12];
 #pragma unroll
   for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
   if constexpr (PC) {
-    float gf[SIC_PC_GEOM_ROWS], cf[SIC_PC_CT_ROWS];
 #pragma unroll
-    for (int k = 0; k < SIC_PC_GEOM_ROWS; ++k) gf[k] = ldg_f32(pc_geom + k * ns + i);
+    for (int k = 0; k < 12; ++k) g[k] = ldg_f32(pc_geom + k * ns + i);
+    vol = ldg_f32(pc_geom + 12 * ns + i);
     const float* ct = pc_ct + SIC_PC_CT_INDEX(0, i);
 #pragma unroll
-    for (int k = 0; k < SIC_PC_CT_ROWS; ++k) cf[k] = ldg_f32(ct + k * SIC_TILE_CELLS);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
-    }
-#pragma unroll
-    for (int k = 0; k < 12; ++k) g[k] = (double)gf[k];
-    vol = (double)gf[12];
-#pragma unroll
-    for (int k = 0; k < SIC_PC_CT_ROWS; ++k) CT[k] = (double)cf[k];
+    for (int k = 0; k < SIC_PC_CT_ROWS; ++k) CT[k] = ldg_f32(ct + k * SIC_TILE_CELLS);
   } else {
 #pragma unroll
     for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
@@ -241,12 +236,12 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
 #pragma unroll
       for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
     }
+  }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+  for (int a = 0; a < 4; ++a) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
-    }
+    for (int j = 0; j < 3; ++j)
+      ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
   }
   // scatter plan of the tile -> shared memory (depends only on q0, requested first)
   const int nq = q1 - q0, ebase = tile * 4 * SIC_TILE_CELLS;
@@ -279,7 +274,7 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) acc += CT[PC ? sic_sym_index(r, k) : r * 6 + k] * eps[k];
-    s[r] = acc;
+    s[r] = (PC && r >= 3) ? 0.5 * acc : acc;       // PC: CT holds S = sym(W C_T), sigma = W^-1 S eps
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {

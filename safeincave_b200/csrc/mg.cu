@@ -98,14 +98,21 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, c
 }
 
 // the compressed operator of the preconditioner (fem.cuh, PC = true): symmetric float C_T, float geometry
-__global__ void __launch_bounds__(SIC_TILE_CELLS, 4) k_mg_ebe_pc(sic_problem_t P, const float* __restrict__ pc_ct,
+#ifndef SIC_PC_MINBLOCKS
+#define SIC_PC_MINBLOCKS 6      /* resident CTAs per SM it is compiled for (latency-bound at 4: ncu, profiles/) */
+#endif
+__global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc(sic_problem_t P, const float* __restrict__ pc_ct,
                                                                const float* __restrict__ pc_geom, const double* __restrict__ x,
                                                                double* __restrict__ y, const int* done) {
   __shared__ TileScratch sc;
   ebe_tile_scatter<0, false, true>(P, x, y, sc, done, pc_ct, pc_geom);
 }
 
-// pc_ct = float(sym(C_T)) of one level (once per set-up; both tiled by 128 cells)
+// pc_ct = float(sym(W C_T)), W = diag(1,1,1,2,2,2), of one level (once per set-up; both tiled by 128 cells).
+// C_T maps TENSORIAL strains to stresses, so the cell energy is eps^T W C_T eps and the operator K = B^T W C_T B is
+// symmetric iff W C_T is (C_T itself is not: for the creep tangents C_T[normal][shear] = 2 C_T[shear][normal], the
+// reference's doubled shear columns).  The compressed operator applies sigma = W^-1 S eps with S = sym(W C_T):
+// exactly K when the tangent has major symmetry, its symmetric part otherwise.
 __global__ void __launch_bounds__(128) k_mg_ct_compress(int n_cells, const double* __restrict__ CT, float* __restrict__ pc_ct) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cells) return;
@@ -113,8 +120,9 @@ __global__ void __launch_bounds__(128) k_mg_ct_compress(int n_cells, const doubl
   for (int r = 0; r < 6; ++r) {
 #pragma unroll
     for (int k = r; k < 6; ++k) {
-      const double v = (r == k) ? __ldg(CT + SIC_CT_INDEX(r * 6 + k, i))
-                                : 0.5 * (__ldg(CT + SIC_CT_INDEX(r * 6 + k, i)) + __ldg(CT + SIC_CT_INDEX(k * 6 + r, i)));
+      const double wr = (r < 3) ? 1.0 : 2.0, wk = (k < 3) ? 1.0 : 2.0;
+      const double v = (r == k) ? wr * __ldg(CT + SIC_CT_INDEX(r * 6 + k, i))
+                                : 0.5 * (wr * __ldg(CT + SIC_CT_INDEX(r * 6 + k, i)) + wk * __ldg(CT + SIC_CT_INDEX(k * 6 + r, i)));
       pc_ct[SIC_PC_CT_INDEX(sic_sym_index(r, k), i)] = (float)v;
     }
   }

@@ -32,15 +32,25 @@ def make(sf, name, levels, case_fn, **kw):
     return h, grid, case, eq, sim
 
 
-def random_tangent(n, seed, nonsym=0.0):
+def random_tangent(n, seed, nonsym=0.0, coupled=0.0):
+    """coupled: relative size of random normal-shear (and all other) couplings with the MAJOR SYMMETRY of a tangent of
+    tensorial strains: W C_T symmetric, W = diag(1,1,1,2,2,2) -- so C_T[normal][shear] = 2 C_T[shear][normal], the structure
+    of the creep tangents (doubled shear columns of G)."""
     rng = np.random.default_rng(seed)
     CT = oc.iso_matrix(102e9 * (1 + 0.5 * rng.random(n)), 0.3 * np.ones(n))
+    if coupled:
+        W = np.array([1.0, 1.0, 1.0, 2.0, 2.0, 2.0])
+        S = W[None, :, None] * CT
+        E = rng.standard_normal((n, 6, 6))
+        S = S + coupled * S[:, :1, :1] * 0.5 * (E + E.transpose(0, 2, 1))
+        CT = S / W[None, :, None]
     if nonsym:
         CT = CT * (1.0 + nonsym * rng.standard_normal((n, 6, 6)))
     return CT
 
 
-def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True, mg_kwargs=None, cycle_tol=None):
+def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=True, mg_kwargs=None, cycle_tol=None,
+                             coupled=0.0):
     """sic_mg_setup (Galerkin C_T, masks, blocks, lambda_max), one V-cycle and the full solve against the
     assembled-matrix oracle and the sparse direct solve."""
     from safeincave_b200 import cases
@@ -48,7 +58,7 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=
     h, grid, case, eq, sim = make(sf, name, levels, cases.triaxial_case if name == "cube_coarse" else cases.cavern_case)
     eng = eq.engine
     N, M = eng.N, eng.M
-    CT = random_tangent(N, 7, nonsym)
+    CT = random_tangent(N, 7, nonsym, coupled)
     eng.put_CT(CT)
     eps_rhs = 1e-5 * np.random.default_rng(3).standard_normal((N, 6))
     eng.put6(eng.eps_rhs, eps_rhs)
@@ -77,7 +87,7 @@ def check_setup_vcycle_solve(sf, name="cube_coarse", levels=2, nonsym=0.0, full=
         assert 0.88 * lam_ref < lam_dev[l] / mg.opts.safety <= 1.03 * lam_ref, (l, lam_dev[l], lam_ref)
         assert lam_dev[l] >= lam_ref, (l, lam_dev[l], lam_ref)
     if full:   # a second setup after the tangent changed restarts the power iteration from the kept vector (4 passes)
-        CT2 = random_tangent(N, 11, nonsym) * (1.0 + 2.0 * (np.arange(N) % 3 == 0))[:, None, None]
+        CT2 = random_tangent(N, 11, nonsym, coupled) * (1.0 + 2.0 * (np.arange(N) % 3 == 0))[:, None, None]
         eng.put_CT(CT2)
         mg.setup(eq.fixed, eq.dinv)
         om2 = OracleMG(h.meshes, h.transfers, CT2, fixed)
