@@ -463,7 +463,8 @@ def run_b200(args):
     ksp_its = sum(r["ksp_iterations"] for r in recs)
     value = N * iters / (ms * 1e-3)
     op_ms = eng.op_ms / max(eng.op_samples, 1)
-    op_launches = eng.op_launches
+    op_launches, op_samples = eng.op_launches, eng.op_samples
+    dot_ms, dot_launches, dot_samples = eng.op_dot_ms / max(eng.op_dot_samples, 1), eng.op_dot_launches, eng.op_dot_samples
     eng.time_operator = False
     prof = eng.profile_summary()
     eng.profile = False
@@ -550,17 +551,16 @@ def run_b200(args):
                 "launches_in_timed_region": n_launches, "share_of_step_time": ms_launch * n_launches / ms if ms > 0 else None}
     if pc == "mg":
         pc_on = bool(eq.mg is not None and eq.mg.compressed)
-        dot_ms = eng.op_dot_ms / max(eng.op_dot_samples, 1)
         r_cycle = roof("k_mg_ebe_pc (finest level, inside the V-cycle)" if pc_on else "k_mg_ebe (finest level, inside the V-cycle)",
-                       op_ms, eng.op_samples, op_launches, 152 if pc_on else 408)
-        r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, eng.op_dot_samples, eng.op_dot_launches, 408)
+                       op_ms, op_samples, op_launches, 152 if pc_on else 408)
+        r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, dot_samples, dot_launches, 408)
         note(f"OPERATOR finest level: V-cycle kernel {op_ms:.3f} ms/launch x {op_launches}, Krylov kernel {dot_ms:.3f} ms/launch "
-             f"x {eng.op_dot_launches}; Krylov iterations {ksp_its}")
+             f"x {dot_launches}; Krylov iterations {ksp_its}")
         both = [r for r in (r_cycle, r_dot) if r]
         both.sort(key=lambda r: -r["share_of_step_time"])
         roofline, roofline_other = (both + [None, None])[:2]
     else:
-        roofline = roof("k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain", op_ms, eng.op_samples, op_launches, 408)
+        roofline = roof("k_ebe_dot" if args.ksp == "cg" else "k_ebe_plain", op_ms, op_samples, op_launches, 408)
         roofline_other = None
 
     line = {
