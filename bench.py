@@ -437,6 +437,7 @@ def run_b200(args):
     eng.profile_summary()
     eng.op_ms, eng.op_samples, eng.op_launches = 0.0, 0, 0
     eng.op_dot_ms, eng.op_dot_samples, eng.op_dot_launches = 0.0, 0, 0
+    eng.xchg_ms, eng.xchg_samples = 0.0, 0
     launches0, nodes0 = eng.launches, getattr(eng, "graph_kernel_nodes", 0)
     graphs0 = eq.mg.graph_launches if eq.mg is not None else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -465,6 +466,7 @@ def run_b200(args):
     op_ms = eng.op_ms / max(eng.op_samples, 1)
     op_launches, op_samples = eng.op_launches, eng.op_samples
     dot_ms, dot_launches, dot_samples = eng.op_dot_ms / max(eng.op_dot_samples, 1), eng.op_dot_launches, eng.op_dot_samples
+    xchg_ms, xchg_samples = eng.xchg_ms / max(eng.xchg_samples, 1), eng.xchg_samples
     eng.time_operator = False
     prof = eng.profile_summary()
     eng.profile = False
@@ -555,7 +557,7 @@ def run_b200(args):
                        op_ms, op_samples, op_launches, 152 if pc_on else 408)
         r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, dot_samples, dot_launches, 408)
         note(f"OPERATOR finest level: V-cycle kernel {op_ms:.3f} ms/launch x {op_launches}, Krylov kernel {dot_ms:.3f} ms/launch "
-             f"x {dot_launches}; Krylov iterations {ksp_its}")
+             f"x {dot_launches}; Krylov iterations {ksp_its}; halo exchange {xchg_ms * 1e3:.1f} us")
         both = [r for r in (r_cycle, r_dot) if r]
         both.sort(key=lambda r: -r["share_of_step_time"])
         roofline, roofline_other = (both + [None, None])[:2]
@@ -585,7 +587,11 @@ def run_b200(args):
         "launch_breakdown": {"graph_launches": graph_launches, "kernels_inside_graphs": graph_nodes,
                              "kernels_executed": launches - graph_launches + graph_nodes,
                              "host_launches_per_step": launches / args.steps},
-        "roofline": roofline, "roofline_other": roofline_other, "constitutive": constitutive,
+        "roofline": roofline, "roofline_other": roofline_other,
+        # several GPUs: one finest-level halo exchange (P2P kernel over NVLink), from the end of the operator kernel to the
+        # end of the exchange kernel -- includes waiting for the slowest neighbour; rank 0's average over its samples
+        "exchange": ({"avg_ms": xchg_ms, "samples": xchg_samples, "interface_nodes": int(part.n_interface),
+                      "neighbours": len(part.peers)} if world > 1 and xchg_samples else None), "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,
     }
     if e2e:

@@ -275,8 +275,11 @@ typedef struct {
   /* sic_mg_solve with time_operator: op_ms / op_samples time the finest-level operator INSIDE the V-cycle (the
    * compressed one when the levels carry pc_ct), op_dot_ms / op_dot_samples the exact Krylov operator (k_mg_ebe_dot) */
   int32_t op_dot_samples;
-  int32_t reserved;
+  int32_t xchg_samples;    /* several GPUs: xchg_ms / xchg_samples time one finest-level halo exchange (3 components) per
+                              solve, from the end of the operator kernel to the end of the exchange kernel, i.e. including
+                              the wait for the slowest neighbour */
   double op_dot_ms;
+  double xchg_ms;
 } sic_ksp_t;
 
 /* Workspace: sic_ksp_workspace_doubles(n_nodes, method) doubles, caller-allocated. */

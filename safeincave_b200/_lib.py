@@ -66,7 +66,7 @@ class SicKsp(ctypes.Structure):
                 ("rnorm", c_double), ("rnorm0", c_double),
                 ("time_operator", c_int32), ("op_samples", c_int32), ("op_ms", c_double),
                 ("graph_launches", c_int32), ("direct_iterations", c_int32),
-                ("op_dot_samples", c_int32), ("reserved", c_int32), ("op_dot_ms", c_double)]
+                ("op_dot_samples", c_int32), ("xchg_samples", c_int32), ("op_dot_ms", c_double), ("xchg_ms", c_double)]
 
 
 class SicMgLevel(ctypes.Structure):

@@ -142,12 +142,16 @@ extern "C" int sic_halo_sum(const sic_halo_t* h, double* vec, int ncomp, void* s
 namespace sic {
 
 #define SIC_P2P_MAX_RANKS 16
-#define SIC_P2P_BPP 4          /* blocks per peer */
+#define SIC_P2P_BPP_MIN 4      /* blocks per peer: at least this many, ... */
+#define SIC_P2P_BPP_MAX 32     /* ... at most this many, sized so that a thread moves <= 16 values (P2P.bpp) */
 #define SIC_P2P_THREADS 256
 #define SIC_P2P_NSCAL 8
 
 struct P2P {
   int rank, n_ranks, cap;                 // cap: interface nodes per peer the mailbox can hold
+  int bpp;                                // blocks per peer of every launch on this context (from cap: the interface of
+                                          // a 7 M-cell rank is ~50 k nodes per neighbour = 1.2 MB per exchange, which 4
+                                          // blocks moved 8 bytes at a time in ~150 dependent trips to HBM / NVLink)
   size_t slot_doubles;                    // doubles per (source rank, parity) slot: 9*cap data + NSCAL scalars + 1 flag
   double* local;                          // this rank's mailbox (cudaMalloc)
   double* remote[SIC_P2P_MAX_RANKS];      // peers' mailboxes mapped into this process (remote[rank] == local)
@@ -166,7 +170,8 @@ __device__ __forceinline__ double* p2p_slot(double* mailbox, size_t slot_doubles
   return mailbox + ((size_t)src * 2 + parity) * slot_doubles;
 }
 
-// grid = n_peers * BPP halo blocks (+ 1 scalar block when n_scal > 0).
+// grid = n_peers * bpp halo blocks (+ 1 scalar block when n_scal > 0); all of them must be resident at once (they wait
+// for each other and for the peers): <= 16 * 32 + 1 blocks of 256 threads, a B200 holds 148 * 8.
 //   halo block (p, c): chunk c of the nodal data exchanged with neighbour p (only ranks that share nodes);
 //   scalar block     : thread r sends this rank's n_scal partial sums to rank r (EVERY rank, neighbour or not),
 //                      waits for rank r's, then the sums are formed in rank order (identical on all ranks).
@@ -192,7 +197,8 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
   const unsigned long long epoch_s = ((volatile unsigned long long*)ctx.epochs)[1];
   const int parity = (int)(epoch & 1ull);
   const size_t scal_off = 9 * (size_t)ctx.cap;
-  const int n_halo_blocks = (ncomp > 0) ? H.n_peers * SIC_P2P_BPP : 0;
+  const int bpp = ctx.bpp;
+  const int n_halo_blocks = (ncomp > 0) ? H.n_peers * bpp : 0;
   __shared__ int ok;
   __shared__ double mine[SIC_P2P_NSCAL];
   if ((int)blockIdx.x >= n_halo_blocks) {
@@ -227,24 +233,34 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     return;
   }
   // ---------------- halo block ---------------------------------------------------------------------
-  const int p = blockIdx.x / SIC_P2P_BPP, chunk = blockIdx.x % SIC_P2P_BPP;
+  const int p = blockIdx.x / bpp, chunk = blockIdx.x % bpp;
   const int peer = H.peer[p];
   const int off = H.peer_off[p], cnt = H.peer_off[p + 1] - off;
   const int n = cnt * ncomp;
-  const int per = (n + SIC_P2P_BPP - 1) / SIC_P2P_BPP;
+  const int per = (n + bpp - 1) / bpp;
   const int lo = chunk * per, hi = min(n, lo + per);
   // send: my partial sums for the nodes shared with `peer` go straight into ITS mailbox
   double* out = p2p_slot(ctx.remote[peer], ctx.slot_doubles, ctx.rank, parity);
-  for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
-    const int k = t / ncomp, c = t - k * ncomp;
-    out[t] = vec[(size_t)H.idx[off + k] * ncomp + c];
+  // four independent gathers in flight per thread, then the four remote stores
+  for (int t0 = lo + threadIdx.x; t0 < hi; t0 += 4 * SIC_P2P_THREADS) {
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j * SIC_P2P_THREADS;
+      if (t < hi) { const int k = t / ncomp, c = t - k * ncomp; v[j] = vec[(size_t)H.idx[off + k] * ncomp + c]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j * SIC_P2P_THREADS;
+      if (t < hi) out[t] = v[j];
+    }
   }
   __syncthreads();                           // CTA-scope ordering of everybody's stores before thread 0's fence
   if (threadIdx.x == 0) {
     __threadfence_system();                  // cumulative: covers the whole CTA's remote stores
     atomicAdd(ctx.gbar, 1ull);               // this block no longer reads vec
     const unsigned done = atomicAdd(ctx.counters + p, 1u);
-    if (done == SIC_P2P_BPP - 1) {           // last chunk for this peer: publish
+    if (done == (unsigned)bpp - 1u) {        // last chunk for this peer: publish
       ctx.counters[p] = 0;
       __threadfence_system();
       *(volatile unsigned long long*)(out + scal_off + SIC_P2P_NSCAL) = epoch + 1;
@@ -270,9 +286,18 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
   }
   __syncthreads();
   if (ok) {
-    for (int t = lo + threadIdx.x; t < hi; t += SIC_P2P_THREADS) {
-      const int k = t / ncomp, c = t - k * ncomp;
-      atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, __ldcv(in + t));
+    for (int t0 = lo + threadIdx.x; t0 < hi; t0 += 4 * SIC_P2P_THREADS) {
+      double v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j * SIC_P2P_THREADS;
+        if (t < hi) v[j] = __ldcv(in + t);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j * SIC_P2P_THREADS;
+        if (t < hi) { const int k = t / ncomp, c = t - k * ncomp; atomicAdd(vec + (size_t)H.idx[off + k] * ncomp + c, v[j]); }
+      }
     }
   }
   p2p_block_done(ctx, ncomp, n_scal, epoch, epoch_s);
@@ -284,6 +309,11 @@ extern "C" int sic_p2p_create(int rank, int n_ranks, int cap_nodes, void** p2p, 
   if (n_ranks < 2 || n_ranks > SIC_P2P_MAX_RANKS) return sic_fail("sic_p2p_create: 2..16 ranks");
   sic::P2P* c = new sic::P2P();
   c->rank = rank; c->n_ranks = n_ranks; c->cap = cap_nodes > 0 ? cap_nodes : 1;
+  {   // 3-component exchanges are the frequent ones: <= 16 values per thread
+    const long long per_block = 16ll * SIC_P2P_THREADS;
+    long long b = (3ll * c->cap + per_block - 1) / per_block;
+    c->bpp = (int)(b < SIC_P2P_BPP_MIN ? SIC_P2P_BPP_MIN : (b > SIC_P2P_BPP_MAX ? SIC_P2P_BPP_MAX : b));
+  }
   c->slot_doubles = 9 * (size_t)c->cap + SIC_P2P_NSCAL + 2;   // + halo flag + scalar flag
   const size_t bytes = sizeof(double) * c->slot_doubles * 2 * n_ranks;
   if (int rc = sic_check_cuda(cudaMalloc((void**)&c->local, bytes), "cudaMalloc mailbox")) return rc;
@@ -359,7 +389,7 @@ extern "C" int sic_exchange(const sic_halo_t* h, double* vec, int ncomp, double*
   }
   if (ncomp > 0 && cap_needed > c->cap) return sic_fail("sic_exchange: mailbox too small for this halo plan");
   if (h->n_ranks > SIC_P2P_THREADS) return sic_fail("sic_exchange: too many ranks");
-  const int blocks = (ncomp > 0 ? h->n_peers * SIC_P2P_BPP : 0) + (n_scal > 0 ? 1 : 0);
+  const int blocks = (ncomp > 0 ? h->n_peers * c->bpp : 0) + (n_scal > 0 ? 1 : 0);
   // every rank takes this path for every call (nodal data to the neighbours, scalars to everybody), so the
   // (device-resident) epoch counters of all ranks advance in lock step; a rank without neighbours on this halo plan
   // launches nothing for a nodal-only exchange and its nodal epoch is then never looked at by anybody

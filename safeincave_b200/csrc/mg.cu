@@ -508,7 +508,8 @@ extern "C" int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes) {
 }
 
 static MgScal* g_mg_host = nullptr;   // pinned mirror of the device scalars
-static cudaEvent_t g_mg_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] V-cycle operator, [2,3] Krylov operator
+static cudaEvent_t g_mg_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0,1] V-cycle operator, [2,3] Krylov operator,
+                                                                                   // [1,4] the halo exchange after the V-cycle operator
 
 static int mg_host_mirror() {
   if (g_mg_host) return 0;
@@ -619,6 +620,7 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     }
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
     if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
+    if (time_top_apply && l == top && h) cudaEventRecord(time_top_apply[4], st);   // [1]..[4]: one finest-level halo exchange
     k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
     // several GPUs: every fine node is restricted by its owner only; the coarse right-hand side is then completed by a
     // halo sum when the coarse level is partitioned too (nested partition: the parents of an owned fine node are
@@ -881,9 +883,11 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   ksp->op_ms = 0.0;
   ksp->op_dot_samples = 0;
   ksp->op_dot_ms = 0.0;
+  ksp->xchg_samples = 0;
+  ksp->xchg_ms = 0.0;
   cudaEvent_t* ev = nullptr;
   if (ksp->time_operator) {
-    if (!g_mg_ev[0]) for (int k = 0; k < 4; ++k) cudaEventCreate(&g_mg_ev[k]);
+    if (!g_mg_ev[0]) for (int k = 0; k < 5; ++k) cudaEventCreate(&g_mg_ev[k]);
     ev = g_mg_ev;
   }
 
@@ -943,6 +947,7 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { ksp->op_ms += ms; ksp->op_samples += 1; }
       if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) { ksp->op_dot_ms += ms; ksp->op_dot_samples += 1; }
+      if (multi && cudaEventElapsedTime(&ms, ev[1], ev[4]) == cudaSuccess) { ksp->xchg_ms += ms; ksp->xchg_samples += 1; }
       timed_batch = false;
     }
     if (g_mg_host->done || launched >= ksp->max_it) break;

@@ -361,4 +361,6 @@ class Multigrid:
         eng.op_dot_ms = getattr(eng, "op_dot_ms", 0.0) + float(ksp.op_dot_ms)
         eng.op_dot_samples = getattr(eng, "op_dot_samples", 0) + int(ksp.op_dot_samples)
         eng.op_dot_launches = getattr(eng, "op_dot_launches", 0) + int(ksp.iterations)
+        eng.xchg_ms = getattr(eng, "xchg_ms", 0.0) + float(ksp.xchg_ms)
+        eng.xchg_samples = getattr(eng, "xchg_samples", 0) + int(ksp.xchg_samples)
         return ksp
