@@ -279,11 +279,20 @@ class LinearMomentum(LinearMomentumBase):
             check = max(1, min(check, self._last_mg_its))
         res = self.mg.solve(self.b_ext, x, rtol=rtol, atol=atol, max_it=min(max_it, ksp.mg_max_it),
                             check_every=check, guess_nonzero=ksp.initial_guess_nonzero,
-                            time_operator=eng.time_operator)
+                            time_operator=self._time_this_solve())
         self._last_mg_its = int(res.iterations)
         eng._toc(t)
         self._record_solve(res)
         return res
+
+    def _time_this_solve(self):
+        """Engine.time_operator: True times one operator launch (and one halo exchange) in EVERY multigrid solve, an
+        integer n in every n-th one -- the timed iteration is launched kernel by kernel instead of as one graph."""
+        every = self.engine.time_operator
+        if not every:
+            return False
+        self._timed_solves = getattr(self, "_timed_solves", 0) + 1
+        return every is True or self._timed_solves % int(every) == 1 or int(every) == 1
 
     def _coarse_dirichlet_mask(self, level, mesh):
         """Dirichlet mask (3 M,) of a coarse mesh of the hierarchy, from the boundary conditions' facet tags

@@ -167,46 +167,37 @@ __global__ void k_mg_zero_free(int nd, double* __restrict__ z, const double* __r
   if (d < nd) z[d] = fixed[d] ? x[d] : 0.0;
 }
 
-// sum a.b over all dofs (w: owner weights on several GPUs, every node counted once; NULL on one)
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int n_nodes, const double* __restrict__ a,
+// sum a.b over all dofs (w: owner weights on several GPUs, every node counted once; NULL on one); one thread per DOF
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int nd, const double* __restrict__ a,
                                                            const double* __restrict__ b, const double* __restrict__ w,
                                                            MgFin fin, int skip_if_done,
                                                            double* __restrict__ partials, unsigned* counter) {
   if (skip_if_done && fin.S->done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
-  if (n < n_nodes) {
-    const double wn = w ? w[n] : 1.0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) v[0] += wn * a[3 * (size_t)n + j] * b[3 * (size_t)n + j];
-  }
+  if (k < nd) v[0] = (w ? w[k / 3] : 1.0) * a[k] * b[k];
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
 }
 
-// x += alpha p ; r -= alpha q (fixed dofs: r = 0) ; rr = r.r -> convergence test
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int n_nodes, double* __restrict__ x,
+// x += alpha p ; r -= alpha q (fixed dofs: r = 0) ; rr = r.r -> convergence test ; one thread per DOF
+__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int nd, double* __restrict__ x,
                                                                  double* __restrict__ r, const double* __restrict__ p,
                                                                  const double* __restrict__ q,
                                                                  const uint8_t* __restrict__ fixed,
                                                                  const double* __restrict__ w, MgFin fin,
                                                                  double* __restrict__ partials, unsigned* counter) {
   if (fin.S->done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const double alpha = fin.S->alpha;
   double v[1] = {0.0};
-  if (n < n_nodes) {
-    const double wn = w ? w[n] : 1.0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const size_t d = 3 * (size_t)n + j;
-      double rn = 0.0;
-      if (!fixed[d]) {
-        x[d] += alpha * p[d];
-        rn = r[d] - alpha * q[d];
-      }
-      r[d] = rn;
-      v[0] += wn * rn * rn;
+  if (k < nd) {
+    double rn = 0.0;
+    if (!fixed[k]) {
+      x[k] += alpha * p[k];
+      rn = r[k] - alpha * q[k];
     }
+    r[k] = rn;
+    v[0] = (w ? w[k / 3] : 1.0) * rn * rn;
   }
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
 }
@@ -248,16 +239,40 @@ __device__ __forceinline__ void mg_cheb_first_node(int n, const double* __restri
     x[k] = zero_guess ? dn : x[k] + dn;
   }
 }
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_first(int n_nodes, const double* __restrict__ b,
+// The stand-alone smoother kernels run one thread per DOF (coalesced 8-byte accesses to r, d, x, t, b; the row of the
+// node's 3x3 block is the three consecutive doubles at dinv[3 k]); the node's other two residual components come
+// through shared memory.  SIC_DOF_THREADS is a multiple of 3, so a node never straddles two blocks.  Same expressions,
+// in the same order, as the per-node functions the fused coarsest-level kernel uses.
+#define SIC_DOF_THREADS 192
+__global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_first(int nd, const double* __restrict__ b,
                                                                   double* __restrict__ r, double* __restrict__ d,
                                                                   double* __restrict__ x, double* __restrict__ t,
                                                                   const double* __restrict__ dinv,
                                                                   const uint8_t* __restrict__ fixed, double inv_theta,
                                                                   int zero_guess, const int* done) {
   if (*done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_nodes) return;
-  mg_cheb_first_node(n, b, r, d, x, t, dinv, fixed, inv_theta, zero_guess);
+  __shared__ double rs[SIC_DOF_THREADS];
+  const int k = blockIdx.x * SIC_DOF_THREADS + threadIdx.x;
+  const bool in = k < nd;
+  bool fx = true;
+  double v = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0, xk = 0.0;
+  if (in) {
+    fx = fixed[k] != 0;
+    v = zero_guess ? b[k] : b[k] - t[k];
+    if (fx) v = 0.0;
+    d0 = __ldg(dinv + 3 * (size_t)k); d1 = __ldg(dinv + 3 * (size_t)k + 1); d2 = __ldg(dinv + 3 * (size_t)k + 2);
+    if (!zero_guess) xk = x[k];
+    r[k] = v;
+    t[k] = 0.0;
+  }
+  rs[threadIdx.x] = v;
+  __syncthreads();
+  if (!in) return;
+  const int base = threadIdx.x - (threadIdx.x % 3);
+  const double z = d0 * rs[base] + d1 * rs[base + 1] + d2 * rs[base + 2];
+  const double dn = fx ? 0.0 : z * inv_theta;
+  d[k] = dn;
+  x[k] = zero_guess ? dn : xk + dn;
 }
 
 // Step k >= 1.  t holds K d: r -= t ; d = a d + c Dinv r ; x += d ; t = 0.
@@ -285,15 +300,34 @@ __device__ __forceinline__ void mg_cheb_step_node(int n, double* r, double* d, d
     x[k] += dn;
   }
 }
-__global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cheb_step(int n_nodes, double* __restrict__ r,
+__global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_step(int nd, double* __restrict__ r,
                                                                  double* __restrict__ d, double* __restrict__ x,
                                                                  double* __restrict__ t, const double* __restrict__ dinv,
                                                                  const uint8_t* __restrict__ fixed, double a, double c,
                                                                  const int* done) {
   if (*done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_nodes) return;
-  mg_cheb_step_node(n, r, d, x, t, dinv, fixed, a, c);
+  __shared__ double rs[SIC_DOF_THREADS];
+  const int k = blockIdx.x * SIC_DOF_THREADS + threadIdx.x;
+  const bool in = k < nd;
+  bool fx = true;
+  double v = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0, dk = 0.0, xk = 0.0;
+  if (in) {
+    fx = fixed[k] != 0;
+    v = fx ? 0.0 : r[k] - t[k];
+    d0 = __ldg(dinv + 3 * (size_t)k); d1 = __ldg(dinv + 3 * (size_t)k + 1); d2 = __ldg(dinv + 3 * (size_t)k + 2);
+    dk = d[k];
+    xk = x[k];
+    r[k] = v;
+    t[k] = 0.0;
+  }
+  rs[threadIdx.x] = v;
+  __syncthreads();
+  if (!in) return;
+  const int base = threadIdx.x - (threadIdx.x % 3);
+  const double z = d0 * rs[base] + d1 * rs[base + 1] + d2 * rs[base + 2];
+  const double dn = fx ? 0.0 : a * dk + c * z;
+  d[k] = dn;
+  x[k] = xk + dn;
 }
 
 #ifndef SIC_HOSTEMU
@@ -349,20 +383,17 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_restrict(int n_coarse, c
                                                                 const uint8_t* __restrict__ fixed_c,
                                                                 const double* __restrict__ w_f, const int* done) {
   if (*done) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_coarse) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per coarse DOF: (node c, component j)
+  if (k >= 3 * n_coarse) return;
+  const int c = k / 3, j = k - 3 * c;
+  double s = 0.0;
   const int e1 = __ldg(ptr + c + 1);
   for (int e = __ldg(ptr + c); e < e1; ++e) {
     const int fn = __ldg(idx + e);
-    const size_t f = 3 * (size_t)fn;
     const double wn = w_f ? w_f[fn] : 1.0;      // several GPUs: a fine node is summed by its owner only
-    s0 += wn * r_f[f]; s1 += wn * r_f[f + 1]; s2 += wn * r_f[f + 2];
+    s += wn * r_f[3 * (size_t)fn + j];
   }
-  const size_t k = 3 * (size_t)c;
-  b_c[k] = fixed_c[k] ? 0.0 : 0.5 * s0;
-  b_c[k + 1] = fixed_c[k + 1] ? 0.0 : 0.5 * s1;
-  b_c[k + 2] = fixed_c[k + 2] ? 0.0 : 0.5 * s2;
+  b_c[k] = fixed_c[k] ? 0.0 : 0.5 * s;
 }
 
 // x_f += P x_c
@@ -371,13 +402,10 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_prolong_add(int n_fine, 
                                                                    const double* __restrict__ x_c, double* __restrict__ x_f,
                                                                    const uint8_t* __restrict__ fixed_f, const int* done) {
   if (*done) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_fine) return;
-  const size_t a = 3 * (size_t)__ldg(pa + n), b = 3 * (size_t)__ldg(pb + n), k = 3 * (size_t)n;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (!fixed_f[k + j]) x_f[k + j] += 0.5 * (x_c[a + j] + x_c[b + j]);
-  }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per fine DOF
+  if (k >= 3 * n_fine) return;
+  const int n = k / 3, j = k - 3 * n;
+  if (!fixed_f[k]) x_f[k] += 0.5 * (x_c[3 * (size_t)__ldg(pa + n) + j] + x_c[3 * (size_t)__ldg(pb + n) + j]);
 }
 
 // CT_c = mean of the eight children's CT_f (Galerkin coarse operator; both in the tiled SIC_CT_INDEX layout)
@@ -500,7 +528,7 @@ static MgWork mg_work(double* work) {
   return MgWork{(MgScal*)work, (unsigned*)(work + SIC_MG_HEADER), work + SIC_MG_HEADER + SIC_MG_COUNTERS};
 }
 static int64_t mg_partial_slots(int n_cells, int n_nodes) {
-  return (int64_t)n_cells / SIC_TILE_CELLS + (int64_t)n_nodes / SIC_VEC_THREADS + 8;
+  return (int64_t)n_cells / SIC_TILE_CELLS + 3 * (int64_t)n_nodes / SIC_VEC_THREADS + 8;
 }
 
 extern "C" int64_t sic_mg_workspace_doubles(int n_cells, int n_nodes) {
@@ -522,19 +550,19 @@ static int mg_host_mirror() {
 static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, double lo, int zero_guess, const int* done,
                         cudaStream_t st) {
   const int nn = L.prob.n_nodes, nc = L.prob.n_cells;
-  const int nb = mg_blocks(nn, SIC_VEC_THREADS);
+  const int nb = mg_blocks(3 * nn, SIC_DOF_THREADS);
   (void)nc;
   const double lmax = L.lambda_max, lmin = lo * lmax;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double rho = 1.0 / sigma;
   if (!zero_guess)
     if (int rc = mg_apply(L, L.x, L.t, done, st)) return rc;                         // t = K x (t is 0 on entry)
-  k_mg_cheb_first<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta, zero_guess,
+  k_mg_cheb_first<<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta, zero_guess,
                                                   done);
   for (int k = 1; k < its; ++k) {
     if (int rc = mg_apply(L, L.d, L.t, done, st)) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
-    k_mg_cheb_step<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
+    k_mg_cheb_step<<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
                                                    2.0 * rho_new / delta, done);
     rho = rho_new;
   }
@@ -625,7 +653,7 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     // several GPUs: every fine node is restricted by its owner only; the coarse right-hand side is then completed by a
     // halo sum when the coarse level is partitioned too (nested partition: the parents of an owned fine node are
     // local), by one all-reduce over NVLink when it is replicated
-    k_mg_restrict<<<mg_blocks(C.prob.n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(
+    k_mg_restrict<<<mg_blocks(3 * C.prob.n_nodes, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(
         C.prob.n_nodes, L.rst_ptr, L.rst_idx, L.r, C.b, C.fixed, h ? h->owner_w : nullptr, done);
     if (h) {
       if (const sic_halo_t* hc = mg_halo(C)) { if (int rc = sic_exchange(hc, C.b, 3, nullptr, 0, (void*)st)) return rc; }
@@ -643,7 +671,7 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     const sic_mg_level_t& C = lv[l - 1];
     const double* b = (l == top) ? b_top : L.b;
     const int nn = L.prob.n_nodes;
-    k_mg_prolong_add<<<mg_blocks(nn, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nn, L.parent_a, L.parent_b, C.x, L.x,
+    k_mg_prolong_add<<<mg_blocks(3 * nn, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nn, L.parent_a, L.parent_b, C.x, L.x,
                                                                                  L.fixed, done);
     if (int rc = mg_chebyshev(L, b, o->nu, o->smooth_lo, 0, done, st)) return rc;
   }
@@ -759,10 +787,11 @@ struct MgGraphKey {
   double rtol, atol;
   double lam[SIC_MG_MAX_LEVELS];      // the levels' lambda_max (kept out of lv: a new set-up changes only these)
   int n_levels, guess, fused_refused;
+  int kind;                           // 0: one CG iteration, 1: the first cycle of a solve (z = M^-1 r0, rz, p = z)
   cudaStream_t st;
 };
 struct MgGraphEntry { MgGraphKey key; cudaGraphExec_t exec; unsigned long long used; };
-#define SIC_MG_GRAPH_SLOTS 4
+#define SIC_MG_GRAPH_SLOTS 8
 static MgGraphEntry g_mg_graphs[SIC_MG_GRAPH_SLOTS];
 static unsigned long long g_mg_graph_clock = 0;
 static int g_mg_graph_broken = 0;      // a capture failed once: launch kernel by kernel from then on
@@ -776,7 +805,7 @@ static cudaStream_t mg_capture_stream() {
 template <class Body>
 static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, const double* b_ext,
                                           double* x, double* work, double rtol, double atol, int guess, cudaStream_t st,
-                                          Body& body) {
+                                          Body& body, int kind = 0) {
   if (g_mg_graph_broken) return nullptr;
   MgGraphKey key;
   memset(&key, 0, sizeof(key));
@@ -784,13 +813,15 @@ static cudaGraphExec_t mg_iteration_graph(const sic_mg_level_t* lv, int n_levels
   memcpy(&key.o, o, sizeof(sic_mg_opts_t));
   key.b_ext = b_ext; key.x = x; key.work = work; key.rtol = rtol; key.atol = atol;
   key.n_levels = n_levels; key.guess = guess; key.fused_refused = g_fused_refused | (g_fused_not_in_capture << 1); key.st = st;
+  key.kind = kind;
   for (int l = 0; l < n_levels; ++l) { key.lam[l] = lv[l].lambda_max; key.lv[l].lambda_max = 0.0; }
   MgGraphEntry* slot = nullptr;
   MgGraphEntry* lru = &g_mg_graphs[0];
   for (int i = 0; i < SIC_MG_GRAPH_SLOTS; ++i) {
     MgGraphEntry& e = g_mg_graphs[i];
     if (e.exec && memcmp(&e.key, &key, sizeof(key)) == 0) { e.used = ++g_mg_graph_clock; return e.exec; }
-    if (e.exec && memcmp(e.key.lv, key.lv, sizeof(key.lv)) == 0 && e.key.x == key.x && e.key.work == key.work)
+    if (e.exec && memcmp(e.key.lv, key.lv, sizeof(key.lv)) == 0 && e.key.x == key.x && e.key.work == key.work &&
+        e.key.kind == key.kind)
       slot = &e;                             // same hierarchy and vectors: its graph has the same topology
     if (e.used < lru->used) lru = &e;        // least recently used (empty slots have used == 0)
   }
@@ -894,16 +925,20 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (guess) {   // reference norm of rtol: the residual of the zero guess (prescribed values only), as PETSc's ||b||
     k_mg_zero_free<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, x, fixed);
     if (int rc = sic_residual0(p, b_ext, pp, r, fixed, halo, stream)) return rc;
-    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, ow, fin(MG_OP_REF), 0, W.partials, W.counter);
+    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_REF), 0, W.partials, W.counter);
     if (int rc = reduce(MG_OP_REF, nullptr, 0)) return rc;
   }
   if (int rc = sic_residual0(p, b_ext, x, r, fixed, halo, stream)) return rc;
-  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, r, ow, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
+  k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
   if (int rc = reduce(MG_OP_INIT_RR, nullptr, 0)) return rc;
-  if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, nullptr)) return rc;
-  k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
-  if (int rc = reduce(MG_OP_INIT_RZ, nullptr, 1)) return rc;
-  k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);   // p = z ; q = 0
+  // first cycle of the solve: z = M^-1 r0, rz = r0.z, p = z ; q = 0 (its own graph when use_graph, below)
+  auto first_cycle = [&](cudaEvent_t*) -> int {
+    if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, nullptr)) return rc;
+    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
+    if (int rc = reduce(MG_OP_INIT_RZ, nullptr, 1)) return rc;
+    k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);
+    return 0;
+  };
 
   // one CG iteration: q = K p with p.Kp summed per cell (cells are partitioned: no owner weights needed); several
   // GPUs: the halo sum of q and the sum of p.Kp over the ranks travel in ONE exchange.  Every argument is either a
@@ -914,10 +949,10 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     if (time_ev) cudaEventRecord(time_ev[3], st);
     k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
     if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
-    k_mg_cg_update<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
+    k_mg_cg_update<<<db, SIC_VEC_THREADS, 0, st>>>(nd, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
     if (int rc = reduce(MG_OP_RR, nullptr, 1)) return rc;
     if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, time_ev)) return rc;
-    k_mg_dot<<<nb, SIC_VEC_THREADS, 0, st>>>(nn, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
+    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
     if (int rc = reduce(MG_OP_RZ, nullptr, 1)) return rc;
     k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
     return 0;
@@ -927,16 +962,22 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
 #ifndef SIC_HOSTEMU
   // Captured on a stream of the library's own (the caller's is normally the legacy default stream, which cannot be
   // captured) and replayed on the caller's stream.  The lambdas above launch on `st` / `stream`, whatever they hold.
-  cudaGraphExec_t gexec = nullptr;
+  cudaGraphExec_t gexec = nullptr, gfirst = nullptr;
   if (ksp->use_graph) {
     if (cudaStream_t cs = mg_capture_stream()) {
       void* const user = stream;
       st = cs; stream = (void*)cs;
       gexec = mg_iteration_graph(lv, n_levels, o, b_ext, x, work, rtol, atol, guess, cs, iteration);
+      if (gexec) gfirst = mg_iteration_graph(lv, n_levels, o, b_ext, x, work, rtol, atol, guess, cs, first_cycle, 1);
       st = (cudaStream_t)user; stream = user;
     }
   }
+  if (gfirst) {
+    if (int rc = sic_check_cuda(cudaGraphLaunch(gfirst, st), "cudaGraphLaunch (mg-cg first cycle)")) return rc;
+    ksp->graph_launches += 1;
+  } else
 #endif
+  if (int rc = first_cycle(nullptr)) return rc;
 
   int launched = 0;
   bool timed_batch = false;

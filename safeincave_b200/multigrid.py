@@ -349,7 +349,8 @@ class Multigrid:
         # host-side launches: the prologue (incl. the first V-cycle) and the iterations launched kernel by kernel, plus
         # ONE graph launch per replayed iteration (graph_kernel_nodes: the kernels inside those graphs)
         per_it = self.launches_per_cycle + 5
-        eng.launches += 6 + per_it * (int(ksp.direct_iterations) + 1) + int(ksp.graph_launches)
+        first_direct = 0 if int(ksp.graph_launches) > 0 else 1       # the first cycle of the solve is a graph of its own
+        eng.launches += 6 + per_it * (int(ksp.direct_iterations) + first_direct) + int(ksp.graph_launches)
         eng.graph_kernel_nodes = getattr(eng, "graph_kernel_nodes", 0) + per_it * int(ksp.graph_launches)
         self.graph_launches += int(ksp.graph_launches)
         eng.op_ms += float(ksp.op_ms)
