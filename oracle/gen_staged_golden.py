@@ -28,6 +28,7 @@ def main(name="cavern_irregular_finemesh", n_eq=2, n_op=2):
     grid = sf.GridHandlerGMSH.from_mesh(tm)
     case_eq, case_op = cases.staged_cavern_cases(grid, n_eq=n_eq, n_op=n_op)
     t0 = time.time()
+    tm = grid.tetmesh            # the Morton-ordered mesh the grid (and the GPU run) uses -- NOT the file order
     osim_eq, h_eq, osim, h_op = oracle_staged_run(case_eq, case_op, tm)
     for h in h_eq[1:] + h_op[1:]:
         print(h["iters"], h["error"], h["converged"], h["dt_used"])

@@ -216,3 +216,32 @@ def check_lagged_setup(sf, name="cube_coarse", levels=2, n_steps=3, gravity=5e3)
     assert k2 <= 1.05 * k0 + 2, (k0, k2)
     assert e0.mg.setups == len(e0.ksp_log) and e2.mg.setups <= 1 + 3 * n_steps, (e0.mg.setups, e2.mg.setups)
     return e0.mg.setups, e2.mg.setups, k0, k2
+
+
+def check_bench_settings_against_lu_golden(sf, tol=1e-8):
+    """The solver configuration bench.py times -- PC mg (compressed preconditioner operator, fused coarsest sweep, graph
+    replay), Krylov guess extrapolated from the Newton iterates, multigrid set-up lagged after the second Newton
+    iteration -- on cavern_regular x8 (114 768 cells), two time steps of BASELINE config 2, against the ORACLE's sparse-LU
+    run of the same steps (tests/golden/cfg2_cavern_regular_L1.npz, oracle/gen_staged_golden.py cfg2)."""
+    from safeincave_b200 import cases
+    g = np.load(os.path.join(GOLD, "cfg2_cavern_regular_L1.npz"))
+    h, grid, case, eq, sim = make(sf, "cavern_regular", int(g["levels"]), cases.cavern_case, n_steps=int(g["n_steps"]),
+                                  ksp_type="cg", rtol=1e-12)
+    assert h.finest.n_cells == int(g["n_cells"]) and abs(float(np.abs(h.finest.coords).sum()) / float(g["coords_checksum"]) - 1) < 1e-12
+    eq.solver.initial_guess_nonzero = True
+    eq.solver.guess_extrapolation = True
+    eq.solver.mg_setup_first = 2
+    sim.verbose = False
+    hist = sim.run()
+    assert all(r["converged"] and r["dt_used"] == r["dt"] for r in hist)
+    assert all(k[1] > 0 for k in eq.ksp_log), "a Krylov solve did not reach its tolerance"
+    assert [r["iterations"] for r in hist] == list(g["iters"])
+    eng = eq.engine
+    assert relerr(eq.X.reshape(-1).cpu().numpy(), g["u"]) < tol
+    sel = g["cell_sel"]
+    sig, eps = eng.get6(eng.sig), eng.get6(eng.eps)
+    assert np.abs(sig[sel] - g["sig_sel"]).max() / float(g["sig_absmax"]) < tol
+    assert np.abs(eps[sel] - g["eps_sel"]).max() / float(g["eps_absmax"]) < tol
+    assert abs(np.linalg.norm(sig) / float(g["sig_norm"]) - 1) < tol
+    assert eq.mg.compressed and eq.mg.setups < len(eq.ksp_log)       # the lag really skipped set-ups
+    return hist

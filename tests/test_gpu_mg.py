@@ -99,3 +99,9 @@ def test_compressed_preconditioner_operator(sf):
     its = C.check_setup_vcycle_solve(sf, "cube_coarse", levels=2, nonsym=0.01, full=False, mg_kwargs=dict(compressed=True),
                                      cycle_tol=0.1)
     assert its <= its_exact + 3, (its, its_exact)
+
+
+def test_bench_solver_settings_against_the_oracle_lu(sf):
+    """what bench.py times (PC mg + extrapolated guess + lagged set-up) against the oracle's sparse LU on
+    114 768 cells, two time steps, 1e-8 on u / sigma / eps, same Newton history."""
+    C.check_bench_settings_against_lu_golden(sf)
