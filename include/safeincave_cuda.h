@@ -333,9 +333,12 @@ typedef struct {
   double* pv;              /* [3 n_nodes] or NULL: power-iteration vector kept BETWEEN calls of sic_mg_setup (warm start) */
   /* compressed operator of the preconditioner, or both NULL: every operator application INSIDE the V-cycle (smoother,
    * residual, power iteration) then reads the symmetric part of C_T as 21 floats per cell and the gradients + volume
-   * as 13 floats -- 152 B per cell instead of 408 -- with FP64 arithmetic; the Krylov operator stays exact */
+   * as 13 floats -- 152 B per cell instead of 408, 144 with the 8 bytes of pc_lidx instead of the 16 of the connectivity -- with FP64 arithmetic; the Krylov operator stays exact */
   float* pc_ct;            /* [cell_stride/128][21][128] filled by sic_mg_setup from prob.CT */
   const float* pc_geom;    /* [13][cell_stride] rows 0-11 = prob.grad, row 12 = prob.vol (filled by the caller) */
+  const uint16_t* pc_lidx; /* [4][cell_stride] position of each cell node in its tile's list of unique nodes
+                              (prob.tile_nodes from prob.tile_ptr[tile] on): x is gathered once per unique node of a tile
+                              into shared memory, the connectivity is not read (filled by the caller) */
   const sic_halo_t* halo;  /* several GPUs: this level's cells are partitioned exactly as for sic_ksp_solve.  Partitioned
                               levels are the finest one and any run of levels below it (never level 0), NESTED: a cell
                               lives on the rank of its ancestor, so the transfer tables between two partitioned levels are

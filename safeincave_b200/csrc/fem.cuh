@@ -172,6 +172,9 @@ __device__ __forceinline__ double ebe_cell_batched(const sic_problem_t& P, int i
 // node of the tile (precomputed plan, sic_problem_t.tile_*), issuing one plain store per tile-interior
 // node component and one atomic per shared node component: ~5-6x fewer global RMWs, and none contended
 // inside the tile.  blockDim.x must be SIC_TILE_CELLS; f_s is double[12][128] in shared memory.
+struct TileGather {                       // + 12 KB for the compressed operator: x of the tile's unique nodes
+  double xs[3 * 4 * SIC_TILE_CELLS];
+};
 struct TileScratch {                      // shared memory of one operator CTA (17.4 KB)
   double f[12][SIC_TILE_CELLS];           // nodal forces of the tile's cells
   unsigned short ent[4 * SIC_TILE_CELLS]; // the tile's (cell,slot) references, grouped by unique node
@@ -193,12 +196,18 @@ __host__ __device__ constexpr int sic_sym_index(int r, int k) {      // upper tr
 }
 
 // XCOH: gather x through the coherent path (x was written earlier in the SAME launch, k_mg_coarse_fused).
-template <int MODE, bool XCOH = false, bool PC = false>
+// LIDX (compressed operator): x is gathered ONCE PER UNIQUE NODE of the tile into shared memory (xg) and every cell
+// picks its four nodes there through pc_lidx ([4][cell_stride] uint16: index of the cell's node in the tile's list of
+// unique nodes, sic_problem_t.tile_nodes) -- ncu showed the per-cell gathers (12 requests x 32 sectors per warp, 8 of
+// every 32 bytes used) keeping L1TEX at 77 % while DRAM idled at 47 %; the connectivity is not read at all.
+template <int MODE, bool XCOH = false, bool PC = false, bool LIDX = false>
 __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const double* __restrict__ x,
                                                    double* __restrict__ y, TileScratch& sc,
                                                    const int* done_flag = nullptr, const float* __restrict__ pc_ct = nullptr,
-                                                   const float* __restrict__ pc_geom = nullptr) {
+                                                   const float* __restrict__ pc_geom = nullptr,
+                                                   const uint16_t* __restrict__ pc_lidx = nullptr, TileGather* xg = nullptr) {
   static_assert(!(PC && MODE != 0), "the compressed operator only applies K");
+  static_assert(!LIDX || (PC && !XCOH), "the unique-node gather belongs to the compressed operator");
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int i = tile * SIC_TILE_CELLS + tid;
   const size_t ns = (size_t)P.cell_stride;
@@ -216,8 +225,17 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
   int node[4];
   store_t g[12], CT[PC ? SIC_PC_CT_ROWS : 36], vol;
   double er[6], ua[12];
+  if constexpr (LIDX) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
+    for (int a = 0; a < 4; ++a) {
+      unsigned short v;
+      asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(pc_lidx + a * ns + i));
+      node[a] = (int)v;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
+  }
   if constexpr (PC) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) g[k] = ldg_f32(pc_geom + k * ns + i);
@@ -237,11 +255,13 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
       for (int k = 0; k < 6; ++k) er[k] = ldg_f64(P.eps_rhs + k * ns + i);
     }
   }
+  if constexpr (!LIDX) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
+      for (int j = 0; j < 3; ++j)
+        ua[3 * a + j] = XCOH ? ldcg_f64(x + 3 * (size_t)node[a] + j) : ldg_f64(x + 3 * (size_t)node[a] + j);
+    }
   }
   // scatter plan of the tile -> shared memory (depends only on q0, requested first)
   const int nq = q1 - q0, ebase = tile * 4 * SIC_TILE_CELLS;
@@ -251,9 +271,22 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(eo) : "l"(P.ent_ptr + q0 + k));
     sc.nodes[k] = nd;
     sc.eoff[k] = eo - ebase;
+    if constexpr (LIDX) {          // x of unique node k, once for the whole tile
+      const double* xn = x + 3 * (size_t)nd;
+      const double x0 = ldg_f64(xn), x1 = ldg_f64(xn + 1), x2 = ldg_f64(xn + 2);
+      xg->xs[3 * k] = x0; xg->xs[3 * k + 1] = x1; xg->xs[3 * k + 2] = x2;
+    }
   }
   if (tid == 0) sc.eoff[nq] = 4 * SIC_TILE_CELLS;
   reinterpret_cast<uint2*>(sc.ent)[tid] = make_uint2(ent_lo, ent_hi);
+  if constexpr (LIDX) {
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ua[3 * a + j] = xg->xs[3 * node[a] + j];
+    }
+  }
   // ---- phase 1: the cell's arithmetic (cells of the padding compute zeros: their C_T, grad, vol are 0) --
   double exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;
 #pragma unroll

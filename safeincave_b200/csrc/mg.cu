@@ -102,10 +102,13 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, c
 #define SIC_PC_MINBLOCKS 6      /* resident CTAs per SM it is compiled for (latency-bound at 4: ncu, profiles/) */
 #endif
 __global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc(sic_problem_t P, const float* __restrict__ pc_ct,
-                                                               const float* __restrict__ pc_geom, const double* __restrict__ x,
-                                                               double* __restrict__ y, const int* done) {
+                                                               const float* __restrict__ pc_geom,
+                                                               const uint16_t* __restrict__ pc_lidx,
+                                                               const double* __restrict__ x, double* __restrict__ y,
+                                                               const int* done) {
   __shared__ TileScratch sc;
-  ebe_tile_scatter<0, false, true>(P, x, y, sc, done, pc_ct, pc_geom);
+  __shared__ TileGather xg;
+  ebe_tile_scatter<0, false, true, true>(P, x, y, sc, done, pc_ct, pc_geom, pc_lidx, &xg);
 }
 
 // pc_ct = float(sym(W C_T)), W = diag(1,1,1,2,2,2), of one level (once per set-up; both tiled by 128 cells).
@@ -489,7 +492,8 @@ static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_
     if (L.prob.abi_version != SIC_ABI_VERSION) return sic_fail("multigrid: sic_problem_t.abi_version mismatch");
     if (!L.fixed || !L.dinv || !L.x || !L.b || !L.r || !L.d || !L.t || !L.prob.CT)
       return sic_fail("multigrid: level with a null buffer");
-    if ((L.pc_ct != nullptr) != (L.pc_geom != nullptr)) return sic_fail("multigrid: pc_ct and pc_geom go together");
+    if ((L.pc_ct != nullptr) != (L.pc_geom != nullptr) || (L.pc_ct != nullptr) != (L.pc_lidx != nullptr))
+      return sic_fail("multigrid: pc_ct, pc_geom and pc_lidx go together");
     const bool part = L.halo && L.halo->n_ranks > 1;
     if (part && l == 0) return sic_fail("multigrid: the coarsest level must be replicated (not partitioned)");
     if (part && l + 1 < n_levels && !(lv[l + 1].halo && lv[l + 1].halo->n_ranks > 1))
@@ -513,7 +517,7 @@ static inline const sic_halo_t* mg_halo(const sic_mg_level_t& L) { return (L.hal
 static int mg_apply(const sic_mg_level_t& L, const double* x, double* t, const int* done, cudaStream_t st) {
   const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
   if (cb > 0) {
-    if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, x, t, done);
+    if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.pc_lidx, x, t, done);
     else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, x, t, done);
   }
   if (const sic_halo_t* h = mg_halo(L)) return sic_exchange(h, t, 3, nullptr, 0, (void*)st);
@@ -643,7 +647,7 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     const sic_halo_t* h = mg_halo(L);
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[0], st);
     if (cb > 0) {
-      if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.d, L.t, done);
+      if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.pc_lidx, L.d, L.t, done);
       else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
     }
     if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);

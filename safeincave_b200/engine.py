@@ -178,6 +178,9 @@ class Engine:
         self.tile_ptr = torch.zeros(nt + 1, dtype=torch.int32, device=dev)
         self.tile_ptr[1:] = torch.cumsum(per_tile, 0).to(torch.int32)
         self.tile_nint = torch.bincount(utile[interior], minlength=nt).to(torch.int32).contiguous()
+        # position of every cell node in its tile's list of unique nodes ([4][ns], < 512): the compressed multigrid
+        # operator gathers x once per unique node of a tile and indexes the shared-memory copy with these
+        self.lidx = (new_inv - self.tile_ptr.long()[tile]).to(torch.int16).reshape(4, ns).contiguous()
 
     # ------------------------------------------------------------------ material
     def set_material(self, table, mat_id, spring_off, thermo_off, n_thermo, elem_specs, keep_state=False, keep=None):

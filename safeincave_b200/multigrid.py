@@ -265,7 +265,7 @@ class Multigrid:
                 pc_geom = torch.cat([eng.grad.to(torch.float32), eng.vol.to(torch.float32).reshape(1, -1)]).contiguous()
                 pc_ct = torch.zeros((eng.ns // 128, 21, 128), dtype=torch.float32, device=dev)
                 self.vec[l]["pc_geom"], self.vec[l]["pc_ct"] = pc_geom, pc_ct
-                lv.pc_ct, lv.pc_geom = _ptr(pc_ct), _ptr(pc_geom)
+                lv.pc_ct, lv.pc_geom, lv.pc_lidx = _ptr(pc_ct), _ptr(pc_geom), _ptr(eng.lidx)
         self.compressed = bool(compressed)
         need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
         self.work = zeros(need)

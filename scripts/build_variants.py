@@ -19,6 +19,7 @@ VARIANTS = {
     # resident CTAs per SM of the compressed preconditioner operator (k_mg_ebe_pc)
     "pc_mb4": ["-DSIC_PC_MINBLOCKS=4"],
     "pc_mb5": ["-DSIC_PC_MINBLOCKS=5"],
+    "pc_mb7": ["-DSIC_PC_MINBLOCKS=7"],
     "pc_mb8": ["-DSIC_PC_MINBLOCKS=8"],
 }
 

@@ -86,7 +86,7 @@ def translate_launches(s):
         pos = a1
 
 
-_LD1 = re.compile(r'asm volatile\("ld\.global(?:\.nc|\.cg)?\.(?:f64|s32|f32) %0, \[%1\];"\s*:\s*"=[drf]"\((\w+)\)\s*:\s*"l"\((.+?)\)\);',
+_LD1 = re.compile(r'asm volatile\("ld\.global(?:\.nc|\.cg)?\.(?:f64|s32|f32|u16) %0, \[%1\];"\s*:\s*"=[drfh]"\((\w+)\)\s*:\s*"l"\((.+?)\)\);',
                   re.S)
 _LD2 = re.compile(r'asm volatile\("ld\.global\.nc\.v2\.u32 \{%0, %1\}, \[%2\];"\s*:\s*"=r"\((\w+)\),\s*"=r"\((\w+)\)\s*:\s*'
                   r'"l"\((.+?)\)\);', re.S)
