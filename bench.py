@@ -529,7 +529,7 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # Two operator kernels run on the finest level: the exact FP64 one of the Krylov iteration (k_mg_ebe_dot, or
     # k_ebe_dot without multigrid: 408 B per cell) and, inside the V-cycle, 2 nu applications of the preconditioner's
-    # (k_mg_ebe_pc on float(sym(W C_T)) + float geometry + 16-bit tile-local node indices, 144 B per cell; k_mg_ebe when --compressed 0).  `roofline` is the
+    # (k_mg_ebe_pc on float(sym(W C_T)) + float geometry, 152 B per cell; k_mg_ebe when --compressed 0).  `roofline` is the
     # one with the larger share of the step, `roofline_other` the other.  Both add 72 B per node (x read, y read-modify-write).
     traffic_ref = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -554,7 +554,7 @@ def run_b200(args):
     if pc == "mg":
         pc_on = bool(eq.mg is not None and eq.mg.compressed)
         r_cycle = roof("k_mg_ebe_pc (finest level, inside the V-cycle)" if pc_on else "k_mg_ebe (finest level, inside the V-cycle)",
-                       op_ms, op_samples, op_launches, 144 if pc_on else 408)
+                       op_ms, op_samples, op_launches, 152 if pc_on else 408)
         r_dot = roof("k_mg_ebe_dot (finest level, Krylov operator)", dot_ms, dot_samples, dot_launches, 408)
         note(f"OPERATOR finest level: V-cycle kernel {op_ms:.3f} ms/launch x {op_launches}, Krylov kernel {dot_ms:.3f} ms/launch "
              f"x {dot_launches}; Krylov iterations {ksp_its}; halo exchange {xchg_ms * 1e3:.1f} us")

@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe(sic_problem_t P, c
 }
 
 // the compressed operator of the preconditioner (fem.cuh, PC = true): symmetric float C_T, float geometry
+// SIC_PC_LIDX=1 (variant, measured SLOWER: 0.304 vs 0.272 ms per launch at 7.35 M cells, profiles/r2_ab2_*): gather x once
+// per unique node of the tile into shared memory through 16-bit tile-local node indices instead of once per cell through
+// the connectivity.  It takes L1TEX from 77 % to ~35 % and the DRAM bytes from 152 to 144 per cell, but the extra barrier
+// and shared-memory hop lengthen a CTA's dependent chain, and latency x resident warps is what bounds this kernel.
+#ifndef SIC_PC_LIDX
+#define SIC_PC_LIDX 0
+#endif
 #ifndef SIC_PC_MINBLOCKS
 #define SIC_PC_MINBLOCKS 6      /* resident CTAs per SM it is compiled for (latency-bound at 4: ncu, profiles/) */
 #endif
@@ -107,8 +114,13 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc(
                                                                const double* __restrict__ x, double* __restrict__ y,
                                                                const int* done) {
   __shared__ TileScratch sc;
+#if SIC_PC_LIDX
   __shared__ TileGather xg;
   ebe_tile_scatter<0, false, true, true>(P, x, y, sc, done, pc_ct, pc_geom, pc_lidx, &xg);
+#else
+  (void)pc_lidx;
+  ebe_tile_scatter<0, false, true, false>(P, x, y, sc, done, pc_ct, pc_geom);
+#endif
 }
 
 // pc_ct = float(sym(W C_T)), W = diag(1,1,1,2,2,2), of one level (once per set-up; both tiled by 128 cells).
