@@ -145,6 +145,9 @@ namespace sic {
 #define SIC_P2P_BPP_MIN 4      /* blocks per peer: at least this many, ... */
 #define SIC_P2P_BPP_MAX 32     /* ... at most this many, sized so that a thread moves <= 16 values (P2P.bpp) */
 #define SIC_P2P_THREADS 256
+// a rank may be late by as much as its host needs between two launches (rank 0 writing output files, uneven set-up
+// work): wait ~2 minutes of SM clocks before declaring the peer dead (sic_p2p_error)
+#define SIC_P2P_TIMEOUT_CYCLES 240000000000ll
 #define SIC_P2P_NSCAL 8
 
 struct P2P {
@@ -195,6 +198,8 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
                                                                  double* __restrict__ scal, int n_scal) {
   const unsigned long long epoch = ((volatile unsigned long long*)ctx.epochs)[0];
   const unsigned long long epoch_s = ((volatile unsigned long long*)ctx.epochs)[1];
+  // once a wait has timed out the run is lost (sic_p2p_error): later launches do not wait again
+  const long long timeout = (*(volatile int*)ctx.error) ? 0ll : SIC_P2P_TIMEOUT_CYCLES;
   const int parity = (int)(epoch & 1ull);
   const size_t scal_off = 9 * (size_t)ctx.cap;
   const int bpp = ctx.bpp;
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
           (volatile unsigned long long*)(p2p_slot(ctx.local, ctx.slot_doubles, r, parity) + scal_off + SIC_P2P_NSCAL + 1);
       const long long t0 = clock64();
       while (*flag != epoch + 1) {
-        if (clock64() - t0 > 20000000000ll) { atomicExch(ctx.error, 1); break; }   // ~10 s
+        if (clock64() - t0 > timeout) { atomicExch(ctx.error, 1); break; }   // ~2 min
       }
       __threadfence_system();
     }
@@ -273,13 +278,13 @@ __global__ void __launch_bounds__(SIC_P2P_THREADS) k_p2p_exchange(sic_halo_t H, 
     const long long t0 = clock64();
     int good = 1;
     while (*flag != epoch + 1) {
-      if (clock64() - t0 > 20000000000ll) { good = 0; atomicExch(ctx.error, 1); break; }   // ~10 s
+      if (clock64() - t0 > timeout) { good = 0; atomicExch(ctx.error, 1); break; }   // ~2 min
     }
     // A node shared by three ranks sits in two neighbours' lists: nobody may ADD to vec before every halo
     // block of this launch has finished READING its part of vec (grid-wide barrier; all blocks are resident).
     const unsigned long long target = (epoch + 1) * (unsigned long long)n_halo_blocks;
     while (*(volatile unsigned long long*)ctx.gbar < target) {
-      if (clock64() - t0 > 20000000000ll) { good = 0; atomicExch(ctx.error, 1); break; }
+      if (clock64() - t0 > timeout) { good = 0; atomicExch(ctx.error, 1); break; }
     }
     __threadfence_system();
     ok = good;
