@@ -335,7 +335,8 @@ typedef struct {
    * residual, power iteration) then reads the symmetric part of C_T as 21 floats per cell and the gradients + volume
    * as 13 floats -- 152 B per cell instead of 408, 144 with the 8 bytes of pc_lidx instead of the 16 of the connectivity -- with FP64 arithmetic; the Krylov operator stays exact */
   float* pc_ct;            /* [cell_stride/128][21][128] filled by sic_mg_setup from prob.CT */
-  const float* pc_geom;    /* [13][cell_stride] rows 0-11 = prob.grad, row 12 = prob.vol (filled by the caller) */
+  const float* pc_geom;    /* [cell_stride/128][13][128] rows 0-11 = prob.grad, row 12 = prob.vol, tiled by 128 cells like
+                              pc_ct (filled by the caller) */
   const uint16_t* pc_lidx; /* [4][cell_stride] position of each cell node in its tile's list of unique nodes
                               (prob.tile_nodes from prob.tile_ptr[tile] on): x is gathered once per unique node of a tile
                               into shared memory, the connectivity is not read (filled by the caller) */

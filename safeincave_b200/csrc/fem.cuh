@@ -184,10 +184,13 @@ struct TileScratch {                      // shared memory of one operator CTA (
 
 // Compressed operator of the multigrid PRECONDITIONER (PC = true): S = sym(W C_T), W = diag(1,1,1,2,2,2) (the form in
 // which the tangent of tensorial strains is symmetric, see k_mg_ct_compress), as 21 floats per cell
-// (tiled like C_T: [tile][21][128]) and the gradients + volume as 13 floats ([13][cell_stride]): 152 B per cell
+// (tiled like C_T: [tile][21][128]) and the gradients + volume as 13 floats (tiled the same way: [tile][13][128]): 152 B per cell
 // instead of 408.  The arithmetic stays FP64 (the vectors are).  A preconditioner only has to approximate K: the
 // non-symmetry of the finite-difference tangent is round-off (1e-6 relative) and float storage perturbs the entries by
 // 6e-8, neither of which moves the Krylov iteration count; the OUTER operator of the solve is always the exact one.
+#ifndef SIC_PC_F32MATH
+#define SIC_PC_F32MATH 1
+#endif
 #define SIC_PC_CT_ROWS 21
 #define SIC_PC_GEOM_ROWS 13
 #define SIC_PC_CT_INDEX(e, i) (((size_t)((i) / SIC_TILE_CELLS) * SIC_PC_CT_ROWS + (e)) * SIC_TILE_CELLS + ((i) % SIC_TILE_CELLS))
@@ -237,9 +240,10 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
     for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
   }
   if constexpr (PC) {
+    const float* gm = pc_geom + (size_t)tile * (SIC_PC_GEOM_ROWS * SIC_TILE_CELLS) + tid;   // tiled like pc_ct: [tile][13][128]
 #pragma unroll
-    for (int k = 0; k < 12; ++k) g[k] = ldg_f32(pc_geom + k * ns + i);
-    vol = ldg_f32(pc_geom + 12 * ns + i);
+    for (int k = 0; k < 12; ++k) g[k] = ldg_f32(gm + k * SIC_TILE_CELLS);
+    vol = ldg_f32(gm + 12 * SIC_TILE_CELLS);
     const float* ct = pc_ct + SIC_PC_CT_INDEX(0, i);
 #pragma unroll
     for (int k = 0; k < SIC_PC_CT_ROWS; ++k) CT[k] = ldg_f32(ct + k * SIC_TILE_CELLS);
@@ -301,35 +305,73 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
 #pragma unroll
     for (int k = 0; k < 6; ++k) eps[k] = er[k] - eps[k];
   }
-  double s[6];
+  // F32 (compressed operator, SIC_PC_F32MATH): the strain is formed in FP64 (differences of displacements), the stress, the
+  // nodal forces, their staging in shared memory and their per-node sums in FP32 -- the operands are floats already and
+  // the preconditioner tolerates 1e-7 relative; full-rate FFMA instead of half-rate DFMA, half the shared-memory traffic.
+  constexpr bool F32 = PC && (SIC_PC_F32MATH != 0);
+  float (*ff)[SIC_TILE_CELLS] = reinterpret_cast<float (*)[SIC_TILE_CELLS]>(&sc.f[0][0]);
+  double energy = 0.0;
+  if constexpr (F32) {
+    float ef[6], sf[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    double acc = 0.0;
+    for (int k = 0; k < 6; ++k) ef[k] = (float)eps[k];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc += CT[PC ? sic_sym_index(r, k) : r * 6 + k] * eps[k];
-    s[r] = (PC && r >= 3) ? 0.5 * acc : acc;       // PC: CT holds S = sym(W C_T), sigma = W^-1 S eps
+    for (int r = 0; r < 6; ++r) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc += (float)CT[sic_sym_index(r, k)] * ef[k];
+      sf[r] = (r >= 3) ? 0.5f * acc : acc;
+    }
+    const float vf = (float)vol;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float gx = (float)g[3 * a], gy = (float)g[3 * a + 1], gz = (float)g[3 * a + 2];
+      ff[3 * a + 0][tid] = vf * (sf[0] * gx + sf[3] * gy + sf[4] * gz);
+      ff[3 * a + 1][tid] = vf * (sf[3] * gx + sf[1] * gy + sf[5] * gz);
+      ff[3 * a + 2][tid] = vf * (sf[4] * gx + sf[5] * gy + sf[2] * gz);
+    }
+  } else {
+    double s[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc += CT[PC ? sic_sym_index(r, k) : r * 6 + k] * eps[k];
+      s[r] = (PC && r >= 3) ? 0.5 * acc : acc;       // PC: CT holds S = sym(W C_T), sigma = W^-1 S eps
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
+      sc.f[3 * a + 0][tid] = vol * (s[0] * gx + s[3] * gy + s[4] * gz);
+      sc.f[3 * a + 1][tid] = vol * (s[3] * gx + s[1] * gy + s[5] * gz);
+      sc.f[3 * a + 2][tid] = vol * (s[4] * gx + s[5] * gy + s[2] * gz);
+    }
+    energy = vol * ((eps[0] * s[0] + eps[1] * s[1] + eps[2] * s[2]) + 2.0 * (eps[3] * s[3] + eps[4] * s[4] + eps[5] * s[5]));
   }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const double gx = g[3 * a], gy = g[3 * a + 1], gz = g[3 * a + 2];
-    sc.f[3 * a + 0][tid] = vol * (s[0] * gx + s[3] * gy + s[4] * gz);
-    sc.f[3 * a + 1][tid] = vol * (s[3] * gx + s[1] * gy + s[5] * gz);
-    sc.f[3 * a + 2][tid] = vol * (s[4] * gx + s[5] * gy + s[2] * gz);
-  }
-  const double energy =
-      vol * ((eps[0] * s[0] + eps[1] * s[1] + eps[2] * s[2]) + 2.0 * (eps[3] * s[3] + eps[4] * s[4] + eps[5] * s[5]));
   __syncthreads();
   if (done) return 0.0;   // uniform over the grid: nothing is written once the solve has converged
   // ---- phase 2: one global write per unique node of the tile, everything read from shared memory ------
   for (int k = tid; k < nq; k += SIC_TILE_CELLS) {
     const int e0 = sc.eoff[k], e1 = sc.eoff[k + 1];
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int e = e0; e < e1; ++e) {
-      const int c = (int)sc.ent[e];
-      const int cell = c >> 2, slot = c & 3;
-      sx += sc.f[3 * slot + 0][cell];
-      sy += sc.f[3 * slot + 1][cell];
-      sz += sc.f[3 * slot + 2][cell];
+    if constexpr (F32) {
+      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+      for (int e = e0; e < e1; ++e) {
+        const int c = (int)sc.ent[e];
+        const int cell = c >> 2, slot = c & 3;
+        fx += ff[3 * slot + 0][cell];
+        fy += ff[3 * slot + 1][cell];
+        fz += ff[3 * slot + 2][cell];
+      }
+      sx = fx; sy = fy; sz = fz;
+    } else {
+      for (int e = e0; e < e1; ++e) {
+        const int c = (int)sc.ent[e];
+        const int cell = c >> 2, slot = c & 3;
+        sx += sc.f[3 * slot + 0][cell];
+        sy += sc.f[3 * slot + 1][cell];
+        sz += sc.f[3 * slot + 2][cell];
+      }
     }
     double* yn = y + 3 * (size_t)sc.nodes[k];
     if (k < nint) { yn[0] = sx; yn[1] = sy; yn[2] = sz; }                 // only this tile touches the node

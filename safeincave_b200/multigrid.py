@@ -262,7 +262,8 @@ class Multigrid:
             for k in ("x", "b", "r", "d", "t", "pv"):
                 setattr(lv, k, _ptr(self.vec[l][k]))
             if compressed:
-                pc_geom = torch.cat([eng.grad.to(torch.float32), eng.vol.to(torch.float32).reshape(1, -1)]).contiguous()
+                pc_geom = torch.cat([eng.grad.to(torch.float32), eng.vol.to(torch.float32).reshape(1, -1)])
+                pc_geom = pc_geom.reshape(13, eng.ns // 128, 128).permute(1, 0, 2).contiguous()      # [tile][13][128]
                 pc_ct = torch.zeros((eng.ns // 128, 21, 128), dtype=torch.float32, device=dev)
                 self.vec[l]["pc_geom"], self.vec[l]["pc_ct"] = pc_geom, pc_ct
                 lv.pc_ct, lv.pc_geom, lv.pc_lidx = _ptr(pc_ct), _ptr(pc_geom), _ptr(eng.lidx)
