@@ -157,6 +157,63 @@ def add_operation_stage(case_op, eq, grid, verbose=False, outputs=None):
     return sf.Simulator_M(eq, tc, outputs or [], compute_elastic_response=False, verbose=verbose)
 
 
+def per_cell(value, tm, n=None):
+    """A case parameter as a per-cell float64 numpy array: a number (uniform) or a dict {region name: number} resolved
+    through the mesh's cell tags (heterogeneous materials, e.g. salt / overburden of thermomechanics/2_cavern/main.py:47-97)."""
+    n = tm.n_cells if n is None else n
+    if isinstance(value, dict):
+        out = np.zeros(n, dtype=np.float64)
+        for name, v in value.items():
+            out[tm.cell_tags == tm.names[3][name]] = float(v)
+        return out
+    return np.full(n, float(value), dtype=np.float64)
+
+
+def overburden_tm_case(grid, n_steps=None, dt_days=0.5, ksp_type="cg", rtol=1e-12):
+    """BASELINE config 4 (examples/thermomechanics/2_cavern/main.py on grids/cavern_overburden_coarse): salt + overburden
+    with their own density / stiffness / viscosity / creep / thermal expansion (:47-97), rollers on the four sides of both
+    layers and at the bottom (:127-138), free top, gas pressure on the cavern wall (:151-167), Spring + Thermoelastic +
+    Kelvin + DislocationCreep + PressureSolutionCreep, theta = 0.5.  The thermal side (HeatDiffusion, :217-272) is in
+    ``thermal``; the Thermoelastic element is added by the caller (``thermo_alpha`` per region)."""
+    x = grid.mesh.geometry.x
+    tm = grid.tetmesh
+    z_top = float(x[:, 2].max())
+    z_roof = float(x[np.unique(tm.tris[tm.tri_tags == grid.get_boundary_tag("Cavern")]), 2].max())
+    ovb_cells = tm.cells[tm.cell_tags == tm.names[3]["Overburden"]]
+    z_ovb = float(x[np.unique(ovb_cells), 2].min())                       # bottom of the overburden
+    salt_density, ovb_density, gas_density, g = 2200.0, 2800.0, 0.082, -9.81
+    p_roof = salt_density * abs(g) * (z_ovb - z_roof) + ovb_density * abs(g) * (z_top - z_ovb)
+    t_final = 240 * day
+    reg = lambda salt, ovb: {"Salt": salt, "Overburden": ovb}
+    sides = [("West", 0), ("East", 0), ("South", 1), ("North", 1)]
+    case = dict(
+        name="overburden_tm", theta=0.5, dt=dt_days * day, t_final=t_final, time_unit="day",
+        density=reg(salt_density, ovb_density), g=[0.0, 0.0, g],
+        T=dict(surface=293.0, gradient=27.0 / 1000.0, z_surface=z_top),
+        spring=dict(E=reg(102 * GPa, 180 * GPa), nu=0.3),
+        elements=[dict(kind="kelvin", eta=reg(105e11, 105e21), E=10 * GPa, nu=0.32),
+                  dict(kind="dislocation", A=reg(1.9e-20, 0.0), Q=51600.0, n=3.0),
+                  dict(kind="pressure_solution", A=reg(1.29e-19, 0.0), d=0.01, Q=13184.0)],
+        thermo_alpha=reg(44e-6, 0.0),
+        dirichlet=[dict(boundary=f"{side}_{layer}", component=c, values=[0.0, 0.0], time_values=[0.0, t_final])
+                   for side, c in sides for layer in ("salt", "ovb")]
+        + [dict(boundary="Bottom", component=2, values=[0.0, 0.0], time_values=[0.0, t_final])],
+        neumann=[dict(boundary="Top", direction=2, density=0.0, ref_pos=z_top, gravity=g, values=[0.0, 0.0],
+                      time_values=[0.0, t_final]),
+                 dict(boundary="Cavern", direction=2, density=gas_density, ref_pos=z_roof, gravity=g,
+                      values=[0.8 * p_roof, 0.8 * p_roof, 0.2 * p_roof, 0.2 * p_roof, 0.8 * p_roof],
+                      time_values=[0 * day, 20 * day, 40 * day, 60 * day, 80 * day])],
+        thermal=dict(T0=293.0 + 0.027 * (z_top - x[:, 2]), t_final=t_final, rho=reg(salt_density, ovb_density), cp=850.0, k=7.0,
+                     dirichlet=[dict(boundary="Top", values=[293.0, 293.0], time_values=[0.0, t_final])],
+                     neumann=[dict(boundary="Bottom", values=[0.027, 0.027], time_values=[0.0, t_final])],
+                     robin=[dict(boundary="Cavern", h=5.0, values=[293.0, 293.0], time_values=[0.0, t_final])]),
+        ksp=dict(type=ksp_type, rtol=rtol), desai_initial_hardening=False,
+    )
+    if n_steps is not None:
+        case["t_final_run"] = n_steps * case["dt"]
+    return case
+
+
 def cell_temperature(case, coords, cells):
     """Per-cell temperature (N,) float64 numpy."""
     T = case["T"]
@@ -172,7 +229,11 @@ def build(case, grid, verbose=False, outputs=None, device="cuda", part=None, ctx
     Partition and DistContext; ``case`` must have been made from the GLOBAL grid)."""
     import safeincave_b200 as sf
     n = grid.n_elems
-    one = to.ones(n, dtype=to.float64)
+
+    class _PerCell:          # `value * one` for numbers and {region: value} dicts alike
+        def __rmul__(self, v):
+            return to.as_tensor(per_cell(v, grid.tetmesh, n))
+    one = _PerCell()
     eq = sf.LinearMomentum(grid, theta=case["theta"], device=device)
     if ctx is not None:
         from . import distributed

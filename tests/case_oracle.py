@@ -3,11 +3,19 @@ import numpy as np
 
 from oracle import constitutive as oc
 from oracle import fem
-from safeincave_b200.cases import cell_temperature
+from safeincave_b200.cases import cell_temperature, per_cell
 
 
-def oracle_material(case, n):
-    one = np.ones(n)
+class _PerCell:              # `value * one` for numbers and {region: value} dicts alike (cases.per_cell)
+    def __init__(self, tm, n):
+        self.tm, self.n = tm, n
+
+    def __rmul__(self, v):
+        return per_cell(v, self.tm, self.n)
+
+
+def oracle_material(case, n, tm=None):
+    one = _PerCell(tm, n) if tm is not None else np.ones(n)
     mat = oc.OracleMaterial(n)
     mat.add_spring(case["spring"]["E"] * one, case["spring"]["nu"] * one)
     for e in case["elements"]:
@@ -30,7 +38,7 @@ def oracle_material(case, n):
 
 def oracle_simulator(case, tm):
     n = tm.n_cells
-    mat = oracle_material(case, n)
+    mat = oracle_material(case, n, tm)
     T = cell_temperature(case, tm.coords, tm.cells)
     tag = lambda name: tm.names[2][name]
     dirichlet = [dict(tag=tag(d["boundary"]), component=d["component"], values=d["values"],
@@ -38,7 +46,7 @@ def oracle_simulator(case, tm):
     neumann = [dict(tag=tag(b["boundary"]), direction=b["direction"], density=b["density"], ref_pos=b["ref_pos"],
                     gravity=b["gravity"], values=b["values"], time_values=b["time_values"]) for b in case["neumann"]]
     sim = fem.OracleSimulatorM(tm.coords, tm.cells, tm.tris, tm.tri_tags, mat, case["theta"], T, T,
-                               case["density"] * np.ones(n), case["g"], dirichlet, neumann)
+                               per_cell(case["density"], tm, n), case["g"], dirichlet, neumann)
     if case.get("desai_initial_hardening"):
         def hook(m, sig):
             for e in m.elems:

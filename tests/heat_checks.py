@@ -26,6 +26,13 @@ def load_grid(sf, name, levels=0):
 
 
 def heat_case(grid, name):
+    if name == "cavern_overburden_coarse":          # BASELINE config 4: thermomechanics/2_cavern/main.py:217-272
+        from safeincave_b200 import cases
+        return cases.overburden_tm_case(grid)["thermal"]
+    return _heat_case(grid, name)
+
+
+def _heat_case(grid, name):
     """Boundary data in the pattern of examples/thermomechanics/2_cavern/main.py:243-273 (Dirichlet top, geothermal
     flux at the bottom, Robin h = 5 W/m2/K towards the gas on the cavern wall; cp 850, k 7)."""
     names = {n.upper(): n for n in grid.get_boundary_names()}
@@ -54,10 +61,11 @@ def build_heat(sf, grid, hc, rtol=1e-13):
     ksp.setTolerances(rtol=rtol, max_it=100)
     heat.set_solver(ksp)
     mat = sf.Material(n)
-    one = to.ones(n, dtype=to.float64)
-    mat.set_density(hc["rho"] * one)
-    mat.set_specific_heat_capacity(hc["cp"] * one)
-    mat.set_thermal_conductivity(hc["k"] * one)
+    from safeincave_b200.cases import per_cell
+    cellwise = lambda v: to.as_tensor(per_cell(v, grid.tetmesh, n))
+    mat.set_density(cellwise(hc["rho"]))
+    mat.set_specific_heat_capacity(cellwise(hc["cp"]))
+    mat.set_thermal_conductivity(cellwise(hc["k"]))
     heat.set_material(mat)
     heat.set_initial_T(to.as_tensor(hc["T0"]))
     bc = heatBC.BcHandler(heat)
@@ -76,8 +84,9 @@ def oracle_heat(tm, hc):
     conv = lambda lst, robin=False: [dict(tag=tag(d["boundary"]), values=d["values"], time_values=d["time_values"],
                                           **({"h": d["h"]} if robin else {})) for d in lst]
     n = tm.n_cells
-    o = oh.OracleHeat(tm.coords, tm.cells, tm.tris, tm.tri_tags, hc["rho"] * np.ones(n), hc["cp"] * np.ones(n),
-                      hc["k"] * np.ones(n), conv(hc["dirichlet"]), conv(hc["neumann"]), conv(hc["robin"], True))
+    from safeincave_b200.cases import per_cell
+    o = oh.OracleHeat(tm.coords, tm.cells, tm.tris, tm.tri_tags, per_cell(hc["rho"], tm), per_cell(hc["cp"], tm),
+                      per_cell(hc["k"], tm), conv(hc["dirichlet"]), conv(hc["neumann"]), conv(hc["robin"], True))
     o.set_initial_T(hc["T0"])
     return o
 
@@ -102,7 +111,7 @@ def check_heat_steps(sf, name, levels, n_steps, dt):
     return max(k[0] for k in heat.ksp_log)
 
 
-def check_thermomechanical_steps(sf, name="cube_coarse", levels=1, n_steps=3, dt=0.5 * DAY, tol=1e-8):
+def check_thermomechanical_steps(sf, name="cube_coarse", levels=1, n_steps=3, dt=0.5 * DAY, tol=1e-8, tol_T=2e-10):
     """Simulator_TM against OracleSimulatorTM: Spring + Thermoelastic + Kelvin + DislocationCreep; the Robin / Dirichlet
     data cool one side by tens of kelvin within the run, so thermal strain and the Arrhenius factor both move."""
     from safeincave_b200 import cases
@@ -110,26 +119,27 @@ def check_thermomechanical_steps(sf, name="cube_coarse", levels=1, n_steps=3, dt
     tm = grid.tetmesh
     hc = heat_case(grid, name)
     heat = build_heat(sf, grid, hc)
-    case = (cases.triaxial_case if name == "cube_coarse" else cases.cavern_case)(grid, n_steps=n_steps)
+    case_fn = {"cube_coarse": cases.triaxial_case, "cavern_overburden_coarse": cases.overburden_tm_case}.get(name, cases.cavern_case)
+    case = case_fn(grid, n_steps=n_steps)
     case["dt"] = dt
     case["t_final_run"] = n_steps * dt
-    case["thermo_alpha"] = 44e-6                                      # thermomechanics/2_cavern/main.py:91
+    case.setdefault("thermo_alpha", 44e-6)                            # thermomechanics/2_cavern/main.py:91
     eq, sim_m = cases.build(case, grid)
-    eq.mat.add_to_thermoelastic(sf.Thermoelastic(case["thermo_alpha"] * to.ones(grid.n_elems, dtype=to.float64)))
+    eq.mat.add_to_thermoelastic(sf.Thermoelastic(to.as_tensor(cases.per_cell(case["thermo_alpha"], tm))))
     eq.set_material(eq.mat)
     sim = sf.Simulator_TM(eq, heat, sim_m.t_control, [], compute_elastic_response=True, verbose=False)
     hist = sim.run()
     om = oracle_simulator(case, tm)
-    om.mat.add_thermoelastic(case["thermo_alpha"] * np.ones(tm.n_cells))
+    om.mat.add_thermoelastic(cases.per_cell(case["thermo_alpha"], tm))
     osim = oh.OracleSimulatorTM(om, oracle_heat(tm, hc))
     ohist = osim.run(0.0, [dt] * n_steps)
     assert [h["iterations"] for h in hist] == [h["iters"] for h in ohist[1:]]
     last = ohist[-1]
     eng = eq.engine
-    assert relerr(heat.T.x.array, last["T"]) < 2e-10
+    assert relerr(heat.T.x.array, last["T"]) < tol_T     # Krylov tolerance of the heat solve (rtol 1e-13 on ||b||, T ~ 300 K)
     assert relerr(eq.X.reshape(-1).cpu().numpy(), last["u"]) < tol
     assert relerr(eng.get6(eng.sig), last["sig"]) < tol
-    assert relerr(eng.get1(eng.T), osim.mech.T) < 2e-10
+    assert relerr(eng.get1(eng.T), osim.mech.T) < tol_T
     assert relerr(eng.get1(eng.T0), osim.mech.T0) < 1e-14
     for e_gpu, e_or in zip(eng.elems, om.mat.elems):
         assert relerr(eng.get6(e_gpu.eps_old), e_or.eps_old) < tol

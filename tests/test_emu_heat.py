@@ -25,3 +25,9 @@ def test_heat_steps_cavern_regular(sf):
 
 def test_thermomechanical_steps_cube(sf):
     C.check_thermomechanical_steps(sf)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SIC_SLOW"), reason="~13 min under emulation (25 608 cells); set SIC_SLOW=1")
+def test_thermomechanical_steps_config4_cavern_overburden_coarse(sf):
+    """BASELINE configs[3] on its own two-region grid (tests/test_gpu_heat.py runs it on the B200)."""
+    C.check_thermomechanical_steps(sf, "cavern_overburden_coarse", 0, 2, 0.5 * C.DAY, tol_T=2e-9)

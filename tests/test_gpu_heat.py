@@ -26,3 +26,10 @@ def test_thermomechanical_steps_cube(sf):
 
 def test_thermomechanical_step_cavern_regular(sf):
     C.check_thermomechanical_steps(sf, "cavern_regular", 0, 1, 2 * C.DAY)
+
+
+def test_thermomechanical_steps_config4_cavern_overburden_coarse(sf):
+    """BASELINE configs[3] on the grid it names (25 608 cells, salt + overburden with their own density, stiffness,
+    viscosity, creep and thermal expansion; set-up of examples/thermomechanics/2_cavern/main.py, cases.overburden_tm_case):
+    two Simulator_TM steps against OracleSimulatorTM -- same Newton history, u / sigma / creep strains <= 1e-8."""
+    C.check_thermomechanical_steps(sf, "cavern_overburden_coarse", 0, 2, 0.5 * C.DAY, tol_T=2e-9)
