@@ -76,6 +76,9 @@ def parse():
                     help="PC mg: replay every Krylov iteration from one captured CUDA graph (sic_ksp_t.use_graph)")
     ap.add_argument("--fused-coarse", type=int, default=1,
                     help="PC mg: the coarsest level's Chebyshev sweep as one cooperative launch (sic_mg_opts_t.fused_coarse)")
+    ap.add_argument("--fused-exchange", type=int, default=1,
+                    help="several GPUs, PC mg: the V-cycle's operator and the halo exchange of its result as one launch "
+                         "(k_mg_ebe_pc_x: interface tiles first, communication CTAs overlap the interior tiles)")
     ap.add_argument("--compressed", type=int, default=1,
                     help="PC mg: operator applications inside the V-cycle read float(sym(C_T)) + float geometry "
                          "(152 B per cell instead of 408); the Krylov operator stays exact FP64")
@@ -411,6 +414,9 @@ def run_b200(args):
         eq.mg_options = dict(eq.mg_options, use_graph=bool(args.graph), fused_coarse=bool(args.fused_coarse),
                              compressed=bool(args.compressed))
     apply_solver_settings(eq.solver, args.warm_start, args.mg_lag)
+    eng_lib = eq.engine.lib
+    if hasattr(eng_lib, "sic_mg_set_fused_exchange"):
+        eng_lib.sic_mg_set_fused_exchange(int(bool(args.fused_exchange)))
     eq.solver.single_reduction = bool(args.cgcg)
     if args.max_it > 0:
         eq.solver.respect_max_it, eq.solver.max_it = True, args.max_it
@@ -591,7 +597,9 @@ def run_b200(args):
         # several GPUs: one finest-level halo exchange (P2P kernel over NVLink), from the end of the operator kernel to the
         # end of the exchange kernel -- includes waiting for the slowest neighbour; rank 0's average over its samples
         "exchange": ({"avg_ms": xchg_ms, "samples": xchg_samples, "interface_nodes": int(part.n_interface),
-                      "neighbours": len(part.peers)} if world > 1 and xchg_samples else None), "constitutive": constitutive,
+                      "neighbours": len(part.peers),
+                      "fused_operator_exchange_launches": int(eng_lib.sic_mg_fused_exchange_launches())
+                      if hasattr(eng_lib, "sic_mg_fused_exchange_launches") else 0} if world > 1 and xchg_samples else None), "constitutive": constitutive,
         "fp64_peak_tflops_measured": fp64_peak / 1e12,
     }
     if e2e:

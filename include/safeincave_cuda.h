@@ -188,6 +188,13 @@ typedef struct {
   void* comm;              /* from sic_comm_init (NCCL path) */
   void* p2p;               /* from sic_p2p_create/connect, or NULL: if set, halo sums and scalar all-reduces are ONE
                               kernel that stores straight into the peers' mailboxes over NVLink (no NCCL call) */
+  /* fused operator + halo exchange (multigrid V-cycle, needs p2p; NULL / 0: the exchange is a kernel of its own):
+   * the tiles of 128 cells in launch order, those that touch an interface node FIRST.  The operator kernel then carries
+   * n_peers * (blocks per peer) extra CTAs right behind the interface tiles which wait for them, exchange the interface
+   * sums over NVLink and add what arrives while the interior tiles are still being processed. */
+  const int32_t* tile_order;   /* [cell_stride / 128] */
+  int32_t n_iface_tiles;
+  int32_t reserved;
 } sic_halo_t;
 
 /* NCCL communicator over NVLink/NVSwitch (libnccl.so.2 is dlopen'ed on first use; single-GPU runs never touch it).
@@ -375,6 +382,12 @@ int sic_mg_solve(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts
  * captured into a CUDA graph (ksp->use_graph). */
 long long sic_mg_fused_coarse_launches(void);
 long long sic_mg_graph_captures(void);
+
+/* Several GPUs: the compressed operator inside the V-cycle and the halo exchange of its result run as ONE launch
+ * (k_mg_ebe_pc_x) whenever the level's halo plan has P2P mailboxes and a tile order (sic_halo_t.tile_order); this switch
+ * (default on) turns that off for A/B measurements, the counter says how many such launches this process has made. */
+void sic_mg_set_fused_exchange(int on);
+long long sic_mg_fused_exchange_launches(void);
 
 /* z = V-cycle(r) alone (tests, and users who bring their own Krylov method): reads levels[top].b, writes .x */
 int sic_mg_vcycle(sic_mg_level_t* levels, int n_levels, const sic_mg_opts_t* opts, double* work, void* stream);

@@ -35,7 +35,7 @@ EXPORTS = (
     "sic_ksp_solve", "sic_guess_workspace_doubles", "sic_guess_extrapolate", "sic_fp64_peak", "sic_comm_unique_id", "sic_comm_init", "sic_comm_destroy", "sic_halo_sum",
     "sic_allreduce_sum", "sic_p2p_create", "sic_p2p_connect", "sic_p2p_destroy", "sic_p2p_error", "sic_exchange",
     "sic_mg_workspace_doubles", "sic_mg_setup", "sic_mg_solve", "sic_mg_vcycle", "sic_mg_fused_coarse_launches",
-    "sic_mg_graph_captures",
+    "sic_mg_graph_captures", "sic_mg_set_fused_exchange", "sic_mg_fused_exchange_launches",
     "sic_heat_workspace_doubles", "sic_heat_step", "sic_heat_cell_mean", "sic_node_volumes", "sic_pq_fields",
 )
 
@@ -97,7 +97,8 @@ class SicHalo(ctypes.Structure):
     _fields_ = [("n_ranks", c_int32), ("rank", c_int32), ("n_peers", c_int32), ("n_shared_total", c_int32),
                 ("peer", c_int32 * SIC_MAX_PEERS), ("peer_off", c_int32 * (SIC_MAX_PEERS + 1)),
                 ("idx", c_void_p), ("owner_w", c_void_p), ("send_buf", c_void_p), ("recv_buf", c_void_p),
-                ("comm", c_void_p), ("p2p", c_void_p)]
+                ("comm", c_void_p), ("p2p", c_void_p), ("tile_order", c_void_p), ("n_iface_tiles", c_int32),
+                ("reserved", c_int32)]
 
 
 class SicError(RuntimeError):
@@ -135,6 +136,9 @@ def declare(lib, single_gpu_only=False):
     lib.sic_mg_workspace_doubles.restype = c_int64
     lib.sic_mg_fused_coarse_launches.restype = c_int64
     lib.sic_mg_graph_captures.restype = c_int64
+    lib.sic_mg_set_fused_exchange.argtypes = [c_int]
+    lib.sic_mg_set_fused_exchange.restype = None
+    lib.sic_mg_fused_exchange_launches.restype = c_int64
     lib.sic_mg_setup.argtypes = [PL, c_int, PO, c_void_p, c_void_p]
     lib.sic_mg_solve.argtypes = [PL, c_int, PO, POINTER(SicKsp), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sic_mg_vcycle.argtypes = [PL, c_int, PO, c_void_p, c_void_p]

@@ -208,10 +208,11 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
                                                    double* __restrict__ y, TileScratch& sc,
                                                    const int* done_flag = nullptr, const float* __restrict__ pc_ct = nullptr,
                                                    const float* __restrict__ pc_geom = nullptr,
-                                                   const uint16_t* __restrict__ pc_lidx = nullptr, TileGather* xg = nullptr) {
+                                                   const uint16_t* __restrict__ pc_lidx = nullptr, TileGather* xg = nullptr,
+                                                   int tile_of_block = -1) {
   static_assert(!(PC && MODE != 0), "the compressed operator only applies K");
   static_assert(!LIDX || (PC && !XCOH), "the unique-node gather belongs to the compressed operator");
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tile = tile_of_block >= 0 ? tile_of_block : (int)blockIdx.x, tid = threadIdx.x;
   const int i = tile * SIC_TILE_CELLS + tid;
   const size_t ns = (size_t)P.cell_stride;
   // ---- phase 0: every load of the tile is issued up front (asm volatile keeps program order) ----------

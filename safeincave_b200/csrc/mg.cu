@@ -31,6 +31,7 @@
 
 #include "fem.cuh"
 #ifndef SIC_HOSTEMU
+#include "comm.cuh"
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -122,6 +123,59 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc(
   ebe_tile_scatter<0, false, true, false>(P, x, y, sc, done, pc_ct, pc_geom);
 #endif
 }
+
+#ifndef SIC_HOSTEMU
+// Operator + halo exchange in ONE launch (several GPUs, P2P mailboxes).  Launch order: the tiles that touch an interface
+// node (H.tile_order[0 .. n_iface)), then n_peers * bpp COMMUNICATION CTAs, then the interior tiles.  The communication
+// CTAs wait until every interface tile of this launch has scattered its forces, then run the halo exchange of comm.cuh on
+// y -- send the interface sums into the neighbours' mailboxes over NVLink, wait for theirs, add them -- while the interior
+// tiles (which touch no interface node) are still streaming: the exchange latency hides behind them and one launch
+// replaces two.  Everything it synchronises on lives in device memory (comm.cuh: epochs[3] counts these launches,
+// epochs[4] the interface tiles that have finished), so the launch replays from the CUDA graph like the others.
+__global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc_x(sic_problem_t P, const float* __restrict__ pc_ct,
+                                                                 const float* __restrict__ pc_geom, sic_halo_t H, P2P ctx,
+                                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                                 const int* done) {
+  __shared__ TileScratch sc;
+  const int n_iface = H.n_iface_tiles, n_comm = H.n_peers * ctx.bpp, b = (int)blockIdx.x;
+  if (b >= n_iface && b < n_iface + n_comm) {
+    // ---- communication CTA -----------------------------------------------------------------------------------
+    const unsigned long long epoch = ((volatile unsigned long long*)ctx.epochs)[0];
+    const unsigned long long fused = ((volatile unsigned long long*)ctx.epochs)[3];
+    const long long timeout = (*(volatile int*)ctx.error) ? 0ll : SIC_P2P_TIMEOUT_CYCLES;
+    if (threadIdx.x == 0) {
+      const unsigned long long target = (fused + 1ull) * (unsigned long long)n_iface;
+      const long long t0 = clock64();
+      while (((volatile unsigned long long*)ctx.epochs)[4] < target) {
+        if (clock64() - t0 > timeout) { atomicExch(ctx.error, 1); break; }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const int c = b - n_iface;
+    p2p_halo_block(H, ctx, y, 3, c / ctx.bpp, c % ctx.bpp, epoch, timeout);
+    __syncthreads();
+    if (threadIdx.x == 0) {          // the last communication CTA advances the device-side epochs for the next launch
+      const unsigned long long t = atomicAdd(ctx.epochs + 2, 1ull);
+      if (t == (unsigned long long)n_comm - 1ull) {
+        ctx.epochs[2] = 0ull;
+        ctx.epochs[0] = epoch + 1ull;
+        ctx.epochs[3] = fused + 1ull;
+        __threadfence();
+      }
+    }
+    return;
+  }
+  // ---- operator CTA ------------------------------------------------------------------------------------------
+  const int slot = (b < n_iface) ? b : b - n_comm;
+  ebe_tile_scatter<0, false, true, false>(P, x, y, sc, done, pc_ct, pc_geom, nullptr, nullptr, H.tile_order[slot]);
+  if (b < n_iface) {                 // tell the communication CTAs that this interface tile's sums are in y
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(ctx.epochs + 4, 1ull);
+  }
+}
+#endif
 
 // pc_ct = float(sym(W C_T)), W = diag(1,1,1,2,2,2), of one level (once per set-up; both tiled by 128 cells).
 // C_T maps TENSORIAL strains to stresses, so the cell energy is eps^T W C_T eps and the operator K = B^T W C_T B is
@@ -525,9 +579,40 @@ static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_
 
 static inline const sic_halo_t* mg_halo(const sic_mg_level_t& L) { return (L.halo && L.halo->n_ranks > 1) ? L.halo : nullptr; }
 
+// The compressed operator and the halo exchange of its result as ONE launch (k_mg_ebe_pc_x): several GPUs with P2P
+// mailboxes, a tile order in the halo plan, and the option switched on.  Returns false when the caller has to launch the
+// operator and the exchange separately.
+static int g_mg_fuse_exchange = 1;
+extern "C" void sic_mg_set_fused_exchange(int on) { g_mg_fuse_exchange = on ? 1 : 0; }
+static long long g_fused_exchange_launches = 0;
+extern "C" long long sic_mg_fused_exchange_launches(void) { return g_fused_exchange_launches; }
+
+static bool mg_apply_fused(const sic_mg_level_t& L, const double* x, double* t, const int* done, cudaStream_t st) {
+#ifdef SIC_HOSTEMU
+  (void)L; (void)x; (void)t; (void)done; (void)st;
+  return false;
+#else
+  const sic_halo_t* h = mg_halo(L);
+  if (!g_mg_fuse_exchange || !h || !h->p2p || !h->tile_order || !L.pc_ct || h->n_peers <= 0) return false;
+  const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+  if (cb <= 0 || h->n_iface_tiles <= 0 || h->n_iface_tiles > cb) return false;
+  const P2P* c = (const P2P*)h->p2p;
+  int cap_needed = 0;
+  for (int p = 0; p < h->n_peers; ++p) {
+    const int cnt = h->peer_off[p + 1] - h->peer_off[p];
+    if (cnt > cap_needed) cap_needed = cnt;
+  }
+  if (cap_needed > c->cap) return false;
+  k_mg_ebe_pc_x<<<cb + h->n_peers * c->bpp, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, *h, *c, x, t, done);
+  g_fused_exchange_launches += 1;
+  return true;
+#endif
+}
+
 // t = K x on level L (t must be zero on entry); several GPUs: completed on the interface nodes by the halo sum
 static int mg_apply(const sic_mg_level_t& L, const double* x, double* t, const int* done, cudaStream_t st) {
   const int cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
+  if (mg_apply_fused(L, x, t, done, st)) return sic_check_launch("k_mg_ebe_pc_x");
   if (cb > 0) {
     if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.pc_lidx, x, t, done);
     else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, x, t, done);
@@ -657,14 +742,18 @@ static int mg_vcycle(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o, c
     if (int rc = mg_chebyshev(L, b, o->nu, o->smooth_lo, 1, done, st)) return rc;
     const int nn = L.prob.n_nodes, nd = 3 * nn, cb = mg_blocks(L.prob.n_cells, SIC_TILE_CELLS);
     const sic_halo_t* h = mg_halo(L);
-    if (time_top_apply && l == top) cudaEventRecord(time_top_apply[0], st);
-    if (cb > 0) {
-      if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.pc_lidx, L.d, L.t, done);
-      else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+    // (the timed launch keeps the operator and its exchange apart so that each can be bracketed by events)
+    const bool timed = time_top_apply && l == top;
+    if (timed || !mg_apply_fused(L, L.d, L.t, done, st)) {
+      if (timed) cudaEventRecord(time_top_apply[0], st);
+      if (cb > 0) {
+        if (L.pc_ct) k_mg_ebe_pc<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.pc_ct, L.pc_geom, L.pc_lidx, L.d, L.t, done);
+        else k_mg_ebe<<<cb, SIC_TILE_CELLS, 0, st>>>(L.prob, L.d, L.t, done);
+      }
+      if (timed) cudaEventRecord(time_top_apply[1], st);
+      if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
+      if (timed && h) cudaEventRecord(time_top_apply[4], st);   // [1]..[4]: one finest-level halo exchange
     }
-    if (time_top_apply && l == top) cudaEventRecord(time_top_apply[1], st);
-    if (h) if (int rc = sic_exchange(h, L.t, 3, nullptr, 0, (void*)st)) return rc;
-    if (time_top_apply && l == top && h) cudaEventRecord(time_top_apply[4], st);   // [1]..[4]: one finest-level halo exchange
     k_mg_resid<<<mg_blocks(nd, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(nd, L.r, L.t, L.fixed, done);
     // several GPUs: every fine node is restricted by its owner only; the coarse right-hand side is then completed by a
     // halo sum when the coarse level is partitioned too (nested partition: the parents of an owned fine node are

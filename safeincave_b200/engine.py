@@ -337,8 +337,19 @@ class Engine:
         h.idx, h.owner_w, h.send_buf, h.recv_buf = _ptr(idx), _ptr(owner_w), _ptr(send), _ptr(recv)
         h.comm = comm
         h.p2p = p2p
+        tile_order = None
+        if p2p is not None and hasattr(self, "tile_ptr") and total > 0:
+            # launch order of the operator's tiles for the fused operator + exchange kernel: tiles that touch an
+            # interface node first (their sums are what the neighbours wait for), interior tiles after them
+            iface = torch.zeros(max(self.M, 1), dtype=torch.bool, device=dev)
+            iface[idx.long()] = True
+            touches = iface[self.conn.long()].any(dim=0)                       # (ns,) cells with an interface node
+            touches[self.N:] = False
+            tile_touch = touches.reshape(-1, 128).any(dim=1)
+            tile_order = torch.cat([torch.nonzero(tile_touch).flatten(), torch.nonzero(~tile_touch).flatten()]).to(torch.int32).contiguous()
+            h.tile_order, h.n_iface_tiles = _ptr(tile_order), int(tile_touch.sum().item())
         self.halo = h
-        self._halo_keep = (idx, owner_w, send, recv)
+        self._halo_keep = (idx, owner_w, send, recv, tile_order)
         self.owner_w = owner_w
 
     def halo_sum(self, vec, ncomp):

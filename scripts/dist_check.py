@@ -89,7 +89,8 @@ e_s = rel(eq.engine.sig[:, :eq.engine.N], eq1.engine.sig[:, c0:c1])
 e_c = rel(eq.engine.elems[0].eps_old[:, :eq.engine.N], eq1.engine.elems[0].eps_old[:, c0:c1])
 its = [r["iterations"] for r in hist], [r["iterations"] for r in hist1]
 print(f"rank {ctx.rank}/{ctx.world}: cells {eq.engine.N} nodes {eq.engine.M} peers {part.peers} interface {part.n_interface} "
-      f"| pc {a.pc} distributed from level {lc} level cells {level_cells} "
+      f"| pc {a.pc} distributed from level {lc} level cells {level_cells} fused operator+exchange launches "
+      f"{int(eq.engine.lib.sic_mg_fused_exchange_launches())} "
       f"| u err {e_u:.2e} sig err {e_s:.2e} eps_cr err {e_c:.2e} | newton {its} ksp {[r['ksp_iterations'] for r in hist]} "
       f"vs {[r['ksp_iterations'] for r in hist1]}", flush=True)
 assert e_u < a.tol and e_s < a.tol and e_c < a.tol and its[0] == its[1]

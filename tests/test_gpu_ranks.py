@@ -38,6 +38,10 @@ def test_two_ranks_multigrid_bench_settings_nested_partition():
     partitioned by the cells' ancestors, level 0 replicated; fields equal to the single-GPU run of the same settings."""
     out = _torchrun(2, "--levels", "2", "--pc", "mg", "--min-cells-per-rank", "20000", "--rtol", "1e-10")
     assert "distributed from level 1" in out
+    # the V-cycle's operator + halo exchange ran as one launch (k_mg_ebe_pc_x), not as a silent fallback to two
+    import re
+    counts = [int(m) for m in re.findall(r"fused operator\+exchange launches (\d+)", out)]
+    assert counts and min(counts) > 0, out[-2000:]
 
 
 def test_two_ranks_thermomechanical_steps():
