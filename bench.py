@@ -76,7 +76,7 @@ def parse():
                     help="PC mg: replay every Krylov iteration from one captured CUDA graph (sic_ksp_t.use_graph)")
     ap.add_argument("--fused-coarse", type=int, default=1,
                     help="PC mg: the coarsest level's Chebyshev sweep as one cooperative launch (sic_mg_opts_t.fused_coarse)")
-    ap.add_argument("--fused-exchange", type=int, default=1,
+    ap.add_argument("--fused-exchange", type=int, default=0,
                     help="several GPUs, PC mg: the V-cycle's operator and the halo exchange of its result as one launch "
                          "(k_mg_ebe_pc_x: interface tiles first, communication CTAs overlap the interior tiles)")
     ap.add_argument("--compressed", type=int, default=1,

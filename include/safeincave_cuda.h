@@ -384,8 +384,9 @@ long long sic_mg_fused_coarse_launches(void);
 long long sic_mg_graph_captures(void);
 
 /* Several GPUs: the compressed operator inside the V-cycle and the halo exchange of its result run as ONE launch
- * (k_mg_ebe_pc_x) whenever the level's halo plan has P2P mailboxes and a tile order (sic_halo_t.tile_order); this switch
- * (default on) turns that off for A/B measurements, the counter says how many such launches this process has made. */
+ * (k_mg_ebe_pc_x) when this switch is on (default OFF: measured neutral to slower than two launches, csrc/mg.cu) and the
+ * level's halo plan has P2P mailboxes and a tile order (sic_halo_t.tile_order); the counter says how many such launches
+ * this process has made. */
 void sic_mg_set_fused_exchange(int on);
 long long sic_mg_fused_exchange_launches(void);
 

@@ -582,7 +582,12 @@ static inline const sic_halo_t* mg_halo(const sic_mg_level_t& L) { return (L.hal
 // The compressed operator and the halo exchange of its result as ONE launch (k_mg_ebe_pc_x): several GPUs with P2P
 // mailboxes, a tile order in the halo plan, and the option switched on.  Returns false when the caller has to launch the
 // operator and the exchange separately.
-static int g_mg_fuse_exchange = 1;
+// OFF by default: measured on 2 x B200 (profiles/r2_fx*_n2_*.json) it is 1.5 % faster than two launches at 7.35 M cells
+// (13.9 k interface nodes) and 5.6 % SLOWER at 58.8 M (55 k interface nodes: the exchange's gathers, NVLink stores and
+// atomics compete with six streaming operator CTAs per SM, and without a common end of the exchange the ranks drift
+// apart until the next blocking one).  Kept, verified by tests/test_gpu_ranks.py, as the starting point for a version
+// that sends from the interface tiles themselves.
+static int g_mg_fuse_exchange = 0;
 extern "C" void sic_mg_set_fused_exchange(int on) { g_mg_fuse_exchange = on ? 1 : 0; }
 static long long g_fused_exchange_launches = 0;
 extern "C" long long sic_mg_fused_exchange_launches(void) { return g_fused_exchange_launches; }

@@ -28,10 +28,13 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--rtol", type=float, default=1e-12)
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--heat", action="store_true")
+ap.add_argument("--fused-exchange", action="store_true", help="V-cycle operator + halo exchange as one launch (k_mg_ebe_pc_x)")
 a = ap.parse_args()
 
 ctx = distributed.init()
 dev = ctx.device
+from safeincave_b200 import _lib  # noqa: E402
+_lib.load().sic_mg_set_fused_exchange(1 if a.fused_exchange else 0)
 h = refine_hierarchy(TetMesh.load_npz(os.path.join(ROOT, "tests/golden/mesh_cavern_regular.npz")), a.levels, device=dev,
                      nested=True)
 tm = h.finest

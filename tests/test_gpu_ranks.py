@@ -38,6 +38,12 @@ def test_two_ranks_multigrid_bench_settings_nested_partition():
     partitioned by the cells' ancestors, level 0 replicated; fields equal to the single-GPU run of the same settings."""
     out = _torchrun(2, "--levels", "2", "--pc", "mg", "--min-cells-per-rank", "20000", "--rtol", "1e-10")
     assert "distributed from level 1" in out
+
+
+def test_two_ranks_multigrid_fused_operator_exchange():
+    """The same with the opt-in fused launch (k_mg_ebe_pc_x: interface tiles first, communication CTAs overlap the interior
+    tiles): same fields as the single-GPU run, and the fused launch was really used."""
+    out = _torchrun(2, "--levels", "2", "--pc", "mg", "--min-cells-per-rank", "20000", "--rtol", "1e-10", "--fused-exchange")
     # the V-cycle's operator + halo exchange ran as one launch (k_mg_ebe_pc_x), not as a silent fallback to two
     import re
     counts = [int(m) for m in re.findall(r"fused operator\+exchange launches (\d+)", out)]
