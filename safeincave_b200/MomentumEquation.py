@@ -144,6 +144,40 @@ class LinearMomentum(LinearMomentumBase):
         self.engine.T0[:self.engine.N] = to.as_tensor(T0).to(self.engine.device, dtype=to.float64)
         self.T0 = T0
 
+    # ---- results to the host without stalling the time loop --------------------------------------------------------
+    def fields_to_host_async(self, u_host, sig_host):
+        """Displacement (M,3) and stress (6,N) of the step just finished into PINNED host tensors, overlapped with the next
+        time step: one device-side copy of each into staging buffers (the next step overwrites the live ones), then the
+        device-to-host copies on a copy stream of their own.  ``wait_fields()`` blocks until the host tensors are complete;
+        calling this again before that simply queues behind the previous transfer."""
+        eng = self.engine
+        if eng.device.type != "cuda":
+            u_host.copy_(self.X)
+            sig_host.copy_(eng.sig[:, :eng.N])
+            return
+        cur = to.cuda.current_stream(eng.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = to.cuda.Stream(eng.device)
+            self._stage_u = to.empty_like(self.X)
+            self._stage_sig = to.empty((6, eng.N), dtype=to.float64, device=eng.device)
+            self._copy_done = None
+        if self._copy_done is not None:
+            cur.wait_event(self._copy_done)              # the staging buffers are free again (device-side wait)
+        self._stage_u.copy_(self.X)
+        self._stage_sig.copy_(eng.sig[:, :eng.N])
+        staged = to.cuda.Event()
+        staged.record(cur)
+        with to.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(staged)
+            u_host.copy_(self._stage_u, non_blocking=True)
+            sig_host.copy_(self._stage_sig, non_blocking=True)
+            self._copy_done = to.cuda.Event()
+            self._copy_done.record(self._copy_stream)
+
+    def wait_fields(self):
+        if getattr(self, "_copy_done", None) is not None:
+            self._copy_done.synchronize()
+
     def set_solver(self, solver):
         if not hasattr(solver, "method"):
             raise TypeError("set_solver expects safeincave_b200.Solver.KSP (the petsc4py facade)")
