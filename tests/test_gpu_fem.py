@@ -420,7 +420,7 @@ def check_staged_config3(sf, grid_name, n_eq=2, n_op=2, golden=None, tol=1e-8, l
         assert [h["iterations"] for h in h_op] == [h["iters"] for h in oh_op[1:]]
         assert relerr(u_eq, oh_eq[-1]["u"]) < tol
         d_or = osim.mat.elems[-1]
-        assert relerr(alpha_0, d_or.alpha_0) < 1e-10           # hardening initialised on the equilibrium stress
+        assert relerr(alpha_0, d_or.alpha_0) < 1e-9            # hardening initialised on the equilibrium stress (itself <= 1e-8)
         check_fields(eq, osim, oh_op, tol=tol, tol_state=DESAI_STATE_TOL)
         assert relerr(desai_gpu.alpha.numpy(), d_or.alpha) < tol
         assert relerr(desai_gpu.qsi_old.numpy(), d_or.qsi_old) < 1e-6 or np.abs(d_or.qsi_old).max() < 1e-30
@@ -439,7 +439,9 @@ def check_staged_config3(sf, grid_name, n_eq=2, n_op=2, golden=None, tol=1e-8, l
     assert np.abs(sig[sel] - g["sig_sel"]).max() / float(g["sig_absmax"]) < tol
     assert np.abs(eps[sel] - g["eps_sel"]).max() / float(g["eps_absmax"]) < tol
     assert abs(np.linalg.norm(sig) / float(g["sig_norm"]) - 1) < tol
-    assert relerr(alpha_0, g["alpha_0"]) < 1e-10
+    # a smooth function of the equilibrium stress, which is compared at `tol`; observed 0.9e-10 .. 1.6e-10 from one B200 run
+    # to the next (the order of the FP64 atomics in the Krylov solves differs)
+    assert relerr(alpha_0, g["alpha_0"]) < 1e-9
     assert relerr(desai_gpu.alpha.numpy(), g["alpha"]) < tol
     assert abs(int((desai_gpu.Fvp.numpy() > 0).sum()) - int(g["n_yielding"])) <= 2 + int(g["n_yielding"]) // 1000
 
