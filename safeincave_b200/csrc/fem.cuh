@@ -188,6 +188,10 @@ struct TileScratch {                      // shared memory of one operator CTA (
 // instead of 408.  The arithmetic stays FP64 (the vectors are).  A preconditioner only has to approximate K: the
 // non-symmetry of the finite-difference tangent is round-off (1e-6 relative) and float storage perturbs the entries by
 // 6e-8, neither of which moves the Krylov iteration count; the OUTER operator of the solve is always the exact one.
+#ifndef SIC_EBE_GEOM_TILES
+#define SIC_EBE_GEOM_TILES 0      /* 1: the exact tile kernels read the tiled copy of the geometry (sic_problem_t.geom_tiles);
+                                     measured no faster than the SoA rows (4.93 vs 4.78 ms at 58.8 M cells, profiles/r2_ab4_*) */
+#endif
 #ifndef SIC_PC_F32MATH
 #define SIC_PC_F32MATH 1
 #endif
@@ -236,6 +240,12 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
       asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(pc_lidx + a * ns + i));
       node[a] = (int)v;
     }
+  } else if (SIC_EBE_GEOM_TILES && !PC) {
+    // connectivity, gradients and volume of the tile from ONE contiguous 15 KB block (sic_geom_tile_t) instead of 17
+    // rows that lie cell_stride apart: constant offsets, one DRAM page
+    const int* ct_conn = &P.geom_tiles[tile].conn[0][0];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) node[a] = ldg_s32(ct_conn + a * SIC_TILE_CELLS + tid);
   } else {
 #pragma unroll
     for (int a = 0; a < 4; ++a) node[a] = ldg_s32(P.conn + a * ns + i);
@@ -249,9 +259,16 @@ __device__ __forceinline__ double ebe_tile_scatter(const sic_problem_t& P, const
 #pragma unroll
     for (int k = 0; k < SIC_PC_CT_ROWS; ++k) CT[k] = ldg_f32(ct + k * SIC_TILE_CELLS);
   } else {
+    if (SIC_EBE_GEOM_TILES) {
+      const double* gt = &P.geom_tiles[tile].grad[0][0] + tid;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
-    vol = ldg_f64(P.vol + i);
+      for (int k = 0; k < 12; ++k) g[k] = ldg_f64(gt + k * SIC_TILE_CELLS);
+      vol = ldg_f64(gt + 12 * SIC_TILE_CELLS);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) g[k] = ldg_f64(P.grad + k * ns + i);
+      vol = ldg_f64(P.vol + i);
+    }
     const double* ct = P.CT + SIC_CT_INDEX(0, i);
 #pragma unroll
     for (int k = 0; k < 36; ++k) CT[k] = ldg_f64(ct + k * SIC_TILE_CELLS);
