@@ -236,19 +236,22 @@ __global__ void k_mg_zero_free(int nd, double* __restrict__ z, const double* __r
   if (d < nd) z[d] = fixed[d] ? x[d] : 0.0;
 }
 
-// sum a.b over all dofs (w: owner weights on several GPUs, every node counted once; NULL on one); one thread per DOF
+// The two reducing vector kernels of the CG recurrence run a GRID-STRIDE loop on about one wave of blocks
+// (mg_reduce_blocks): with one block per 256 DOFs every block paid the ticket's atomic round trip and two barriers of
+// grid_reduce for a few hundred bytes of work (ncu: k_mg_dot 33 us for 62 MB, "barrier" the top stall).
+// sum a.b over all dofs (w: owner weights on several GPUs, every node counted once; NULL on one)
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_dot(int nd, const double* __restrict__ a,
                                                            const double* __restrict__ b, const double* __restrict__ w,
                                                            MgFin fin, int skip_if_done,
                                                            double* __restrict__ partials, unsigned* counter) {
   if (skip_if_done && fin.S->done) return;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
-  if (k < nd) v[0] = (w ? w[k / 3] : 1.0) * a[k] * b[k];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x)
+    v[0] += (w ? w[k / 3] : 1.0) * a[k] * b[k];
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
 }
 
-// x += alpha p ; r -= alpha q (fixed dofs: r = 0) ; rr = r.r -> convergence test ; one thread per DOF
+// x += alpha p ; r -= alpha q (fixed dofs: r = 0) ; rr = r.r -> convergence test
 __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int nd, double* __restrict__ x,
                                                                  double* __restrict__ r, const double* __restrict__ p,
                                                                  const double* __restrict__ q,
@@ -256,17 +259,16 @@ __global__ void __launch_bounds__(SIC_VEC_THREADS) k_mg_cg_update(int nd, double
                                                                  const double* __restrict__ w, MgFin fin,
                                                                  double* __restrict__ partials, unsigned* counter) {
   if (fin.S->done) return;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const double alpha = fin.S->alpha;
   double v[1] = {0.0};
-  if (k < nd) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) {
     double rn = 0.0;
     if (!fixed[k]) {
       x[k] += alpha * p[k];
       rn = r[k] - alpha * q[k];
     }
     r[k] = rn;
-    v[0] = (w ? w[k / 3] : 1.0) * rn * rn;
+    v[0] += (w ? w[k / 3] : 1.0) * rn * rn;
   }
   grid_reduce<1, SIC_VEC_THREADS>(v, partials, counter, [&](const double* tot) { fin.run(tot[0]); });
 }
@@ -546,6 +548,22 @@ __global__ void k_mg_pw_scale(int nd, double* __restrict__ v, const double* __re
 using namespace sic;
 
 static inline int mg_blocks(int n, int t) { return (n + t - 1) / t; }
+
+// blocks of a reducing grid-stride kernel: one wave of 8 resident 256-thread blocks per SM, or fewer for small vectors
+static int mg_reduce_blocks(int n) {
+  static int wave = 0;
+  if (!wave) {
+    int sms = 8;
+#ifndef SIC_HOSTEMU
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 64;
+#endif
+    wave = 8 * sms;
+  }
+  const int b = mg_blocks(n, SIC_VEC_THREADS);
+  return b < wave ? (b > 0 ? b : 1) : wave;
+}
 
 static int mg_check_levels(const sic_mg_level_t* lv, int n_levels, const sic_mg_opts_t* o) {
   if (!lv || !o) return sic_fail("multigrid: null argument");
@@ -1005,6 +1023,8 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     if (int rc = sic_check_cuda(cudaMemsetAsync(lv[l].t, 0, sizeof(double) * 3 * lv[l].prob.n_nodes, st), "memset t"))
       return rc;
   const int nb = mg_blocks(nn, SIC_VEC_THREADS), db = mg_blocks(nd, SIC_VEC_THREADS), cb = mg_blocks(nc, SIC_TILE_CELLS);
+  const int rb = mg_reduce_blocks(nd);
+  (void)nb;
   const int check = ksp->check_every > 0 ? ksp->check_every : 4;
   const int guess = ksp->guess_nonzero ? 1 : 0;
   const double rtol = ksp->rtol, atol = ksp->atol;
@@ -1035,16 +1055,16 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
   if (guess) {   // reference norm of rtol: the residual of the zero guess (prescribed values only), as PETSc's ||b||
     k_mg_zero_free<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, x, fixed);
     if (int rc = sic_residual0(p, b_ext, pp, r, fixed, halo, stream)) return rc;
-    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_REF), 0, W.partials, W.counter);
+    k_mg_dot<<<rb, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_REF), 0, W.partials, W.counter);
     if (int rc = reduce(MG_OP_REF, nullptr, 0)) return rc;
   }
   if (int rc = sic_residual0(p, b_ext, x, r, fixed, halo, stream)) return rc;
-  k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
+  k_mg_dot<<<rb, SIC_VEC_THREADS, 0, st>>>(nd, r, r, ow, fin(MG_OP_INIT_RR), 0, W.partials, W.counter);
   if (int rc = reduce(MG_OP_INIT_RR, nullptr, 0)) return rc;
   // first cycle of the solve: z = M^-1 r0, rz = r0.z, p = z ; q = 0 (its own graph when use_graph, below)
   auto first_cycle = [&](cudaEvent_t*) -> int {
     if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, nullptr)) return rc;
-    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
+    k_mg_dot<<<rb, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_INIT_RZ), 1, W.partials, W.counter);
     if (int rc = reduce(MG_OP_INIT_RZ, nullptr, 1)) return rc;
     k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 1);
     return 0;
@@ -1059,10 +1079,10 @@ extern "C" int sic_mg_solve(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     if (time_ev) cudaEventRecord(time_ev[3], st);
     k_mg_sum_pq<<<1, 1024, 0, st>>>(W.partials, cb, fin(MG_OP_PQ));
     if (int rc = reduce(MG_OP_PQ, q, 1)) return rc;
-    k_mg_cg_update<<<db, SIC_VEC_THREADS, 0, st>>>(nd, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
+    k_mg_cg_update<<<rb, SIC_VEC_THREADS, 0, st>>>(nd, x, r, pp, q, fixed, ow, fin(MG_OP_RR), W.partials, W.counter);
     if (int rc = reduce(MG_OP_RR, nullptr, 1)) return rc;
     if (int rc = mg_vcycle(lv, n_levels, o, r, &S->done, st, time_ev)) return rc;
-    k_mg_dot<<<db, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
+    k_mg_dot<<<rb, SIC_VEC_THREADS, 0, st>>>(nd, r, z, ow, fin(MG_OP_RZ), 1, W.partials, W.counter);
     if (int rc = reduce(MG_OP_RZ, nullptr, 1)) return rc;
     k_mg_cg_p<<<db, SIC_VEC_THREADS, 0, st>>>(nd, pp, z, q, fixed, S, 0);
     return 0;
