@@ -61,3 +61,22 @@ def test_fields_and_units(tmp_path):
     p = tmp_path / "a.json"
     ut.save_json({"k": [1, 2.5]}, str(p))
     assert ut.read_json(str(p)) == {"k": [1, 2.5]}
+
+
+def test_case_parameters_per_region():
+    """cases.per_cell: a number is uniform, a {region: value} dict is resolved through the mesh's cell tags (the salt /
+    overburden materials of BASELINE config 4, cases.overburden_tm_case)."""
+    import os
+    import numpy as np
+    from safeincave_b200 import cases
+    from safeincave_b200.mesh import TetMesh
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    tm = TetMesh.load_npz(os.path.join(gold, "mesh_cavern_overburden_coarse.npz"))
+    assert (cases.per_cell(2.5, tm) == 2.5).all()
+    rho = cases.per_cell({"Salt": 2200.0, "Overburden": 2800.0}, tm)
+    salt = tm.cell_tags == tm.names[3]["Salt"]
+    assert (rho[salt] == 2200.0).all() and (rho[~salt] == 2800.0).all() and 0 < salt.sum() < tm.n_cells
+    import safeincave_b200 as sf
+    case = cases.overburden_tm_case(sf.GridHandlerGMSH.from_mesh(tm), n_steps=2)
+    assert len(case["dirichlet"]) == 9 and {d["boundary"] for d in case["dirichlet"]} >= {"West_salt", "East_ovb", "Bottom"}
+    assert case["thermal"]["robin"][0]["boundary"] == "Cavern" and case["thermo_alpha"]["Overburden"] == 0.0
