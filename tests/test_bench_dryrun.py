@@ -117,7 +117,9 @@ def test_reference_arm_line(dry, capsys, monkeypatch):
     assert line["impl"] == "reference" and line["metric"] == "cell_updates_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["n_cells"] == 384 and line["cpu_baseline_unrefined_lu"]["cores"] == 1
+    # the line names the GPU arm's workload (default --levels 4) and says which member of the family the sample was
+    assert line["config"]["n_cells"] == 14346 * 8 ** 4 and "x8^4" in line["config"]["workload"]
+    assert line["config"]["sample_n_cells"] == 384 and line["cpu_baseline_unrefined_lu"]["cores"] == 1
 
 
 def test_bench_line_block_jacobi(dry, capsys):
