@@ -344,6 +344,7 @@ typedef struct {
   float* pc_ct;            /* [cell_stride/128][21][128] filled by sic_mg_setup from prob.CT */
   const float* pc_geom;    /* [cell_stride/128][13][128] rows 0-11 = prob.grad, row 12 = prob.vol, tiled by 128 cells like
                               pc_ct (filled by the caller) */
+  float* pc_dinv;          /* [9 n_nodes] or NULL: float copy of dinv, filled by sic_mg_setup, read by the smoother kernels */
   const uint16_t* pc_lidx; /* [4][cell_stride] position of each cell node in its tile's list of unique nodes
                               (prob.tile_nodes from prob.tile_ptr[tile] on): x is gathered once per unique node of a tile
                               into shared memory, the connectivity is not read (filled by the caller) */

@@ -74,7 +74,7 @@ class SicMgLevel(ctypes.Structure):
                 ("parent_a", c_void_p), ("parent_b", c_void_p), ("rst_ptr", c_void_p), ("rst_idx", c_void_p),
                 ("children", c_void_p),
                 ("x", c_void_p), ("b", c_void_p), ("r", c_void_p), ("d", c_void_p), ("t", c_void_p), ("pv", c_void_p),
-                ("pc_ct", c_void_p), ("pc_geom", c_void_p), ("pc_lidx", c_void_p), ("halo", c_void_p)]
+                ("pc_ct", c_void_p), ("pc_geom", c_void_p), ("pc_dinv", c_void_p), ("pc_lidx", c_void_p), ("halo", c_void_p)]
 
 
 class SicMgOpts(ctypes.Structure):

@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_PC_MINBLOCKS) k_mg_ebe_pc_
 }
 #endif
 
+__global__ void k_mg_to_float(int n, const double* __restrict__ a, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (float)a[k];
+}
+
 // pc_ct = float(sym(W C_T)), W = diag(1,1,1,2,2,2), of one level (once per set-up; both tiled by 128 cells).
 // C_T maps TENSORIAL strains to stresses, so the cell energy is eps^T W C_T eps and the operator K = B^T W C_T B is
 // symmetric iff W C_T is (C_T itself is not: for the creep tangents C_T[normal][shear] = 2 C_T[shear][normal], the
@@ -315,10 +320,13 @@ __device__ __forceinline__ void mg_cheb_first_node(int n, const double* __restri
 // through shared memory.  SIC_DOF_THREADS is a multiple of 3, so a node never straddles two blocks.  Same expressions,
 // in the same order, as the per-node functions the fused coarsest-level kernel uses.
 #define SIC_DOF_THREADS 192
+// DT: the blocks are read as doubles (exact preconditioner) or from the float copy sic_mg_setup keeps for the compressed
+// one (pc_dinv: 12 instead of 24 of a step's 89 bytes per DOF)
+template <class DT>
 __global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_first(int nd, const double* __restrict__ b,
                                                                   double* __restrict__ r, double* __restrict__ d,
                                                                   double* __restrict__ x, double* __restrict__ t,
-                                                                  const double* __restrict__ dinv,
+                                                                  const DT* __restrict__ dinv,
                                                                   const uint8_t* __restrict__ fixed, double inv_theta,
                                                                   int zero_guess, const int* done) {
   if (*done) return;
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_first(int nd, const
     fx = fixed[k] != 0;
     v = zero_guess ? b[k] : b[k] - t[k];
     if (fx) v = 0.0;
-    d0 = __ldg(dinv + 3 * (size_t)k); d1 = __ldg(dinv + 3 * (size_t)k + 1); d2 = __ldg(dinv + 3 * (size_t)k + 2);
+    d0 = (double)__ldg(dinv + 3 * (size_t)k); d1 = (double)__ldg(dinv + 3 * (size_t)k + 1); d2 = (double)__ldg(dinv + 3 * (size_t)k + 2);
     if (!zero_guess) xk = x[k];
     r[k] = v;
     t[k] = 0.0;
@@ -371,9 +379,10 @@ __device__ __forceinline__ void mg_cheb_step_node(int n, double* r, double* d, d
     x[k] += dn;
   }
 }
+template <class DT>
 __global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_step(int nd, double* __restrict__ r,
                                                                  double* __restrict__ d, double* __restrict__ x,
-                                                                 double* __restrict__ t, const double* __restrict__ dinv,
+                                                                 double* __restrict__ t, const DT* __restrict__ dinv,
                                                                  const uint8_t* __restrict__ fixed, double a, double c,
                                                                  const int* done) {
   if (*done) return;
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(SIC_DOF_THREADS) k_mg_cheb_step(int nd, double
   if (in) {
     fx = fixed[k] != 0;
     v = fx ? 0.0 : r[k] - t[k];
-    d0 = __ldg(dinv + 3 * (size_t)k); d1 = __ldg(dinv + 3 * (size_t)k + 1); d2 = __ldg(dinv + 3 * (size_t)k + 2);
+    d0 = (double)__ldg(dinv + 3 * (size_t)k); d1 = (double)__ldg(dinv + 3 * (size_t)k + 1); d2 = (double)__ldg(dinv + 3 * (size_t)k + 2);
     dk = d[k];
     xk = x[k];
     r[k] = v;
@@ -681,13 +690,21 @@ static int mg_chebyshev(const sic_mg_level_t& L, const double* b, int its, doubl
   double rho = 1.0 / sigma;
   if (!zero_guess)
     if (int rc = mg_apply(L, L.x, L.t, done, st)) return rc;                         // t = K x (t is 0 on entry)
-  k_mg_cheb_first<<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta, zero_guess,
-                                                  done);
+  if (L.pc_dinv)
+    k_mg_cheb_first<float><<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, b, L.r, L.d, L.x, L.t, L.pc_dinv, L.fixed, 1.0 / theta,
+                                                           zero_guess, done);
+  else
+    k_mg_cheb_first<double><<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, b, L.r, L.d, L.x, L.t, L.dinv, L.fixed, 1.0 / theta,
+                                                            zero_guess, done);
   for (int k = 1; k < its; ++k) {
     if (int rc = mg_apply(L, L.d, L.t, done, st)) return rc;
     const double rho_new = 1.0 / (2.0 * sigma - rho);
-    k_mg_cheb_step<<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
-                                                   2.0 * rho_new / delta, done);
+    if (L.pc_dinv)
+      k_mg_cheb_step<float><<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, L.r, L.d, L.x, L.t, L.pc_dinv, L.fixed, rho_new * rho,
+                                                            2.0 * rho_new / delta, done);
+    else
+      k_mg_cheb_step<double><<<nb, SIC_DOF_THREADS, 0, st>>>(3 * nn, L.r, L.d, L.x, L.t, L.dinv, L.fixed, rho_new * rho,
+                                                             2.0 * rho_new / delta, done);
     rho = rho_new;
   }
   return sic_check_launch("multigrid: Chebyshev sweep");
@@ -841,6 +858,10 @@ extern "C" int sic_mg_setup(sic_mg_level_t* lv, int n_levels, const sic_mg_opts_
     const int multi = h ? 1 : 0;
     const double* ow = h ? h->owner_w : nullptr;
     if (int rc = sic_block_jacobi(&L.prob, L.dinv, L.fixed, h, stream)) return rc;
+    if (L.pc_dinv && L.prob.n_nodes > 0) {
+      const int n9 = 9 * L.prob.n_nodes;
+      k_mg_to_float<<<mg_blocks(n9, SIC_VEC_THREADS), SIC_VEC_THREADS, 0, st>>>(n9, L.dinv, L.pc_dinv);
+    }
     if (o->power_its <= 0) {
       if (!(L.lambda_max > 0.0)) return sic_fail("sic_mg_setup: power_its = 0 needs lambda_max from an earlier call");
       continue;

@@ -265,8 +265,9 @@ class Multigrid:
                 pc_geom = torch.cat([eng.grad.to(torch.float32), eng.vol.to(torch.float32).reshape(1, -1)])
                 pc_geom = pc_geom.reshape(13, eng.ns // 128, 128).permute(1, 0, 2).contiguous()      # [tile][13][128]
                 pc_ct = torch.zeros((eng.ns // 128, 21, 128), dtype=torch.float32, device=dev)
-                self.vec[l]["pc_geom"], self.vec[l]["pc_ct"] = pc_geom, pc_ct
-                lv.pc_ct, lv.pc_geom, lv.pc_lidx = _ptr(pc_ct), _ptr(pc_geom), _ptr(eng.lidx)
+                pc_dinv = torch.zeros(9 * max(eng.M, 1), dtype=torch.float32, device=dev)
+                self.vec[l]["pc_geom"], self.vec[l]["pc_ct"], self.vec[l]["pc_dinv"] = pc_geom, pc_ct, pc_dinv
+                lv.pc_ct, lv.pc_geom, lv.pc_lidx, lv.pc_dinv = _ptr(pc_ct), _ptr(pc_geom), _ptr(eng.lidx), _ptr(pc_dinv)
         self.compressed = bool(compressed)
         need = int(self.lib.sic_mg_workspace_doubles(fine_engine.N, fine_engine.M))
         self.work = zeros(need)
