@@ -51,7 +51,6 @@ __global__ void k_add_mask(int n, double* __restrict__ r, const double* __restri
 __global__ void __launch_bounds__(SIC_EBE_THREADS) k_diag_blocks(sic_problem_t P, double* __restrict__ dblk) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_cells) return;
-  const int ns = P.cell_stride;
   CellGeom c;
   load_geom(P, i, c);
   double CT[36];

@@ -50,7 +50,6 @@ __device__ __forceinline__ void strain_from_nodal(const CellGeom& c, const doubl
 
 // sigma = C_T eps with C_T streamed from its SoA rows
 __device__ __forceinline__ void stress_from_CT(const sic_problem_t& P, int i, const double eps[6], double sig[6]) {
-  const int ns = P.cell_stride;
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     double s = 0.0;
