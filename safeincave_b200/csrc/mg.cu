@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(128) k_mg_ct_compress(int n_cells, const doubl
 }
 
 // q = K p with the per-cell energies p.Kp summed per block (finished by k_mg_sum_pq)
-__global__ void __launch_bounds__(SIC_TILE_CELLS, 3) k_mg_ebe_dot(sic_problem_t P, const double* __restrict__ x,
+#ifndef SIC_EBE_DOT_MINBLOCKS
+#define SIC_EBE_DOT_MINBLOCKS 3      /* 4 (128 registers, 64 bytes of spills) measured the same: 4.825 vs 4.834 ms at 58.8 M cells */
+#endif
+__global__ void __launch_bounds__(SIC_TILE_CELLS, SIC_EBE_DOT_MINBLOCKS) k_mg_ebe_dot(sic_problem_t P, const double* __restrict__ x,
                                                                 double* __restrict__ y, double* __restrict__ partials,
                                                                 const int* done) {
   __shared__ TileScratch sc;

@@ -20,6 +20,7 @@ VARIANTS = {
     "pc_mb4": ["-DSIC_PC_MINBLOCKS=4"],
     "pc_mb5": ["-DSIC_PC_MINBLOCKS=5"],
     "pc_mb7": ["-DSIC_PC_MINBLOCKS=7"],
+    "ebedot_mb4": ["-DSIC_EBE_DOT_MINBLOCKS=4"],     # exact Krylov operator compiled for 4 resident CTAs per SM
     "geom_soa": ["-DSIC_EBE_GEOM_TILES=0"],          # exact tile kernels read conn / grad / vol from the SoA rows
     "pcmath_f64": ["-DSIC_PC_F32MATH=0"],           # stress / forces / staging of k_mg_ebe_pc in FP64 (the default is FP32)
     "pcmath_f32_mb7": ["-DSIC_PC_F32MATH=1", "-DSIC_PC_MINBLOCKS=7"],
