@@ -463,3 +463,28 @@ def test_staged_config3_cavern_irregular_finemesh(sf):
     """The same on the grid BASELINE configs[2] names (91 896 cells), against the oracle's committed output
     (tests/golden/staged_cfg3_cavern_irregular_finemesh.npz; the oracle's sparse LU needs minutes on this grid)."""
     check_staged_config3(sf, "cavern_irregular_finemesh", golden="staged_cfg3_cavern_irregular_finemesh.npz")
+
+
+def test_fields_to_host_async_overlaps_and_delivers(sf):
+    """LinearMomentum.fields_to_host_async / wait_fields (what bench.py's e2e leg uses): the results of step n reach the
+    pinned host tensors intact although step n+1 has already overwritten the live device fields."""
+    import torch
+    from safeincave_b200 import cases
+    grid = load_grid(sf, "cavern_regular")
+    case = cases.cavern_case(grid, n_steps=3, ksp_type="cg", rtol=1e-10)
+    eq, sim = cases.build(case, grid)
+    sim.verbose = False
+    sim.initialize()
+    eng = eq.engine
+    u_host = torch.empty((eng.M, 3), dtype=torch.float64).pin_memory()
+    sig_host = torch.empty((6, eng.N), dtype=torch.float64).pin_memory()
+    sim.step()
+    u1, s1 = eq.X.clone(), eng.sig[:, :eng.N].clone()
+    eq.fields_to_host_async(u_host, sig_host)
+    sim.step()                                   # overwrites eq.X / eng.sig while the copy may still be in flight
+    eq.wait_fields()
+    assert torch.equal(u_host, u1.cpu().reshape(eng.M, 3)) and torch.equal(sig_host, s1.cpu())
+    assert not torch.equal(eq.X.cpu().reshape(eng.M, 3), u_host)          # the second step did move the fields
+    eq.fields_to_host_async(u_host, sig_host)    # queues behind nothing; a second call reuses the staging buffers
+    eq.wait_fields()
+    assert torch.equal(u_host, eq.X.cpu().reshape(eng.M, 3))
